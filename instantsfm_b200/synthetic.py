@@ -1,0 +1,269 @@
+"""Seeded synthetic BA / GP problems shaped like the BASELINE.json configs.
+
+Everything is vectorised numpy so that the 5 M- and 60 M-observation configs are
+generated in seconds to a minute on the host.  Geometry: cameras orbit a point cloud on a
+closed loop looking inward (depth ~15..45), point ``p`` is observed by ``k_p`` distinct
+cameras drawn from a window of ``window`` consecutive loop positions around a random
+anchor, so camera pairs further apart than ``window`` share no point and the reduced
+camera system S is banded; ``window >= n_cam`` gives the dense S of the BAL sets.
+Track length ``k_p = 2 + Geometric`` (cap 200) trimmed so that the totals hit the
+requested n_obs exactly.  Observations come out sorted by point, as the reference's
+flattening loop produces them (bundle_adjustment.py:88-96).
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .geometry import quat_mul, quat_to_mat, rotvec_to_quat, matrices_to_pose7
+
+# number of intrinsics once the principal point is removed, per CameraModelId.value
+N_INTR = {0: 1, 1: 2, 2: 2, 3: 3, 4: 6, 5: 6, 6: 10, 8: 2, 9: 3}
+N_FOCAL = {0: 1, 1: 2, 2: 1, 3: 1, 4: 2, 5: 2, 6: 2, 8: 1, 9: 1}
+
+CONFIGS = {
+    # name: (n_cam, n_pt, n_obs, window, seed)
+    "C1": (64, 10_000, 60_000, 64, 1001),
+    "C2": (1_723, 156_000, 678_000, 1_723, 1002),
+    "C3": (1_778, 993_000, 5_000_000, 1_778, 1003),
+    "C5": (20_000, 10_000_000, 60_000_000, 256, 1005),
+}
+GP_CONFIGS = {"C4": (2_500, 500_000, 3_000_000, 2_500, 1004)}
+
+
+@dataclass
+class BAArrays:
+    """Flat BA problem in the compacted index space of bundle_adjustment.py:108-113."""
+    model_id: int
+    camera_params: np.ndarray      # [Nc, 7 + n_intr] = [t, q_xyzw, intrinsics without pp]
+    camera_pps: np.ndarray         # [Nc, 2]
+    points_3d: np.ndarray          # [Np, 3]
+    points_2d: np.ndarray          # [N, 2]
+    camera_indices: np.ndarray     # int32 [N]
+    point_indices: np.ndarray      # int32 [N], non-decreasing
+    gt_camera_params: np.ndarray = field(default=None, repr=False)
+    gt_points_3d: np.ndarray = field(default=None, repr=False)
+
+    @property
+    def n_cam(self):
+        return self.camera_params.shape[0]
+
+    @property
+    def n_pt(self):
+        return self.points_3d.shape[0]
+
+    @property
+    def n_obs(self):
+        return self.points_2d.shape[0]
+
+
+def distort_numpy(model_id, u, k):
+    """Distortion * focal for the nine implemented models (cost_function.py:32-177)."""
+    r2 = (u * u).sum(-1, keepdims=True)
+
+    def fisheye(u):
+        r = np.sqrt(r2)
+        return u * np.arctan(r) / r
+
+    def tangential(p):
+        uv = u[:, :1] * u[:, 1:2]
+        return 2 * p * uv + p[:, ::-1] * (r2 + 2 * u * u)
+
+    if model_id == 0:
+        return u * k[:, 0:1]
+    if model_id == 1:
+        return u * k[:, 0:2]
+    if model_id == 2:
+        return u * (1 + k[:, 1:2] * r2) * k[:, 0:1]
+    if model_id == 3:
+        return u * (1 + k[:, 1:2] * r2 + k[:, 2:3] * r2 ** 2) * k[:, 0:1]
+    if model_id == 4:
+        return (u + u * (k[:, 2:3] * r2 + k[:, 3:4] * r2 ** 2) + tangential(k[:, 4:6])) * k[:, 0:2]
+    if model_id == 5:
+        return fisheye(u) * (1 + k[:, 2:3] * r2 + k[:, 3:4] * r2 ** 2 + k[:, 4:5] * r2 ** 3) * k[:, 0:2]
+    if model_id == 6:
+        rad = (1 + k[:, 2:3] * r2 + k[:, 3:4] * r2 ** 2 + k[:, 6:7] * r2 ** 3) / \
+              (1 + k[:, 7:8] * r2 + k[:, 8:9] * r2 ** 2 + k[:, 9:10] * r2 ** 3) - 1
+        return (u + u * rad + tangential(k[:, 4:6])) * k[:, 0:2]
+    if model_id == 8:
+        return fisheye(u) * (1 + k[:, 1:2] * r2) * k[:, 0:1]
+    if model_id == 9:
+        return fisheye(u) * (1 + k[:, 1:2] * r2 + k[:, 2:3] * r2 ** 2) * k[:, 0:1]
+    raise NotImplementedError("Unsupported camera model")
+
+
+def project_numpy(model_id, X, cam, pp, chunk=4_000_000):
+    """Row-wise projection of X[N,3] with camera rows cam[N,7+ni], pp[N,2]; chunked."""
+    out = np.empty((X.shape[0], 2))
+    depth = np.empty(X.shape[0])
+    for s in range(0, X.shape[0], chunk):
+        e = min(s + chunk, X.shape[0])
+        R = quat_to_mat(cam[s:e, 3:7])
+        y = np.einsum("nij,nj->ni", R, X[s:e]) + cam[s:e, :3]
+        u = y[:, :2] / y[:, 2:3]
+        out[s:e] = distort_numpy(model_id, u, cam[s:e, 7:]) + pp[s:e]
+        depth[s:e] = y[:, 2]
+    return out, depth
+
+
+def _prev_prime(n):
+    def is_p(m):
+        if m < 2:
+            return False
+        i = 2
+        while i * i <= m:
+            if m % i == 0:
+                return False
+            i += 1
+        return True
+    while not is_p(n):
+        n -= 1
+    return n
+
+
+def _track_lengths(rng, n_pt, n_obs, kmax, kmin=2):
+    mean_extra = n_obs / n_pt - kmin
+    assert mean_extra >= 0, "too few observations per point"
+    assert n_obs <= n_pt * kmax, "too many observations per point for this window"
+    if mean_extra == 0:
+        return np.full(n_pt, kmin, dtype=np.int64)
+    p = 1.0 / (1.0 + mean_extra)
+    k = kmin + (rng.geometric(p, size=n_pt) - 1)
+    k = np.minimum(k, kmax).astype(np.int64)
+    diff = int(n_obs - k.sum())
+    while diff != 0:
+        if diff > 0:
+            cand = np.flatnonzero(k < kmax)
+            pick = rng.choice(cand, size=min(diff, cand.size), replace=False)
+            k[pick] += 1
+        else:
+            cand = np.flatnonzero(k > kmin)
+            pick = rng.choice(cand, size=min(-diff, cand.size), replace=False)
+            k[pick] -= 1
+        diff = int(n_obs - k.sum())
+    return k
+
+
+def _orbit_cameras(rng, n_cam, radius=30.0):
+    ang = 2 * np.pi * np.arange(n_cam) / n_cam
+    C = np.stack([radius * np.cos(ang), radius * np.sin(ang), rng.uniform(-3, 3, n_cam)], 1)
+    C[:, :2] *= rng.uniform(0.9, 1.1, (n_cam, 1))
+    target = rng.normal(scale=1.5, size=(n_cam, 3))
+    z = target - C
+    z /= np.linalg.norm(z, axis=1, keepdims=True)
+    up = np.array([0.0, 0.0, 1.0])
+    x = np.cross(z, up)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    y = np.cross(z, x)
+    R = np.stack([x, y, z], axis=1)                    # rows = camera axes in world coords
+    M = np.zeros((n_cam, 4, 4))
+    M[:, :3, :3] = R
+    M[:, :3, 3] = -np.einsum("nij,nj->ni", R, C)
+    M[:, 3, 3] = 1
+    return matrices_to_pose7(M), C
+
+
+def _visibility(rng, n_cam, n_pt, n_obs, window, kmin=2):
+    """Sorted-by-point observation lists: camera_indices, point_indices (int32).
+
+    Slots inside the window are visited with a per-point stride modulo a prime W, so the
+    k_p cameras of a point are distinct."""
+    W = _prev_prime(min(window, n_cam))
+    k = _track_lengths(rng, n_pt, n_obs, min(200, W), kmin)
+    stride = rng.integers(1, W, size=n_pt) if W > 2 else np.ones(n_pt, dtype=np.int64)
+    anchor = rng.integers(0, n_cam, size=n_pt)
+    start = rng.integers(0, W, size=n_pt)
+    pt = np.repeat(np.arange(n_pt, dtype=np.int64), k)
+    offs = np.cumsum(k) - k
+    j = np.arange(pt.shape[0], dtype=np.int64) - offs[pt]
+    slot = (start[pt] + j * stride[pt]) % W
+    cam = (anchor[pt] + slot - W // 2) % n_cam
+    return cam.astype(np.int32), pt.astype(np.int32)
+
+
+def make_ba_problem(n_cam, n_pt, n_obs, window=None, seed=0, model_id=3, noise_px=0.5,
+                    outlier_frac=0.01, perturb=1.0):
+    """Build a BAL-shaped problem; ``perturb`` scales the initial-state perturbation."""
+    rng = np.random.default_rng(seed)
+    window = n_cam if window is None else window
+    pose_gt, _ = _orbit_cameras(rng, n_cam)
+    ni, nf = N_INTR[model_id], N_FOCAL[model_id]
+    intr_gt = np.empty((n_cam, ni))
+    intr_gt[:, :nf] = rng.uniform(800, 1200, (n_cam, 1))
+    if ni > nf:
+        scales = np.array([1e-2, 1e-3] + [1e-4] * 8)[: ni - nf]
+        intr_gt[:, nf:] = rng.normal(size=(n_cam, ni - nf)) * scales
+    cam_gt = np.concatenate([pose_gt, intr_gt], 1)
+    pps = np.zeros((n_cam, 2))                          # BAL convention
+    # points in a ball of radius 10 around the origin
+    X = rng.normal(size=(n_pt, 3))
+    X *= (10.0 * rng.uniform(0, 1, (n_pt, 1)) ** (1 / 3)) / np.linalg.norm(X, axis=1, keepdims=True)
+    ci, pi = _visibility(rng, n_cam, n_pt, n_obs, window)
+    obs, depth = project_numpy(model_id, X[pi], cam_gt[ci], pps[ci])
+    assert depth.min() > 0.1
+    obs += rng.normal(scale=noise_px, size=obs.shape)
+    n_out = int(outlier_frac * obs.shape[0])
+    if n_out:
+        which = rng.choice(obs.shape[0], size=n_out, replace=False)
+        obs[which] += rng.uniform(-20, 20, size=(n_out, 2))
+    # perturbed initial state: rotation 0.5 deg rms, translation 1 % of scene scale (30),
+    # points 2 % of depth, focal 1 %
+    cam0 = cam_gt.copy()
+    dq = rotvec_to_quat(rng.normal(scale=perturb * np.deg2rad(0.5) / np.sqrt(3), size=(n_cam, 3)))
+    cam0[:, 3:7] = quat_mul(dq, cam_gt[:, 3:7])
+    cam0[:, :3] += rng.normal(scale=perturb * 0.3 / np.sqrt(3), size=(n_cam, 3))
+    cam0[:, 7:7 + nf] *= 1 + rng.normal(scale=perturb * 0.01, size=(n_cam, nf))
+    X0 = X + rng.normal(scale=perturb * 0.6 / np.sqrt(3), size=X.shape)
+    return BAArrays(model_id, cam0, pps, X0, obs, ci, pi, cam_gt, X)
+
+
+def make_config(name, scale=1.0, model_id=3):
+    """BASELINE.json config by name ('C1','C2','C3','C5'); ``scale`` < 1 shrinks points/obs."""
+    n_cam, n_pt, n_obs, window, seed = CONFIGS[name]
+    if scale != 1.0:
+        n_pt = max(int(n_pt * scale), 16)
+        n_obs = max(int(n_obs * scale), 2 * n_pt)
+    return make_ba_problem(n_cam, n_pt, n_obs, window, seed, model_id)
+
+
+@dataclass
+class GPArrays:
+    """Flat global-positioning problem (global_positioning.py:101-152)."""
+    camera_translations: np.ndarray   # [Nc, 3] camera centres (initial)
+    points_3d: np.ndarray             # [Np, 3] (initial)
+    translations: np.ndarray          # [N, 3] world-frame unit rays
+    camera_indices: np.ndarray        # int32 [N]
+    point_indices: np.ndarray         # int32 [N]
+    is_calibrated: np.ndarray         # bool [Nc]
+    scales: np.ndarray                # [N, 1]
+    gt_centres: np.ndarray = field(default=None, repr=False)
+    gt_points_3d: np.ndarray = field(default=None, repr=False)
+
+
+def make_gp_problem(n_cam, n_pt, n_obs, window=None, seed=0, ray_noise_deg=0.2, outlier_frac=0.02):
+    rng = np.random.default_rng(seed)
+    window = n_cam if window is None else window
+    _, C = _orbit_cameras(rng, n_cam)
+    X = rng.normal(size=(n_pt, 3))
+    X *= (10.0 * rng.uniform(0, 1, (n_pt, 1)) ** (1 / 3)) / np.linalg.norm(X, axis=1, keepdims=True)
+    ci, pi = _visibility(rng, n_cam, n_pt, n_obs, window, kmin=3)
+    d = X[pi] - C[ci]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    dq = rotvec_to_quat(rng.normal(scale=np.deg2rad(ray_noise_deg) / np.sqrt(3), size=d.shape))
+    d = np.einsum("nij,nj->ni", quat_to_mat(dq), d)
+    n_out = int(outlier_frac * d.shape[0])
+    if n_out:
+        which = rng.choice(d.shape[0], size=n_out, replace=False)
+        o = rng.normal(size=(n_out, 3))
+        d[which] = o / np.linalg.norm(o, axis=1, keepdims=True)
+    cal = rng.uniform(size=n_cam) < 0.9
+    c0 = 100.0 * rng.uniform(-1, 1, (n_cam, 3))       # global_positioning.py:31-35, seeded here
+    X0 = 100.0 * rng.uniform(-1, 1, (n_pt, 3))
+    return GPArrays(c0, X0, d, ci, pi, cal, np.ones((d.shape[0], 1)), C, X)
+
+
+def make_gp_config(name="C4", scale=1.0):
+    n_cam, n_pt, n_obs, window, seed = GP_CONFIGS[name]
+    if scale != 1.0:
+        n_pt = max(int(n_pt * scale), 16)
+        n_obs = max(int(n_obs * scale), 3 * n_pt)
+    return make_gp_problem(n_cam, n_pt, n_obs, window, seed)

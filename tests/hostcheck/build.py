@@ -1,0 +1,16 @@
+"""Builds tests/hostcheck/libhostcheck.so (g++ host build of csrc/math.cuh).  TEST-ONLY."""
+import ctypes
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostcheck.cpp")
+HDR = os.path.join(HERE, "..", "..", "instantsfm_b200", "csrc", "math.cuh")
+LIB = os.path.join(HERE, "libhostcheck.so")
+
+
+def load():
+    stale = (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR))
+    if stale:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-fPIC", "-shared", "-o", LIB, SRC])
+    return ctypes.CDLL(LIB)
