@@ -26,6 +26,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
 
 typedef enum isfm_status {
   ISFM_OK = 0,
@@ -217,6 +220,9 @@ int isfm_gp_cost(isfm_gp* h, double* robust_cost_out, double* sq_cost_out);
 int isfm_gp_get_timers(isfm_gp* h, double ms_out[ISFM_N_TIMERS], int64_t launches_out[ISFM_N_TIMERS]);
 int isfm_gp_reset_timers(isfm_gp* h, int32_t enable);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

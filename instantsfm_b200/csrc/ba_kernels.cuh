@@ -1,0 +1,456 @@
+// ba_kernels.cuh -- CUDA kernels of the bundle-adjustment LM step (K1, K2, K3, K5).
+//
+// Data layout in HBM (T = float in the product build), "sorted position" a = observation
+// index after the stable sort by point:
+//   cam   [n_cam][7+NI]   t, q_xyzw, intrinsics (pp removed)      pp  [n_cam][2]
+//   pts   [n_pt][3]                                               obs [n_obs][2]   (sorted)
+//   R     [n_obs][2]      Triggs-weighted residual
+//   JC    [n_obs][2*D]    weighted camera block, row-major 2 x D  (D = 6 + NI)
+//   JP    [n_obs][6]      weighted point block, 2 x 3
+//   V     [n_obs][6]      JP * Hpp^-1 (2 x 3), per trial
+//   HPP   [n_pt][6]  GPT [n_pt][3]  HPPINV [n_pt][6]  TP [n_pt][3] = Hpp^-1 g_p
+//   HCC   [n_cam][D*D]  GC [n_cam][D]   (undamped, all ranks' sum)
+//   E     [nnzb][D*D]     BSR values of sum_p Hcp Hpp^-1 Hcp^T; S = damp(Hcc) - E
+// The J-form is kept instead of Hcp = Jc^T Jp (27 floats / obs): every Schur product is
+// Jc_a^T (V_a Jp_b^T) Jc_b with a 2x2 middle factor.
+#pragma once
+#include "common.cuh"
+#include "math.cuh"
+
+namespace isfm {
+
+constexpr int BA_TPB = 256;
+constexpr int RED_BLOCKS = 148 * 4;  // grid of the grid-stride reduction kernels (4 CTAs / SM)
+
+// ---------------------------------------------------------------------------------------
+// K1: residual + Huber weight + Jacobian blocks per observation; cost partials per block.
+// ---------------------------------------------------------------------------------------
+template <typename T, int MODEL>
+__global__ void __launch_bounds__(BA_TPB)
+linearize_kernel(int64_t n_obs, const T* __restrict__ cam, const T* __restrict__ pp, const T* __restrict__ pts,
+                 const T* __restrict__ obs, const int32_t* __restrict__ cam_of, const int32_t* __restrict__ pt_of,
+                 T delta, T* __restrict__ R, T* __restrict__ JC, T* __restrict__ JP,
+                 double* __restrict__ part_rho, double* __restrict__ part_sq) {
+  constexpr int NI = ModelTraits<MODEL>::NI;
+  constexpr int D = 6 + NI;
+  constexpr int CW = 7 + NI;
+  double rho_sum = 0.0, sq_sum = 0.0;
+  for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < n_obs; a += (int64_t)gridDim.x * blockDim.x) {
+    const int c = cam_of[a], p = pt_of[a];
+    T cr[CW], ppv[2], X[3], o[2], r[2], jc[2 * D], jp[6];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) cr[i] = __ldg(cam + (size_t)c * CW + i);
+    ppv[0] = __ldg(pp + 2 * (size_t)c); ppv[1] = __ldg(pp + 2 * (size_t)c + 1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) X[i] = __ldg(pts + 3 * (size_t)p + i);
+    o[0] = obs[2 * a]; o[1] = obs[2 * a + 1];
+    ba_linearize<MODEL, T>(cr, ppv, X, o, r, jc, jp);
+    T s = r[0] * r[0] + r[1] * r[1], rho, w;
+    huber(s, delta, rho, w);
+    rho_sum += (double)rho; sq_sum += (double)s;
+    R[2 * a] = w * r[0]; R[2 * a + 1] = w * r[1];
+#pragma unroll
+    for (int i = 0; i < 2 * D; ++i) JC[(size_t)a * (2 * D) + i] = w * jc[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) JP[(size_t)a * 6 + i] = w * jp[i];
+  }
+  rho_sum = block_sum(rho_sum);
+  sq_sum = block_sum(sq_sum);
+  if (threadIdx.x == 0) { part_rho[blockIdx.x] = rho_sum; part_sq[blockIdx.x] = sq_sum; }
+}
+
+// trial cost: residual only
+template <typename T, int MODEL>
+__global__ void __launch_bounds__(BA_TPB)
+cost_kernel(int64_t n_obs, const T* __restrict__ cam, const T* __restrict__ pp, const T* __restrict__ pts,
+            const T* __restrict__ obs, const int32_t* __restrict__ cam_of, const int32_t* __restrict__ pt_of,
+            T delta, double* __restrict__ part_rho, double* __restrict__ part_sq) {
+  constexpr int NI = ModelTraits<MODEL>::NI;
+  constexpr int CW = 7 + NI;
+  double rho_sum = 0.0, sq_sum = 0.0;
+  for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < n_obs; a += (int64_t)gridDim.x * blockDim.x) {
+    const int c = cam_of[a], p = pt_of[a];
+    T cr[CW], ppv[2], X[3], o[2], r[2];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) cr[i] = __ldg(cam + (size_t)c * CW + i);
+    ppv[0] = __ldg(pp + 2 * (size_t)c); ppv[1] = __ldg(pp + 2 * (size_t)c + 1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) X[i] = __ldg(pts + 3 * (size_t)p + i);
+    o[0] = obs[2 * a]; o[1] = obs[2 * a + 1];
+    ba_residual<MODEL, T>(cr, ppv, X, o, r);
+    T s = r[0] * r[0] + r[1] * r[1], rho, w;
+    huber(s, delta, rho, w);
+    rho_sum += (double)rho; sq_sum += (double)s;
+  }
+  rho_sum = block_sum(rho_sum);
+  sq_sum = block_sum(sq_sum);
+  if (threadIdx.x == 0) { part_rho[blockIdx.x] = rho_sum; part_sq[blockIdx.x] = sq_sum; }
+}
+
+// unweighted residuals (debug / parity)
+template <typename T, int MODEL>
+__global__ void residual_kernel(int64_t n_obs, const T* __restrict__ cam, const T* __restrict__ pp,
+                                const T* __restrict__ pts, const T* __restrict__ obs,
+                                const int32_t* __restrict__ cam_of, const int32_t* __restrict__ pt_of, T* __restrict__ out) {
+  constexpr int NI = ModelTraits<MODEL>::NI;
+  constexpr int CW = 7 + NI;
+  int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a >= n_obs) return;
+  ba_residual<MODEL, T>(cam + (size_t)cam_of[a] * CW, pp + 2 * (size_t)cam_of[a], pts + 3 * (size_t)pt_of[a], obs + 2 * a,
+                        out + 2 * a);
+}
+
+// out[k] = sum of partials k (one block per output scalar)
+static __global__ void reduce_scalars_kernel(const double* __restrict__ p0, const double* __restrict__ p1,
+                                      const double* __restrict__ p2, int n0, int n1, int n2, double* out) {
+  const double* p = blockIdx.x == 0 ? p0 : (blockIdx.x == 1 ? p1 : p2);
+  int n = blockIdx.x == 0 ? n0 : (blockIdx.x == 1 ? n1 : n2);
+  if (!p) { if (threadIdx.x == 0) out[blockIdx.x] = 0.0; return; }
+  double v = reduce_partials(p, n);
+  if (threadIdx.x == 0) out[blockIdx.x] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 (point side) + K3 (3x3): one thread per point over its contiguous observations.
+// BUILD: accumulate Hpp = sum Jp^T Jp and g_p = sum Jp^T R.  Always: damp, invert, TP, V.
+// ---------------------------------------------------------------------------------------
+template <typename T, bool BUILD>
+__global__ void __launch_bounds__(BA_TPB)
+point_solve_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const T* __restrict__ JP, const T* __restrict__ R,
+                   T mu, T* __restrict__ HPP, T* __restrict__ GPT, T* __restrict__ HPPINV, T* __restrict__ TP,
+                   T* __restrict__ V) {
+  int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n_pt) return;
+  const int beg = pt_off[p], end = pt_off[p + 1];
+  T h[6], g[3];
+  if (BUILD) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) h[i] = T(0);
+    g[0] = g[1] = g[2] = T(0);
+    for (int a = beg; a < end; ++a) {
+      const T* j = JP + (size_t)a * 6;
+      T j0 = j[0], j1 = j[1], j2 = j[2], j3 = j[3], j4 = j[4], j5 = j[5];
+      T r0 = R[2 * (size_t)a], r1 = R[2 * (size_t)a + 1];
+      h[0] += j0 * j0 + j3 * j3; h[1] += j0 * j1 + j3 * j4; h[2] += j0 * j2 + j3 * j5;
+      h[3] += j1 * j1 + j4 * j4; h[4] += j1 * j2 + j4 * j5; h[5] += j2 * j2 + j5 * j5;
+      g[0] += j0 * r0 + j3 * r1; g[1] += j1 * r0 + j4 * r1; g[2] += j2 * r0 + j5 * r1;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) HPP[(size_t)p * 6 + i] = h[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) GPT[(size_t)p * 3 + i] = g[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) h[i] = HPP[(size_t)p * 6 + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) g[i] = GPT[(size_t)p * 3 + i];
+  }
+  h[0] = damp_diag(h[0], mu); h[3] = damp_diag(h[3], mu); h[5] = damp_diag(h[5], mu);
+  T iv[6];
+  sym3_inverse(h, iv);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) HPPINV[(size_t)p * 6 + i] = iv[i];
+  TP[(size_t)p * 3 + 0] = iv[0] * g[0] + iv[1] * g[1] + iv[2] * g[2];
+  TP[(size_t)p * 3 + 1] = iv[1] * g[0] + iv[3] * g[1] + iv[4] * g[2];
+  TP[(size_t)p * 3 + 2] = iv[2] * g[0] + iv[4] * g[1] + iv[5] * g[2];
+  if (V) {
+    for (int a = beg; a < end; ++a) {
+      const T* j = JP + (size_t)a * 6;
+      T* v = V + (size_t)a * 6;
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        T a0 = j[3 * row], a1 = j[3 * row + 1], a2 = j[3 * row + 2];
+        v[3 * row + 0] = a0 * iv[0] + a1 * iv[1] + a2 * iv[2];
+        v[3 * row + 1] = a0 * iv[1] + a1 * iv[3] + a2 * iv[4];
+        v[3 * row + 2] = a0 * iv[2] + a1 * iv[4] + a2 * iv[5];
+      }
+    }
+  }
+}
+
+// points-only BA (optimize_poses = False): D_p = -Hpp^-1 g_p, trial points, model term
+template <typename T>
+__global__ void __launch_bounds__(BA_TPB)
+point_only_step_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const T* __restrict__ JP,
+                       const T* __restrict__ R, const T* __restrict__ TP, const T* __restrict__ pts,
+                       T* __restrict__ pts_trial, T* __restrict__ DP, double* __restrict__ part_m) {
+  double msum = 0.0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_pt; p += (int64_t)gridDim.x * blockDim.x) {
+    T d0 = -TP[3 * p], d1 = -TP[3 * p + 1], d2 = -TP[3 * p + 2];
+    DP[3 * p] = d0; DP[3 * p + 1] = d1; DP[3 * p + 2] = d2;
+    pts_trial[3 * p] = pts[3 * p] + d0; pts_trial[3 * p + 1] = pts[3 * p + 1] + d1; pts_trial[3 * p + 2] = pts[3 * p + 2] + d2;
+    for (int a = pt_off[p]; a < pt_off[p + 1]; ++a) {
+      const T* j = JP + (size_t)a * 6;
+      T jd0 = j[0] * d0 + j[1] * d1 + j[2] * d2, jd1 = j[3] * d0 + j[4] * d1 + j[5] * d2;
+      msum += (double)(jd0 * (2 * R[2 * (size_t)a] + jd0) + jd1 * (2 * R[2 * (size_t)a + 1] + jd1));
+    }
+  }
+  msum = block_sum(msum);
+  if (threadIdx.x == 0) part_m[blockIdx.x] = msum;
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 (camera side): one CTA per camera over its observations (camera-major list).
+// PASS_E = false: Hcc_i = sum Jc^T Jc, g_c = sum Jc^T R            (once per LM step)
+// PASS_E = true : E_ii  = sum Jc^T (V Jp^T) Jc, e_i = sum Jc^T (Jp t_p)   (once per trial)
+// Warp-shuffle + shared-memory reduction; no atomics.
+// ---------------------------------------------------------------------------------------
+constexpr int CAM_TPB = 128;
+
+template <typename T, int D, bool PASS_E>
+__global__ void __launch_bounds__(CAM_TPB)
+camera_blocks_kernel(const int32_t* __restrict__ cam_off, const int32_t* __restrict__ cam_perm,
+                     const int32_t* __restrict__ pt_of, const T* __restrict__ JC, const T* __restrict__ R,
+                     const T* __restrict__ JP, const T* __restrict__ V, const T* __restrict__ TP,
+                     T* __restrict__ out_blocks, const int32_t* __restrict__ out_slot, T* __restrict__ out_vec) {
+  constexpr int NU = D * (D + 1) / 2;
+  constexpr int NACC = NU + D;
+  constexpr int NW = CAM_TPB / 32;
+  __shared__ T sh[NW][NACC];
+  const int cam = blockIdx.x;
+  const int beg = cam_off[cam], end = cam_off[cam + 1];
+  T acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = T(0);
+  for (int k = beg + threadIdx.x; k < end; k += CAM_TPB) {
+    const int a = cam_perm[k];
+    T jc[2 * D];
+#pragma unroll
+    for (int i = 0; i < 2 * D; ++i) jc[i] = JC[(size_t)a * (2 * D) + i];
+    T m00, m01, m10, m11, s0, s1;
+    if (PASS_E) {
+      const T* v = V + (size_t)a * 6;
+      const T* j = JP + (size_t)a * 6;
+      const T* t = TP + 3 * (size_t)pt_of[a];
+      m00 = v[0] * j[0] + v[1] * j[1] + v[2] * j[2]; m01 = v[0] * j[3] + v[1] * j[4] + v[2] * j[5];
+      m10 = v[3] * j[0] + v[4] * j[1] + v[5] * j[2]; m11 = v[3] * j[3] + v[4] * j[4] + v[5] * j[5];
+      s0 = j[0] * t[0] + j[1] * t[1] + j[2] * t[2]; s1 = j[3] * t[0] + j[4] * t[1] + j[5] * t[2];
+    } else {
+      m00 = T(1); m01 = T(0); m10 = T(0); m11 = T(1);
+      s0 = R[2 * (size_t)a]; s1 = R[2 * (size_t)a + 1];
+    }
+    int u = 0;
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      // row r of Jc^T M : (jc[r], jc[D + r]) * M
+      T l0 = jc[r] * m00 + jc[D + r] * m10, l1 = jc[r] * m01 + jc[D + r] * m11;
+#pragma unroll
+      for (int c = r; c < D; ++c) acc[u++] += l0 * jc[c] + l1 * jc[D + c];
+      acc[NU + r] += jc[r] * s0 + jc[D + r] * s1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) {
+    T v = acc[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    acc[i] = v;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) sh[w][i] = acc[i];
+  }
+  __syncthreads();
+  // thread t < NACC sums the NW warp partials of accumulator t and scatters it
+  for (int t = threadIdx.x; t < NACC; t += CAM_TPB) {
+    T v = T(0);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) v += sh[k][t];
+    if (t >= NU) {
+      out_vec[(size_t)cam * D + (t - NU)] = v;
+    } else {
+      // invert the packed upper-triangle index
+      int r = 0, rem = t;
+      while (rem >= D - r) { rem -= D - r; ++r; }
+      int c = r + rem;
+      T* blk = out_blocks + (size_t)(out_slot ? out_slot[cam] : cam) * (D * D);
+      blk[r * D + c] = v;
+      blk[c * D + r] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 (Schur off-diagonal): one warp per list of observation pairs (a, b) of block (i, j),
+// i <= j.  E_ij = sum Jc_a^T (V_a Jp_b^T) Jc_b.  Lanes stride over the pairs with the whole
+// D x CT tile in registers, then a warp xor-reduction; block (j, i) gets the transpose.
+// Diagonal lists (same camera twice in a track) add onto E_ii written by the camera pass.
+// ---------------------------------------------------------------------------------------
+template <int D> struct SchurTile { static constexpr int CT = (D <= 9) ? D : D / 2; };
+
+template <typename T, int D>
+__global__ void __launch_bounds__(128)
+schur_offdiag_kernel(int64_t n_lists, const int64_t* __restrict__ list_off, const uint64_t* __restrict__ pairs,
+                     const int32_t* __restrict__ list_slot, const int32_t* __restrict__ list_slot_t,
+                     const T* __restrict__ JC, const T* __restrict__ JP, const T* __restrict__ V, T* __restrict__ E) {
+  constexpr int CT = SchurTile<D>::CT;
+  const int lane = threadIdx.x & 31;
+  const int64_t u = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (u >= n_lists) return;
+  const int c0 = blockIdx.y * CT;
+  T acc[D * CT];
+#pragma unroll
+  for (int i = 0; i < D * CT; ++i) acc[i] = T(0);
+  const int64_t beg = list_off[u], end = list_off[u + 1];
+  for (int64_t t = beg + lane; t < end; t += 32) {
+    const uint64_t ab = pairs[t];
+    const uint32_t a = (uint32_t)(ab >> 32), b = (uint32_t)ab;
+    const T* va = V + (size_t)a * 6;
+    const T* jb = JP + (size_t)b * 6;
+    T m00 = va[0] * jb[0] + va[1] * jb[1] + va[2] * jb[2], m01 = va[0] * jb[3] + va[1] * jb[4] + va[2] * jb[5];
+    T m10 = va[3] * jb[0] + va[4] * jb[1] + va[5] * jb[2], m11 = va[3] * jb[3] + va[4] * jb[4] + va[5] * jb[5];
+    const T* ja = JC + (size_t)a * (2 * D);
+    const T* jcb = JC + (size_t)b * (2 * D);
+    T t0[CT], t1[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      T b0 = jcb[c0 + c], b1 = jcb[D + c0 + c];
+      t0[c] = m00 * b0 + m01 * b1;
+      t1[c] = m10 * b0 + m11 * b1;
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      T a0 = ja[r], a1 = ja[D + r];
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[r * CT + c] += a0 * t0[c] + a1 * t1[c];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D * CT; ++i) {
+    T v = acc[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[i] = v;
+  }
+  const int slot = list_slot[u], slot_t = list_slot_t[u];
+  T* blk = E + (size_t)slot * (D * D);
+  if (slot_t >= 0) {
+    T* blk_t = E + (size_t)slot_t * (D * D);
+#pragma unroll
+    for (int i = 0; i < D * CT; ++i) {
+      if (lane == (i & 31)) {
+        const int r = i / CT, c = c0 + i % CT;
+        blk[r * D + c] = acc[i];
+        blk_t[c * D + r] = acc[i];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < D * CT; ++i) {
+      if (lane == (i & 31)) {
+        const int r = i / CT, c = c0 + i % CT;
+        blk[r * D + c] += acc[i];
+      }
+    }
+  }
+}
+
+// gather diag(E) blocks and e into the reduction buffer [n_cam][D*D + D]
+template <typename T, int D>
+__global__ void gather_diag_kernel(int n_cam, const int32_t* __restrict__ diag_slot, const T* __restrict__ E,
+                                   const T* __restrict__ EG, T* __restrict__ red) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cam * (D * D + D)) return;
+  int cam = i / (D * D + D), k = i % (D * D + D);
+  red[i] = k < D * D ? E[(size_t)diag_slot[cam] * (D * D) + k] : EG[(size_t)cam * D + (k - D * D)];
+}
+
+// K3: Hd = damp(Hcc); Minv = (Hd - sum_ranks E_ii)^-1 ; b = -(g_c - sum_ranks e)
+template <typename T, int D>
+__global__ void precond_kernel(int n_cam, const T* __restrict__ HCC, const T* __restrict__ GC, const T* __restrict__ red,
+                               T mu, T* __restrict__ HD, T* __restrict__ MINV, T* __restrict__ bvec, int* __restrict__ fail) {
+  int cam = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cam >= n_cam) return;
+  double M[D * D];
+  const T* h = HCC + (size_t)cam * (D * D);
+  const T* e = red + (size_t)cam * (D * D + D);
+#pragma unroll 1
+  for (int r = 0; r < D; ++r)
+    for (int c = 0; c < D; ++c) {
+      T v = h[r * D + c];
+      if (r == c) v = damp_diag(v, mu);
+      HD[(size_t)cam * (D * D) + r * D + c] = v;
+      M[r * D + c] = (double)v - (double)e[r * D + c];
+    }
+  if (!spd_inverse<D>(M)) *fail = 1;
+#pragma unroll 1
+  for (int k = 0; k < D * D; ++k) MINV[(size_t)cam * (D * D) + k] = (T)M[k];
+#pragma unroll 1
+  for (int k = 0; k < D; ++k) bvec[(size_t)cam * D + k] = -(GC[(size_t)cam * D + k] - e[D * D + k]);
+}
+
+// ---------------------------------------------------------------------------------------
+// K5: back-substitution D_p = -Hpp^-1 (g_p + sum Jp^T (Jc D_c)), trial points, and the
+// trust-region model term sum (JD)^T (2R + JD).  One thread per point.
+// ---------------------------------------------------------------------------------------
+template <typename T, int D>
+__global__ void __launch_bounds__(BA_TPB)
+backsub_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const int32_t* __restrict__ cam_of,
+               const T* __restrict__ JC, const T* __restrict__ JP, const T* __restrict__ R, const T* __restrict__ GPT,
+               const T* __restrict__ HPPINV, const T* __restrict__ DC, const T* __restrict__ pts,
+               T* __restrict__ pts_trial, T* __restrict__ DP, double* __restrict__ part_m) {
+  double msum = 0.0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_pt; p += (int64_t)gridDim.x * blockDim.x) {
+    const int beg = pt_off[p], end = pt_off[p + 1];
+    T u0 = GPT[3 * p], u1 = GPT[3 * p + 1], u2 = GPT[3 * p + 2];
+    for (int a = beg; a < end; ++a) {
+      const T* jc = JC + (size_t)a * (2 * D);
+      const T* dc = DC + (size_t)cam_of[a] * D;
+      T w0 = T(0), w1 = T(0);
+#pragma unroll
+      for (int c = 0; c < D; ++c) { T d = dc[c]; w0 += jc[c] * d; w1 += jc[D + c] * d; }
+      const T* j = JP + (size_t)a * 6;
+      u0 += j[0] * w0 + j[3] * w1; u1 += j[1] * w0 + j[4] * w1; u2 += j[2] * w0 + j[5] * w1;
+    }
+    const T* iv = HPPINV + (size_t)p * 6;
+    T d0 = -(iv[0] * u0 + iv[1] * u1 + iv[2] * u2);
+    T d1 = -(iv[1] * u0 + iv[3] * u1 + iv[4] * u2);
+    T d2 = -(iv[2] * u0 + iv[4] * u1 + iv[5] * u2);
+    DP[3 * p] = d0; DP[3 * p + 1] = d1; DP[3 * p + 2] = d2;
+    pts_trial[3 * p] = pts[3 * p] + d0; pts_trial[3 * p + 1] = pts[3 * p + 1] + d1; pts_trial[3 * p + 2] = pts[3 * p + 2] + d2;
+    for (int a = beg; a < end; ++a) {
+      const T* jc = JC + (size_t)a * (2 * D);
+      const T* dc = DC + (size_t)cam_of[a] * D;
+      T w0 = T(0), w1 = T(0);
+#pragma unroll
+      for (int c = 0; c < D; ++c) { T d = dc[c]; w0 += jc[c] * d; w1 += jc[D + c] * d; }
+      const T* j = JP + (size_t)a * 6;
+      T jd0 = w0 + j[0] * d0 + j[1] * d1 + j[2] * d2, jd1 = w1 + j[3] * d0 + j[4] * d1 + j[5] * d2;
+      msum += (double)(jd0 * (2 * R[2 * (size_t)a] + jd0) + jd1 * (2 * R[2 * (size_t)a + 1] + jd1));
+    }
+  }
+  msum = block_sum(msum);
+  if (threadIdx.x == 0) part_m[blockIdx.x] = msum;
+}
+
+// x <- x (+) D for cameras: Exp(D[:6]) * pose, intrinsics += D[6:]   (bae update_parameter)
+template <typename T, int NI>
+__global__ void camera_update_kernel(int n_cam, const T* __restrict__ cam, const T* __restrict__ DC, T* __restrict__ cam_trial,
+                                     double* __restrict__ part_norm) {
+  constexpr int D = 6 + NI, CW = 7 + NI;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double nrm = 0.0;
+  if (i < n_cam) {
+    T d[D], in[CW], out[CW];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { d[k] = DC[(size_t)i * D + k]; nrm += (double)d[k] * (double)d[k]; }
+#pragma unroll
+    for (int k = 0; k < CW; ++k) in[k] = cam[(size_t)i * CW + k];
+    se3_retract(in, d, out);
+#pragma unroll
+    for (int k = 0; k < NI; ++k) out[7 + k] = in[7 + k] + d[6 + k];
+#pragma unroll
+    for (int k = 0; k < CW; ++k) cam_trial[(size_t)i * CW + k] = out[k];
+  }
+  nrm = block_sum(nrm);
+  if (threadIdx.x == 0) part_norm[blockIdx.x] = nrm;
+}
+
+// gather rows: dst[i] = src[idx[i]] with row width W (set-up only)
+template <typename T>
+__global__ void gather_rows_kernel(int64_t n, int W, const T* __restrict__ src, const int32_t* __restrict__ idx, T* __restrict__ dst) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * W) return;
+  dst[i] = src[(size_t)idx[i / W] * W + i % W];
+}
+
+}  // namespace isfm

@@ -1,0 +1,427 @@
+// ba_solver.cuh -- host driver of one bae.optim.LM.step for bundle adjustment, solved by
+// Schur complement + block-Jacobi PCG instead of the reference's full-system Jacobi PCG
+// (SURVEY.md 9.3).  One instance per handle; T in {float, double}, MODEL = CameraModelId.
+#pragma once
+#include <algorithm>
+#include <cmath>
+
+#include "ba_kernels.cuh"
+#include "comm.cuh"
+#include "index_prep.cuh"
+#include "pcg.cuh"
+
+namespace isfm {
+
+// pp.optim.strategy.TrustRegion; scalars live on the host in double.
+struct TrustRegionState {
+  double radius, high = 0.5, low = 1e-3, up, down0, down, factor = 0.5, max, min = 1e-6, damping;
+  void init(double radius_, double max_, double up_, double down_) {
+    radius = radius_; max = max_; up = up_; down0 = down = down_; damping = 1.0 / radius_;
+  }
+  double update(double last, double loss, double model_term /* (JD)^T (2R + JD) */) {
+    double denom = -model_term;
+    double quality = denom != 0.0 ? (last - loss) / denom : 0.0;
+    double r = 1.0 / damping;
+    if (quality > high) { r = up * r; down = down0; }
+    else if (quality > low) { down = down0; }
+    else { r = r * down; down = down * factor; }
+    down = std::max(min, std::min(down, max));
+    r = std::max(min, std::min(r, max));
+    radius = r; damping = 1.0 / r;
+    return quality;
+  }
+};
+
+struct BASolverBase {
+  virtual ~BASolverBase() {}
+  virtual void set_problem(int64_t n_cam, int64_t n_pt, int64_t n_obs, const void* cam, const void* pp, const void* pts,
+                           const void* obs, const int32_t* cam_idx, const int32_t* pt_idx) = 0;
+  virtual void step(double* loss_out, isfm_step_stats* stats) = 0;
+  virtual void get_params(void* cam_out, void* pts_out) = 0;
+  virtual void set_params(const void* cam, const void* pts) = 0;
+  virtual void cost(double* robust, double* sq) = 0;
+  virtual void get_structure(int32_t* obs_perm, int64_t* pt_off, int32_t* cam_perm, int64_t* cam_off) = 0;
+  virtual void get_schur_pattern(int64_t* nnzb, int64_t* n_pairs, int64_t* row_ptr, int32_t* col_idx) = 0;
+  virtual void debug_get(int what, void* dst) = 0;
+  KernelTimers timers;
+  bool has_problem = false;
+};
+
+template <typename T, int MODEL>
+struct BASolver : BASolverBase {
+  static constexpr int NI = ModelTraits<MODEL>::NI;
+  static constexpr int D = 6 + NI;
+  static constexpr int CW = 7 + NI;
+
+  isfm_ba_desc desc;
+  cudaStream_t s;
+  isfm_comm* comm;
+  TrustRegionState tr;
+  int64_t n_cam = 0, n_pt = 0, n_obs = 0;
+  ObsIndex ix;
+  SchurPattern sp;
+  DeviceBuffer<T> cam[2], pts[2], pp, obs;
+  DeviceBuffer<T> R, JC, JP, V, HPP, GPT, HPPINV, TP, DP;
+  DeviceBuffer<T> HCC_GC, HD, E, EG, RED, MINV, bvec;  // HCC_GC = [HCC | GC | cost] packed for one all-reduce
+  DeviceBuffer<double> part_a, part_b, part_c, scalars;
+  DeviceBuffer<int> fail;
+  double* h_scalars = nullptr;  // pinned [4]
+  BlockPCG<T, D> pcg;
+  int cur = 0;
+  bool have_loss = false;
+  double loss = 0.0;
+  double mu_last = 1.0;
+
+  explicit BASolver(const isfm_ba_desc& d) : desc(d) {
+    s = static_cast<cudaStream_t>(d.stream);
+    comm = d.comm;
+    timers.stream = s;
+    tr.init(d.tr_radius, d.tr_max, d.tr_up, d.tr_down);
+    ISFM_CUDA(cudaMallocHost(&h_scalars, 4 * sizeof(double)));
+  }
+  ~BASolver() override { if (h_scalars) cudaFreeHost(h_scalars); }
+
+  T* HCC() { return HCC_GC.get(); }
+  T* GC() { return HCC_GC.get() + (size_t)n_cam * D * D; }
+
+  template <typename U>
+  void upload(DeviceBuffer<U>& dst, const void* src, size_t count) {
+    dst.alloc(count);
+    ISFM_CUDA(cudaMemcpyAsync(dst.get(), src, count * sizeof(U), cudaMemcpyDefault, s));
+  }
+
+  void set_problem(int64_t nc, int64_t np, int64_t no, const void* cam_in, const void* pp_in, const void* pts_in,
+                   const void* obs_in, const int32_t* cam_idx, const int32_t* pt_idx) override {
+    ISFM_REQUIRE(cam_in && pp_in && pts_in && obs_in && cam_idx && pt_idx, ISFM_EINVAL, "null input");
+    n_cam = nc; n_pt = np; n_obs = no;
+    upload(cam[0], cam_in, (size_t)nc * CW); cam[1].alloc((size_t)nc * CW);
+    upload(pts[0], pts_in, (size_t)np * 3); pts[1].alloc((size_t)np * 3);
+    upload(pp, pp_in, (size_t)nc * 2);
+    DeviceBuffer<T> obs_raw; DeviceBuffer<int32_t> ci, pi;
+    upload(obs_raw, obs_in, (size_t)no * 2);
+    upload(ci, cam_idx, (size_t)no); upload(pi, pt_idx, (size_t)no);
+    build_obs_index(ix, nc, np, no, ci.get(), pi.get(), s, timers);
+    obs.alloc((size_t)no * 2);
+    { TimerScope ts(timers, T_INDEX_PREP);
+      gather_rows_kernel<T><<<div_up(no * 2, BA_TPB), BA_TPB, 0, s>>>(no, 2, obs_raw.get(), ix.obs_perm.get(), obs.get()); }
+    R.alloc((size_t)no * 2); JP.alloc((size_t)no * 6);
+    HPP.alloc((size_t)np * 6); GPT.alloc((size_t)np * 3); HPPINV.alloc((size_t)np * 6); TP.alloc((size_t)np * 3);
+    DP.alloc((size_t)np * 3);
+    part_a.alloc(std::max<int64_t>(RED_BLOCKS, nc)); part_b.alloc(std::max<int64_t>(RED_BLOCKS, nc));
+    part_c.alloc(std::max<int64_t>(RED_BLOCKS, nc));
+    scalars.alloc(4); fail.alloc(1); fail.zero(s);
+    JC.alloc((size_t)no * 2 * D);  // also needed by points-only mode for nothing but kept simple
+    if (desc.optimize_poses) {
+      V.alloc((size_t)no * 6);
+      build_schur_pattern(sp, ix, s, timers);
+      HCC_GC.alloc((size_t)nc * (D * D + D)); HD.alloc((size_t)nc * D * D);
+      E.alloc((size_t)sp.nnzb * D * D); EG.alloc((size_t)nc * D); RED.alloc((size_t)nc * (D * D + D));
+      MINV.alloc((size_t)nc * D * D); bvec.alloc((size_t)nc * D);
+      pcg.resize((int)nc);
+    }
+    ISFM_CUDA(cudaStreamSynchronize(s));
+    cur = 0; have_loss = false; has_problem = true;
+    tr.init(desc.tr_radius, desc.tr_max, desc.tr_up, desc.tr_down);
+  }
+
+  int red_grid(int64_t n) const { return (int)std::min<int64_t>(RED_BLOCKS, div_up(n, BA_TPB)); }
+
+  // reduce up to three partial arrays to scalars, all-reduce them, copy to the host
+  void fetch_scalars(const double* p0, int n0, const double* p1, int n1, const double* p2, int n2, bool allreduce) {
+    { TimerScope ts(timers, T_REDUCE);
+      reduce_scalars_kernel<<<3, 256, 0, s>>>(p0, p1, p2, n0, n1, n2, scalars.get()); }
+    if (allreduce && comm_world(comm) > 1) {
+      TimerScope ts(timers, T_COMM);
+      comm_allreduce_sum(comm, scalars.get(), 3, true, s);
+    }
+    ISFM_CUDA(cudaMemcpyAsync(h_scalars, scalars.get(), 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));
+  }
+
+  void run_linearize() {
+    const int g = red_grid(n_obs);
+    TimerScope ts(timers, T_LINEARIZE);
+    linearize_kernel<T, MODEL><<<g, BA_TPB, 0, s>>>(n_obs, cam[cur].get(), pp.get(), pts[cur].get(), obs.get(),
+                                                    ix.cam_of.get(), ix.pt_of.get(), (T)desc.huber_delta, R.get(), JC.get(),
+                                                    JP.get(), part_a.get(), part_b.get());
+  }
+
+  void run_cost(int which, double* robust, double* sq) {
+    const int g = red_grid(n_obs);
+    { TimerScope ts(timers, T_COST);
+      cost_kernel<T, MODEL><<<g, BA_TPB, 0, s>>>(n_obs, cam[which].get(), pp.get(), pts[which].get(), obs.get(),
+                                                 ix.cam_of.get(), ix.pt_of.get(), (T)desc.huber_delta, part_a.get(),
+                                                 part_b.get()); }
+    fetch_scalars(part_a.get(), g, part_b.get(), g, nullptr, 0, true);
+    *robust = h_scalars[0];
+    if (sq) *sq = h_scalars[1];
+  }
+
+  void run_point_solve(bool build, T mu) {
+    TimerScope ts(timers, build ? T_POINT_BLOCKS : T_POINT_SOLVE);
+    const int g = div_up(n_pt, BA_TPB);
+    if (build)
+      point_solve_kernel<T, true><<<g, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), JP.get(), R.get(), mu, HPP.get(), GPT.get(),
+                                                       HPPINV.get(), TP.get(), V.get());
+    else
+      point_solve_kernel<T, false><<<g, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), JP.get(), R.get(), mu, HPP.get(), GPT.get(),
+                                                        HPPINV.get(), TP.get(), V.get());
+  }
+
+  void run_camera_hessian() {
+    { TimerScope ts(timers, T_CAMERA_BLOCKS);
+      camera_blocks_kernel<T, D, false><<<(int)n_cam, CAM_TPB, 0, s>>>(ix.cam_off.get(), ix.cam_perm.get(), ix.pt_of.get(),
+                                                                      JC.get(), R.get(), JP.get(), nullptr, nullptr, HCC(),
+                                                                      nullptr, GC()); }
+    if (comm_world(comm) > 1) {
+      TimerScope ts(timers, T_COMM);
+      comm_allreduce_sum(comm, HCC_GC.get(), (size_t)n_cam * (D * D + D), sizeof(T) == 8, s);
+    }
+  }
+
+  // builds E, the preconditioner and the right-hand side for damping mu; solves for D_c
+  int run_schur_and_pcg(T mu, int* pcg_status) {
+    { TimerScope ts(timers, T_CAMERA_BLOCKS);
+      camera_blocks_kernel<T, D, true><<<(int)n_cam, CAM_TPB, 0, s>>>(ix.cam_off.get(), ix.cam_perm.get(), ix.pt_of.get(),
+                                                                     JC.get(), R.get(), JP.get(), V.get(), TP.get(), E.get(),
+                                                                     sp.diag_slot.get(), EG.get()); }
+    if (sp.n_lists > 0) {
+      TimerScope ts(timers, T_SCHUR_OFFDIAG);
+      dim3 grid(div_up(sp.n_lists, 4), D / SchurTile<D>::CT);
+      schur_offdiag_kernel<T, D><<<grid, 128, 0, s>>>(sp.n_lists, sp.list_off.get(), sp.pairs.get(), sp.list_slot.get(),
+                                                      sp.list_slot_t.get(), JC.get(), JP.get(), V.get(), E.get());
+    }
+    { TimerScope ts(timers, T_PRECOND);
+      gather_diag_kernel<T, D><<<div_up(n_cam * (D * D + D), BA_TPB), BA_TPB, 0, s>>>((int)n_cam, sp.diag_slot.get(), E.get(),
+                                                                                      EG.get(), RED.get()); }
+    if (comm_world(comm) > 1) {
+      TimerScope ts(timers, T_COMM);
+      comm_allreduce_sum(comm, RED.get(), (size_t)n_cam * (D * D + D), sizeof(T) == 8, s);
+    }
+    { TimerScope ts(timers, T_PRECOND);
+      precond_kernel<T, D><<<div_up(n_cam, 64), 64, 0, s>>>((int)n_cam, HCC(), GC(), RED.get(), mu, HD.get(), MINV.get(),
+                                                            bvec.get(), fail.get()); }
+    int max_iter = desc.pcg_max_iter > 0 ? desc.pcg_max_iter : (int)std::min<int64_t>(10 * n_cam * D, 5000);
+    return pcg.solve(sp.row_ptr.get(), sp.col_idx.get(), E.get(), HD.get(), MINV.get(), bvec.get(), desc.pcg_tol, max_iter,
+                     comm, s, timers, pcg_status);
+  }
+
+  void step(double* loss_out, isfm_step_stats* st) override {
+    ISFM_REQUIRE(has_problem, ISFM_ESTATE, "isfm_ba_step before isfm_ba_set_problem");
+    // R, J at the current parameters (+ the initial loss on the first call: `self.loss`)
+    run_linearize();
+    if (!have_loss) {
+      const int g = red_grid(n_obs);
+      fetch_scalars(part_a.get(), g, part_b.get(), g, nullptr, 0, true);
+      loss = h_scalars[0];
+      have_loss = true;
+      ISFM_REQUIRE(std::isfinite(loss), ISFM_ENONFINITE, "initial cost is not finite");
+    }
+    const double last = loss;
+    isfm_step_stats stats;
+    memset(&stats, 0, sizeof stats);
+    stats.loss_before = last;
+    double mu = 1.0;
+    bool built = false;
+    if (desc.optimize_poses) run_camera_hessian();
+    int rejects = 0;
+    const int trial = cur ^ 1;
+    while (last <= loss) {
+      mu *= 1.0 + tr.damping;  // cumulative across rejected trials (pypose LM)
+      run_point_solve(!built, (T)mu);
+      built = true;
+      int mterm_parts;
+      if (desc.optimize_poses) {
+        int pcg_status = 0;
+        stats.pcg_iters += run_schur_and_pcg((T)mu, &pcg_status);
+        { TimerScope ts(timers, T_BACKSUB);
+          mterm_parts = red_grid(n_pt);
+          backsub_kernel<T, D><<<mterm_parts, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), ix.cam_of.get(), JC.get(), JP.get(), R.get(),
+                                                             GPT.get(), HPPINV.get(), pcg.x.get(), pts[cur].get(),
+                                                             pts[trial].get(), DP.get(), part_c.get()); }
+        { TimerScope ts(timers, T_UPDATE);
+          camera_update_kernel<T, NI><<<div_up(n_cam, 128), 128, 0, s>>>((int)n_cam, cam[cur].get(), pcg.x.get(),
+                                                                        cam[trial].get(), pcg.part_a.get()); }
+      } else {
+        TimerScope ts(timers, T_BACKSUB);
+        mterm_parts = red_grid(n_pt);
+        point_only_step_kernel<T><<<mterm_parts, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), JP.get(), R.get(), TP.get(),
+                                                                 pts[cur].get(), pts[trial].get(), DP.get(), part_c.get());
+        ISFM_CUDA(cudaMemcpyAsync(cam[trial].get(), cam[cur].get(), (size_t)n_cam * CW * sizeof(T), cudaMemcpyDeviceToDevice, s));
+      }
+      const int g = red_grid(n_obs);
+      { TimerScope ts(timers, T_COST);
+        cost_kernel<T, MODEL><<<g, BA_TPB, 0, s>>>(n_obs, cam[trial].get(), pp.get(), pts[trial].get(), obs.get(),
+                                                   ix.cam_of.get(), ix.pt_of.get(), (T)desc.huber_delta, part_a.get(),
+                                                   part_b.get()); }
+      // scalars: [0] new robust cost, [1] plain squared cost, [2] model term (summed over ranks)
+      fetch_scalars(part_a.get(), g, part_b.get(), g, part_c.get(), mterm_parts, true);
+      const double new_loss = h_scalars[0];
+      const double mterm = h_scalars[2];
+      stats.trials++;
+      stats.model_term = -mterm;
+      stats.quality = tr.update(last, new_loss, mterm);
+      const bool worse = !(new_loss <= last);  // NaN counts as worse (the reference would keep it)
+      if (worse && rejects < desc.reject) {
+        rejects++;
+        loss = last;
+        stats.accepted = 0;
+      } else {
+        cur = trial;
+        loss = new_loss;
+        stats.accepted = 1;
+        break;
+      }
+    }
+    mu_last = mu;
+    stats.rejects = rejects;
+    stats.loss = loss;
+    stats.damping = tr.damping;
+    if (desc.optimize_poses) {
+      // ||D_c|| of the last trial, from the per-block partials of camera_update_kernel
+      { TimerScope ts(timers, T_REDUCE);
+        reduce_scalars_kernel<<<1, 256, 0, s>>>(pcg.part_a.get(), nullptr, nullptr, div_up(n_cam, 128), 0, 0, scalars.get() + 3); }
+      ISFM_CUDA(cudaMemcpyAsync(h_scalars + 3, scalars.get() + 3, sizeof(double), cudaMemcpyDeviceToHost, s));
+      ISFM_CUDA(cudaStreamSynchronize(s));
+      stats.step_norm_cam = std::sqrt(h_scalars[3]);
+    }
+    ISFM_CUDA(cudaGetLastError());
+    if (loss_out) *loss_out = loss;
+    if (st) *st = stats;
+  }
+
+  void get_params(void* cam_out, void* pts_out) override {
+    ISFM_REQUIRE(has_problem, ISFM_ESTATE, "no problem set");
+    if (cam_out) ISFM_CUDA(cudaMemcpyAsync(cam_out, cam[cur].get(), (size_t)n_cam * CW * sizeof(T), cudaMemcpyDefault, s));
+    if (pts_out) ISFM_CUDA(cudaMemcpyAsync(pts_out, pts[cur].get(), (size_t)n_pt * 3 * sizeof(T), cudaMemcpyDefault, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));
+  }
+
+  void set_params(const void* cam_in, const void* pts_in) override {
+    ISFM_REQUIRE(has_problem, ISFM_ESTATE, "no problem set");
+    if (cam_in) ISFM_CUDA(cudaMemcpyAsync(cam[cur].get(), cam_in, (size_t)n_cam * CW * sizeof(T), cudaMemcpyDefault, s));
+    if (pts_in) ISFM_CUDA(cudaMemcpyAsync(pts[cur].get(), pts_in, (size_t)n_pt * 3 * sizeof(T), cudaMemcpyDefault, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));
+    have_loss = false;
+  }
+
+  void cost(double* robust, double* sq) override {
+    ISFM_REQUIRE(has_problem, ISFM_ESTATE, "no problem set");
+    double r, q;
+    run_cost(cur, &r, &q);
+    if (robust) *robust = r;
+    if (sq) *sq = q;
+  }
+
+  template <typename U>
+  static void d2h(std::vector<U>& h, const U* d, size_t n, cudaStream_t s) {
+    h.resize(n);
+    ISFM_CUDA(cudaMemcpyAsync(h.data(), d, n * sizeof(U), cudaMemcpyDeviceToHost, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));
+  }
+
+  void get_structure(int32_t* obs_perm, int64_t* pt_off, int32_t* cam_perm, int64_t* cam_off) override {
+    ISFM_REQUIRE(has_problem, ISFM_ESTATE, "no problem set");
+    std::vector<int32_t> h;
+    if (obs_perm) { d2h(h, ix.obs_perm.get(), (size_t)n_obs, s); std::copy(h.begin(), h.end(), obs_perm); }
+    if (cam_perm) { d2h(h, ix.cam_perm.get(), (size_t)n_obs, s); std::copy(h.begin(), h.end(), cam_perm); }
+    if (pt_off) { d2h(h, ix.pt_off.get(), (size_t)n_pt + 1, s); std::copy(h.begin(), h.end(), pt_off); }
+    if (cam_off) { d2h(h, ix.cam_off.get(), (size_t)n_cam + 1, s); std::copy(h.begin(), h.end(), cam_off); }
+  }
+
+  void get_schur_pattern(int64_t* nnzb, int64_t* n_pairs, int64_t* row_ptr, int32_t* col_idx) override {
+    ISFM_REQUIRE(has_problem && desc.optimize_poses, ISFM_ESTATE, "no reduced camera system (optimize_poses = 0?)");
+    if (nnzb) *nnzb = sp.nnzb;
+    if (n_pairs) *n_pairs = sp.n_pairs;
+    std::vector<int32_t> h;
+    if (row_ptr) { d2h(h, sp.row_ptr.get(), (size_t)n_cam + 1, s); std::copy(h.begin(), h.end(), row_ptr); }
+    if (col_idx) { d2h(h, sp.col_idx.get(), (size_t)sp.nnzb, s); std::copy(h.begin(), h.end(), col_idx); }
+  }
+
+  // copies a [n_obs, W] sorted-order buffer back in the caller's observation order
+  void unsort_rows(const T* dev, int W, void* dst) {
+    std::vector<T> h; std::vector<int32_t> perm;
+    d2h(h, dev, (size_t)n_obs * W, s);
+    d2h(perm, ix.obs_perm.get(), (size_t)n_obs, s);
+    T* out = static_cast<T*>(dst);
+    for (int64_t a = 0; a < n_obs; ++a)
+      for (int k = 0; k < W; ++k) out[(size_t)perm[a] * W + k] = h[(size_t)a * W + k];
+  }
+
+  void debug_get(int what, void* dst) override {
+    ISFM_REQUIRE(has_problem && dst, ISFM_ESTATE, "no problem set");
+    if (what == ISFM_BA_STEP_CAM || what == ISFM_BA_STEP_POINT) {
+      if (what == ISFM_BA_STEP_CAM) {
+        ISFM_REQUIRE(desc.optimize_poses, ISFM_ESTATE, "no camera step in points-only mode");
+        ISFM_CUDA(cudaMemcpyAsync(dst, pcg.x.get(), (size_t)n_cam * D * sizeof(T), cudaMemcpyDeviceToHost, s));
+      } else {
+        ISFM_CUDA(cudaMemcpyAsync(dst, DP.get(), (size_t)n_pt * 3 * sizeof(T), cudaMemcpyDeviceToHost, s));
+      }
+      ISFM_CUDA(cudaStreamSynchronize(s));
+      return;
+    }
+    if (what == ISFM_BA_RESIDUALS) {
+      DeviceBuffer<T> tmp; tmp.alloc((size_t)n_obs * 2);
+      residual_kernel<T, MODEL><<<div_up(n_obs, BA_TPB), BA_TPB, 0, s>>>(n_obs, cam[cur].get(), pp.get(), pts[cur].get(),
+                                                                       obs.get(), ix.cam_of.get(), ix.pt_of.get(), tmp.get());
+      unsort_rows(tmp.get(), 2, dst);
+      return;
+    }
+    const T mu = (T)(1.0 + tr.damping);
+    run_linearize();
+    run_point_solve(true, mu);
+    switch (what) {
+      case ISFM_BA_JAC_CAM: unsort_rows(JC.get(), 2 * D, dst); return;
+      case ISFM_BA_JAC_POINT: unsort_rows(JP.get(), 6, dst); return;
+      case ISFM_BA_WEIGHTED_RES: unsort_rows(R.get(), 2, dst); return;
+      case ISFM_BA_HPP: ISFM_CUDA(cudaMemcpyAsync(dst, HPP.get(), (size_t)n_pt * 6 * sizeof(T), cudaMemcpyDeviceToHost, s)); break;
+      case ISFM_BA_GP: ISFM_CUDA(cudaMemcpyAsync(dst, GPT.get(), (size_t)n_pt * 3 * sizeof(T), cudaMemcpyDeviceToHost, s)); break;
+      default: {
+        ISFM_REQUIRE(desc.optimize_poses, ISFM_ESTATE, "camera blocks need optimize_poses = 1");
+        run_camera_hessian();
+        if (what == ISFM_BA_HCC) { ISFM_CUDA(cudaMemcpyAsync(dst, HCC(), (size_t)n_cam * D * D * sizeof(T), cudaMemcpyDeviceToHost, s)); break; }
+        if (what == ISFM_BA_GC) { ISFM_CUDA(cudaMemcpyAsync(dst, GC(), (size_t)n_cam * D * sizeof(T), cudaMemcpyDeviceToHost, s)); break; }
+        ISFM_REQUIRE(what == ISFM_BA_SCHUR_DENSE || what == ISFM_BA_SCHUR_RHS, ISFM_EINVAL, "unknown debug buffer");
+        int status = 0;
+        run_schur_and_pcg(mu, &status);
+        if (what == ISFM_BA_SCHUR_RHS) { ISFM_CUDA(cudaMemcpyAsync(dst, bvec.get(), (size_t)n_cam * D * sizeof(T), cudaMemcpyDeviceToHost, s)); break; }
+        std::vector<T> hE, hHD; std::vector<int32_t> rp, ci;
+        d2h(hE, E.get(), (size_t)sp.nnzb * D * D, s); d2h(hHD, HD.get(), (size_t)n_cam * D * D, s);
+        d2h(rp, sp.row_ptr.get(), (size_t)n_cam + 1, s); d2h(ci, sp.col_idx.get(), (size_t)sp.nnzb, s);
+        const size_t n = (size_t)n_cam * D;
+        T* out = static_cast<T*>(dst);
+        std::fill(out, out + n * n, T(0));
+        for (int64_t i = 0; i < n_cam; ++i) {
+          for (int r = 0; r < D; ++r)
+            for (int c = 0; c < D; ++c) out[(i * D + r) * n + i * D + c] = hHD[(size_t)i * D * D + r * D + c];
+          for (int e = rp[i]; e < rp[i + 1]; ++e)
+            for (int r = 0; r < D; ++r)
+              for (int c = 0; c < D; ++c) out[(i * D + r) * n + (size_t)ci[e] * D + c] -= hE[(size_t)e * D * D + r * D + c];
+        }
+        return;
+      }
+    }
+    ISFM_CUDA(cudaStreamSynchronize(s));
+  }
+};
+
+BASolverBase* make_ba_solver_f32(const isfm_ba_desc& d);
+BASolverBase* make_ba_solver_f64(const isfm_ba_desc& d);
+
+template <typename T>
+BASolverBase* make_ba_solver_t(const isfm_ba_desc& d) {
+  switch (d.model_id) {
+    case 0: return new BASolver<T, 0>(d);
+    case 1: return new BASolver<T, 1>(d);
+    case 2: return new BASolver<T, 2>(d);
+    case 3: return new BASolver<T, 3>(d);
+    case 4: return new BASolver<T, 4>(d);
+    case 5: return new BASolver<T, 5>(d);
+    case 6: return new BASolver<T, 6>(d);
+    case 8: return new BASolver<T, 8>(d);
+    case 9: return new BASolver<T, 9>(d);
+    default: throw IsfmError(ISFM_EUNSUPPORTED_MODEL, "Unsupported camera model");
+  }
+}
+
+}  // namespace isfm

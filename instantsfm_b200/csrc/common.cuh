@@ -1,0 +1,155 @@
+// common.cuh -- error handling, device buffers, launch accounting, block reductions.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/isfm_b200.h"
+
+namespace isfm {
+
+// thread-local last error (isfm_last_error)
+void set_last_error(const std::string& msg);
+const char* get_last_error();
+
+struct IsfmError : std::runtime_error {
+  int code;
+  IsfmError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define ISFM_CUDA(call)                                                                    \
+  do {                                                                                     \
+    cudaError_t err__ = (call);                                                            \
+    if (err__ != cudaSuccess) {                                                            \
+      char buf__[512];                                                                     \
+      snprintf(buf__, sizeof buf__, "%s at %s:%d: %s", #call, __FILE__, __LINE__,          \
+               cudaGetErrorString(err__));                                                 \
+      throw ::isfm::IsfmError(ISFM_ECUDA, buf__);                                          \
+    }                                                                                      \
+  } while (0)
+
+#define ISFM_REQUIRE(cond, code, msg)                                                      \
+  do {                                                                                     \
+    if (!(cond)) throw ::isfm::IsfmError(code, std::string(msg) + " (" #cond ")");         \
+  } while (0)
+
+// global launch counter (isfm_launch_count) -- the bench reports it as gpu_launches
+extern int64_t g_launch_count;
+
+enum Timer {
+  T_LINEARIZE = 0, T_POINT_BLOCKS, T_POINT_SOLVE, T_CAMERA_BLOCKS, T_SCHUR_OFFDIAG, T_PRECOND,
+  T_PCG_SPMV, T_PCG_VEC, T_BACKSUB, T_UPDATE, T_COST, T_INDEX_PREP, T_REDUCE, T_COMM, T_MISC, T_SPARE
+};
+static_assert(T_SPARE + 1 == ISFM_N_TIMERS, "timer table size");
+
+// Optional per-kernel-family CUDA-event timing on the handle's stream.
+struct KernelTimers {
+  bool enabled = false;
+  cudaStream_t stream = nullptr;
+  double ms[ISFM_N_TIMERS] = {0};
+  int64_t launches[ISFM_N_TIMERS] = {0};
+  struct Pending { cudaEvent_t a, b; int id; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+
+  cudaEvent_t get_event() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; ISFM_CUDA(cudaEventCreate(&e)); return e;
+  }
+  void begin(int id) {
+    launches[id]++;
+    g_launch_count++;
+    if (!enabled) return;
+    Pending p{get_event(), get_event(), id};
+    ISFM_CUDA(cudaEventRecord(p.a, stream));
+    pending.push_back(p);
+  }
+  void end() {
+    if (!enabled) return;
+    ISFM_CUDA(cudaEventRecord(pending.back().b, stream));
+  }
+  void resolve() {
+    if (pending.empty()) return;
+    ISFM_CUDA(cudaStreamSynchronize(stream));
+    for (auto& p : pending) {
+      float t = 0.f;
+      ISFM_CUDA(cudaEventElapsedTime(&t, p.a, p.b));
+      ms[p.id] += t;
+      pool.push_back(p.a); pool.push_back(p.b);
+    }
+    pending.clear();
+  }
+  void reset(bool enable) {
+    resolve();
+    for (int i = 0; i < ISFM_N_TIMERS; ++i) { ms[i] = 0; launches[i] = 0; }
+    enabled = enable;
+  }
+  ~KernelTimers() {
+    for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : pool) cudaEventDestroy(e);
+  }
+};
+
+// RAII scope: KT(timers, id); kernel<<<>>>(); -- end recorded at scope exit
+struct TimerScope {
+  KernelTimers& t;
+  TimerScope(KernelTimers& t_, int id) : t(t_) { t.begin(id); }
+  ~TimerScope() { t.end(); }
+};
+
+template <typename T>
+struct DeviceBuffer {
+  T* ptr = nullptr;
+  size_t count = 0;
+  DeviceBuffer() {}
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  ~DeviceBuffer() { release(); }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; count = 0; }
+  void alloc(size_t n) {
+    if (n <= count && ptr) return;
+    release();
+    if (n == 0) n = 1;
+    ISFM_CUDA(cudaMalloc(&ptr, n * sizeof(T)));
+    count = n;
+  }
+  void zero(cudaStream_t s) { if (ptr) ISFM_CUDA(cudaMemsetAsync(ptr, 0, count * sizeof(T), s)); }
+  T* get() const { return ptr; }
+};
+
+inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+// block-wide sum in double; result valid in thread 0.  blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh__[32];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh__[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? sh__[threadIdx.x] : 0.0;
+  if (w == 0)
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic grid-wide sum of per-block partials: every block re-reduces `n` doubles.
+__device__ __forceinline__ double reduce_partials(const double* __restrict__ part, int n) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[i];
+  v = block_sum(v);
+  __shared__ double bc__;
+  if (threadIdx.x == 0) bc__ = v;
+  __syncthreads();
+  return bc__;
+}
+#endif
+
+}  // namespace isfm

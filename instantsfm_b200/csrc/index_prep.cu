@@ -1,0 +1,254 @@
+// index_prep.cu -- see index_prep.cuh.
+#include <cub/cub.cuh>
+
+#include "index_prep.cuh"
+
+namespace isfm {
+namespace {
+
+constexpr int TPB = 256;
+
+__global__ void iota_kernel(int32_t* v, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (int32_t)i;
+}
+
+__global__ void validate_kernel(const int32_t* cam_idx, const int32_t* pt_idx, int64_t n, int32_t n_cam,
+                                int32_t n_pt, int* bad) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t c = cam_idx[i], p = pt_idx[i];
+  if (c < 0 || c >= n_cam || p < 0 || p >= n_pt) *bad = 1;
+}
+
+__global__ void gather_i32(const int32_t* src, const int32_t* idx, int32_t* dst, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
+// off[k] = first position whose sorted key >= k, for k = 0..n_keys  (searchsorted, side=left)
+__global__ void lower_bound_kernel(const int32_t* __restrict__ sorted, int64_t n, int32_t* off, int64_t n_keys) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k > n_keys) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (sorted[mid] < (int32_t)k) lo = mid + 1; else hi = mid;
+  }
+  off[k] = (int32_t)lo;
+}
+
+// pairs emitted by sorted position a: every b > a of the same point; twice if same camera.
+__global__ void pair_count_kernel(const int32_t* __restrict__ pt_of, const int32_t* __restrict__ cam_of,
+                                  const int32_t* __restrict__ pt_off, int64_t n, int64_t* cnt) {
+  int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  int32_t end = pt_off[pt_of[a] + 1];
+  int32_t ca = cam_of[a];
+  int64_t c = 0;
+  for (int32_t b = (int32_t)a + 1; b < end; ++b) c += (cam_of[b] == ca) ? 2 : 1;
+  cnt[a] = c;
+}
+
+__global__ void pair_fill_kernel(const int32_t* __restrict__ pt_of, const int32_t* __restrict__ cam_of,
+                                 const int32_t* __restrict__ pt_off, int64_t n, const int64_t* __restrict__ off,
+                                 int64_t n_cam, uint64_t* keys, uint64_t* vals) {
+  int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  int32_t end = pt_off[pt_of[a] + 1];
+  int64_t ca = cam_of[a];
+  int64_t o = off[a];
+  for (int32_t b = (int32_t)a + 1; b < end; ++b) {
+    int64_t cb = cam_of[b];
+    uint64_t ab = ((uint64_t)a << 32) | (uint32_t)b, ba = ((uint64_t)(uint32_t)b << 32) | (uint32_t)a;
+    if (ca < cb) { keys[o] = (uint64_t)(ca * n_cam + cb); vals[o] = ab; ++o; }
+    else if (ca > cb) { keys[o] = (uint64_t)(cb * n_cam + ca); vals[o] = ba; ++o; }
+    else { keys[o] = (uint64_t)(ca * n_cam + cb); vals[o] = ab; ++o; keys[o] = (uint64_t)(ca * n_cam + cb); vals[o] = ba; ++o; }
+  }
+}
+
+// BSR entry keys: for each list u with i < j: (i, j) and (j, i); for each camera: (i, i).
+// tag: u*2 (upper) / u*2+1 (lower) for list entries, -(i+1) for diagonal entries.
+__global__ void bsr_keys_kernel(const uint64_t* __restrict__ list_key, int64_t n_lists, int64_t n_cam,
+                                uint64_t* keys, int64_t* tags) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n_lists) {
+    uint64_t k = list_key[t];
+    uint64_t i = k / (uint64_t)n_cam, j = k % (uint64_t)n_cam;
+    if (i != j) {
+      keys[2 * t] = k; tags[2 * t] = 2 * t;
+      keys[2 * t + 1] = j * (uint64_t)n_cam + i; tags[2 * t + 1] = 2 * t + 1;
+    } else {  // diagonal list: no BSR entry of its own (sorts past every real key, dropped)
+      keys[2 * t] = ~0ull; tags[2 * t] = 0;
+      keys[2 * t + 1] = ~0ull; tags[2 * t + 1] = 0;
+    }
+  } else if (t < n_lists + n_cam) {
+    int64_t i = t - n_lists;
+    keys[n_lists + t] = (uint64_t)i * (uint64_t)n_cam + (uint64_t)i;
+    tags[n_lists + t] = -(i + 1);
+  }
+}
+
+__global__ void count_valid_kernel(const uint64_t* __restrict__ keys, int64_t n, unsigned long long* count) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n && keys[t] != ~0ull) atomicAdd(count, 1ull);  // set-up only; integer, order-free
+}
+
+__global__ void bsr_scatter_kernel(const uint64_t* __restrict__ keys, const int64_t* __restrict__ tags, int64_t nnzb,
+                                   int64_t n_cam, int32_t* col_idx, int32_t* row_of, int32_t* list_slot,
+                                   int32_t* list_slot_t, int32_t* diag_slot) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nnzb) return;
+  uint64_t k = keys[e];
+  col_idx[e] = (int32_t)(k % (uint64_t)n_cam);
+  row_of[e] = (int32_t)(k / (uint64_t)n_cam);
+  int64_t tag = tags[e];
+  if (tag < 0) diag_slot[-tag - 1] = (int32_t)e;
+  else if (tag & 1) list_slot_t[tag >> 1] = (int32_t)e;
+  else list_slot[tag >> 1] = (int32_t)e;
+}
+
+__global__ void diag_list_slot_kernel(const uint64_t* __restrict__ list_key, int64_t n_lists, int64_t n_cam,
+                                      const int32_t* __restrict__ diag_slot, int32_t* list_slot, int32_t* list_slot_t) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_lists) return;
+  uint64_t k = list_key[t];
+  uint64_t i = k / (uint64_t)n_cam, j = k % (uint64_t)n_cam;
+  if (i == j) { list_slot[t] = diag_slot[i]; list_slot_t[t] = -1; }
+}
+
+int bits_for(uint64_t max_value) {
+  int b = 1;
+  while (b < 64 && (max_value >> b) != 0) ++b;
+  return b;
+}
+
+template <typename K, typename V>
+void sort_pairs(const K* k_in, K* k_out, const V* v_in, V* v_out, int64_t n, int end_bit, cudaStream_t s) {
+  size_t bytes = 0;
+  ISFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k_in, k_out, v_in, v_out, n, 0, end_bit, s));
+  DeviceBuffer<uint8_t> tmp;
+  tmp.alloc(bytes);
+  ISFM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), bytes, k_in, k_out, v_in, v_out, n, 0, end_bit, s));
+  ISFM_CUDA(cudaStreamSynchronize(s));  // tmp is freed at scope exit
+}
+
+}  // namespace
+
+void build_obs_index(ObsIndex& ix, int64_t n_cam, int64_t n_pt, int64_t n_obs, const int32_t* cam_idx,
+                     const int32_t* pt_idx, cudaStream_t s, KernelTimers& kt) {
+  ISFM_REQUIRE(n_cam > 0 && n_pt > 0 && n_obs > 0, ISFM_EINVAL, "empty problem");
+  ISFM_REQUIRE(n_obs < (1ll << 31) && n_pt < (1ll << 31) && n_cam < (1ll << 31), ISFM_EINVAL, "sizes must fit int32");
+  ix.n_cam = n_cam; ix.n_pt = n_pt; ix.n_obs = n_obs;
+  TimerScope ts(kt, T_INDEX_PREP);
+  const int g = div_up(n_obs, TPB);
+  DeviceBuffer<int> bad; bad.alloc(1); bad.zero(s);
+  validate_kernel<<<g, TPB, 0, s>>>(cam_idx, pt_idx, n_obs, (int32_t)n_cam, (int32_t)n_pt, bad.get());
+  int h_bad = 0;
+  ISFM_CUDA(cudaMemcpyAsync(&h_bad, bad.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
+  ISFM_CUDA(cudaStreamSynchronize(s));
+  ISFM_REQUIRE(h_bad == 0, ISFM_EINVAL, "camera / point index out of range");
+
+  DeviceBuffer<int32_t> iota, tmp_keys;
+  iota.alloc(n_obs); tmp_keys.alloc(n_obs);
+  iota_kernel<<<g, TPB, 0, s>>>(iota.get(), n_obs);
+  // stable sort by point
+  ix.obs_perm.alloc(n_obs); ix.pt_of.alloc(n_obs); ix.cam_of.alloc(n_obs);
+  sort_pairs(pt_idx, ix.pt_of.get(), iota.get(), ix.obs_perm.get(), n_obs, bits_for((uint64_t)n_pt), s);
+  gather_i32<<<g, TPB, 0, s>>>(cam_idx, ix.obs_perm.get(), ix.cam_of.get(), n_obs);
+  ix.pt_off.alloc(n_pt + 1);
+  lower_bound_kernel<<<div_up(n_pt + 1, TPB), TPB, 0, s>>>(ix.pt_of.get(), n_obs, ix.pt_off.get(), n_pt);
+  // stable sort of the point-major positions by camera
+  ix.cam_perm.alloc(n_obs);
+  sort_pairs(ix.cam_of.get(), tmp_keys.get(), iota.get(), ix.cam_perm.get(), n_obs, bits_for((uint64_t)n_cam), s);
+  ix.cam_off.alloc(n_cam + 1);
+  lower_bound_kernel<<<div_up(n_cam + 1, TPB), TPB, 0, s>>>(tmp_keys.get(), n_obs, ix.cam_off.get(), n_cam);
+  ISFM_CUDA(cudaGetLastError());
+  ISFM_CUDA(cudaStreamSynchronize(s));
+}
+
+void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, KernelTimers& kt) {
+  TimerScope ts(kt, T_INDEX_PREP);
+  const int64_t n = ix.n_obs, n_cam = ix.n_cam;
+  const int g = div_up(n, TPB);
+  // 1. pair counts -> offsets
+  DeviceBuffer<int64_t> cnt, off;
+  cnt.alloc(n + 1); off.alloc(n + 1);
+  ISFM_CUDA(cudaMemsetAsync(cnt.get(), 0, (n + 1) * sizeof(int64_t), s));
+  pair_count_kernel<<<g, TPB, 0, s>>>(ix.pt_of.get(), ix.cam_of.get(), ix.pt_off.get(), n, cnt.get());
+  {
+    size_t bytes = 0;
+    ISFM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt.get(), off.get(), n + 1, s));
+    DeviceBuffer<uint8_t> tmp; tmp.alloc(bytes);
+    ISFM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.get(), bytes, cnt.get(), off.get(), n + 1, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));
+  }
+  int64_t n_pairs = 0;
+  ISFM_CUDA(cudaMemcpyAsync(&n_pairs, off.get() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  ISFM_CUDA(cudaStreamSynchronize(s));
+  sp.n_pairs = n_pairs;
+  // 2. fill + sort by block key
+  DeviceBuffer<uint64_t> keys, vals, keys_s;
+  keys.alloc(n_pairs); vals.alloc(n_pairs); keys_s.alloc(n_pairs); sp.pairs.alloc(n_pairs);
+  pair_fill_kernel<<<g, TPB, 0, s>>>(ix.pt_of.get(), ix.cam_of.get(), ix.pt_off.get(), n, off.get(), n_cam,
+                                     keys.get(), vals.get());
+  cnt.release(); off.release();
+  int64_t n_lists = 0;
+  DeviceBuffer<uint64_t> list_key;
+  if (n_pairs > 0) {
+    sort_pairs(keys.get(), keys_s.get(), vals.get(), sp.pairs.get(), n_pairs,
+               bits_for((uint64_t)n_cam * (uint64_t)n_cam), s);
+    keys.release(); vals.release();
+    // 3. run-length encode -> lists
+    DeviceBuffer<int64_t> run_len; DeviceBuffer<int64_t> n_runs;
+    list_key.alloc(n_pairs); run_len.alloc(n_pairs + 1); n_runs.alloc(1);
+    size_t bytes = 0;
+    ISFM_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, bytes, keys_s.get(), list_key.get(), run_len.get(),
+                                                 n_runs.get(), n_pairs, s));
+    {
+      DeviceBuffer<uint8_t> tmp; tmp.alloc(bytes);
+      ISFM_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.get(), bytes, keys_s.get(), list_key.get(), run_len.get(),
+                                                   n_runs.get(), n_pairs, s));
+      ISFM_CUDA(cudaMemcpyAsync(&n_lists, n_runs.get(), sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+      ISFM_CUDA(cudaStreamSynchronize(s));
+    }
+    keys_s.release();
+    sp.list_off.alloc(n_lists + 1);
+    ISFM_CUDA(cudaMemsetAsync(run_len.get() + n_lists, 0, sizeof(int64_t), s));
+    ISFM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, run_len.get(), sp.list_off.get(), n_lists + 1, s));
+    DeviceBuffer<uint8_t> tmp; tmp.alloc(bytes);
+    ISFM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.get(), bytes, run_len.get(), sp.list_off.get(), n_lists + 1, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));
+  } else {
+    sp.list_off.alloc(1);
+    ISFM_CUDA(cudaMemsetAsync(sp.list_off.get(), 0, sizeof(int64_t), s));
+  }
+  sp.n_lists = n_lists;
+  // 4. BSR pattern: both triangles + all diagonal blocks
+  const int64_t n_ent = 2 * n_lists + n_cam;
+  DeviceBuffer<uint64_t> ekeys, ekeys_s; DeviceBuffer<int64_t> etags, etags_s;
+  ekeys.alloc(n_ent); ekeys_s.alloc(n_ent); etags.alloc(n_ent); etags_s.alloc(n_ent);
+  bsr_keys_kernel<<<div_up(n_lists + n_cam, TPB), TPB, 0, s>>>(list_key.get(), n_lists, n_cam, ekeys.get(), etags.get());
+  sort_pairs(ekeys.get(), ekeys_s.get(), etags.get(), etags_s.get(), n_ent, 64, s);
+  DeviceBuffer<unsigned long long> valid; valid.alloc(1); valid.zero(s);
+  count_valid_kernel<<<div_up(n_ent, TPB), TPB, 0, s>>>(ekeys_s.get(), n_ent, valid.get());
+  unsigned long long nnzb = 0;
+  ISFM_CUDA(cudaMemcpyAsync(&nnzb, valid.get(), sizeof(nnzb), cudaMemcpyDeviceToHost, s));
+  ISFM_CUDA(cudaStreamSynchronize(s));
+  ISFM_REQUIRE(nnzb < (1ull << 31), ISFM_EINVAL, "reduced camera system has too many blocks for int32 slots");
+  sp.nnzb = (int64_t)nnzb;
+  sp.col_idx.alloc(nnzb); sp.row_ptr.alloc(n_cam + 1); sp.diag_slot.alloc(n_cam);
+  sp.list_slot.alloc(n_lists); sp.list_slot_t.alloc(n_lists);
+  DeviceBuffer<int32_t> row_of; row_of.alloc(nnzb);
+  bsr_scatter_kernel<<<div_up(nnzb, TPB), TPB, 0, s>>>(ekeys_s.get(), etags_s.get(), (int64_t)nnzb, n_cam, sp.col_idx.get(),
+                                                       row_of.get(), sp.list_slot.get(), sp.list_slot_t.get(),
+                                                       sp.diag_slot.get());
+  lower_bound_kernel<<<div_up(n_cam + 1, TPB), TPB, 0, s>>>(row_of.get(), (int64_t)nnzb, sp.row_ptr.get(), n_cam);
+  if (n_lists > 0)
+    diag_list_slot_kernel<<<div_up(n_lists, TPB), TPB, 0, s>>>(list_key.get(), n_lists, n_cam, sp.diag_slot.get(),
+                                                               sp.list_slot.get(), sp.list_slot_t.get());
+  ISFM_CUDA(cudaGetLastError());
+  ISFM_CUDA(cudaStreamSynchronize(s));
+}
+
+}  // namespace isfm

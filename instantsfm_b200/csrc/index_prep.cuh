@@ -1,0 +1,42 @@
+// index_prep.cuh -- integer preparation (I1): stable sorts of the observations by point and
+// by camera, CSR offsets, the (a, b) observation-pair lists that feed every off-diagonal
+// block of the reduced camera system, and its BSR pattern.  Replaces torch.unique / bae's
+// index tracing (bundle_adjustment.py:108-109).  Everything here is bit-exact testable
+// against numpy (stable argsort, searchsorted).
+#pragma once
+#include "common.cuh"
+
+namespace isfm {
+
+struct ObsIndex {
+  int64_t n_cam = 0, n_pt = 0, n_obs = 0;
+  // point-major order ("sorted position" a = 0..n_obs-1)
+  DeviceBuffer<int32_t> obs_perm;   // [n_obs] sorted position -> original observation
+  DeviceBuffer<int32_t> pt_of;      // [n_obs] point of sorted position (non-decreasing)
+  DeviceBuffer<int32_t> cam_of;     // [n_obs] camera of sorted position
+  DeviceBuffer<int32_t> pt_off;     // [n_pt + 1]
+  // camera-major view
+  DeviceBuffer<int32_t> cam_perm;   // [n_obs] camera-major rank -> sorted position
+  DeviceBuffer<int32_t> cam_off;    // [n_cam + 1]
+};
+
+// Reduced camera system pattern: lists of observation pairs grouped by upper block (i <= j).
+struct SchurPattern {
+  int64_t n_pairs = 0;   // total (a, b) pairs
+  int64_t n_lists = 0;   // unique (i, j), i <= j, with at least one pair
+  int64_t nnzb = 0;      // BSR blocks, both triangles + every diagonal block
+  DeviceBuffer<uint64_t> pairs;      // [n_pairs] (a << 32) | b, cam(a) <= cam(b), grouped by list
+  DeviceBuffer<int64_t> list_off;    // [n_lists + 1]
+  DeviceBuffer<int32_t> list_slot;   // [n_lists] BSR slot of block (i, j)
+  DeviceBuffer<int32_t> list_slot_t; // [n_lists] BSR slot of block (j, i), -1 for diagonal lists
+  DeviceBuffer<int32_t> row_ptr;     // [n_cam + 1]
+  DeviceBuffer<int32_t> col_idx;     // [nnzb]
+  DeviceBuffer<int32_t> diag_slot;   // [n_cam]
+};
+
+// cam_idx / pt_idx: device int32 [n_obs] in the caller's order.
+void build_obs_index(ObsIndex& ix, int64_t n_cam, int64_t n_pt, int64_t n_obs, const int32_t* cam_idx,
+                     const int32_t* pt_idx, cudaStream_t stream, KernelTimers& kt);
+void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t stream, KernelTimers& kt);
+
+}  // namespace isfm

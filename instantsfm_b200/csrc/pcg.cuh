@@ -1,0 +1,281 @@
+// pcg.cuh -- block-Jacobi preconditioned CG on the reduced camera system (K4).
+//
+//   S p = Hd p - E p
+//
+// Hd: damped block diagonal Hcc (replicated on every rank), E: this rank's Schur
+// contribution sum_p Hcp Hpp^-1 Hcp^T as BSR (both triangles).  With several ranks the only
+// communication per iteration is the all-reduce of y = E p; every rank holds the full
+// vectors and computes the dot products redundantly (bit-identical across ranks).
+// Replaces bae.utils.pysolvers.PCG (bundle_adjustment.py:117): x0 = 0, stop when
+// ||r|| < tol ||b||.
+#pragma once
+#include "comm.cuh"
+#include "common.cuh"
+
+namespace isfm {
+
+struct PcgState {
+  double rho[2];   // r.z, double-buffered by iteration parity
+  double bb;       // ||b||^2
+  double rr;       // ||r||^2 after the last completed iteration
+  int done;        // 1: converged, 2: breakdown (non-finite / non-positive curvature)
+  int iters;
+};
+
+constexpr int PCG_TPB = 128;
+
+// y_i = sum_j E_ij p_j ; one CTA per block row.  FUSED (single rank): q_i = Hd_i p_i - y_i
+// and the per-row partial of p.q.
+template <typename T, int D, bool FUSED>
+__global__ void __launch_bounds__(PCG_TPB)
+pcg_spmv_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                const T* __restrict__ E, const T* __restrict__ Hd, const T* __restrict__ p, T* __restrict__ out,
+                double* __restrict__ partial, const PcgState* __restrict__ st) {
+  if (st->done) return;
+  constexpr int BPW = 32 / D;          // blocks per warp iteration
+  constexpr int NW = PCG_TPB / 32;
+  __shared__ T sh[NW][D];
+  const int row = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int bl = lane / D, r = lane % D;
+  T acc = T(0);
+  if (bl < BPW) {
+    const int beg = row_ptr[row], end = row_ptr[row + 1];
+    for (int b = beg + w * BPW + bl; b < end; b += NW * BPW) {
+      const T* __restrict__ e = E + (size_t)b * (D * D) + r * D;
+      const T* __restrict__ pj = p + (size_t)col_idx[b] * D;
+#pragma unroll
+      for (int c = 0; c < D; ++c) acc += e[c] * pj[c];
+    }
+  }
+  // fold the BPW block lanes of this warp onto lanes 0..D-1
+#pragma unroll
+  for (int k = 1; k < BPW; ++k) {
+    T o = __shfl_sync(0xffffffffu, acc, (lane + k * D) & 31);
+    if (lane < D) acc += o;
+  }
+  if (lane < D) sh[w][lane] = acc;
+  __syncthreads();
+  if (threadIdx.x < D) {
+    T y = T(0);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) y += sh[k][threadIdx.x];
+    if (FUSED) {
+      const T* __restrict__ h = Hd + (size_t)row * (D * D) + threadIdx.x * D;
+      const T* __restrict__ pi = p + (size_t)row * D;
+      T q = T(0);
+#pragma unroll
+      for (int c = 0; c < D; ++c) q += h[c] * pi[c];
+      q -= y;
+      out[(size_t)row * D + threadIdx.x] = q;
+      sh[0][threadIdx.x] = q * pi[threadIdx.x];
+    } else {
+      out[(size_t)row * D + threadIdx.x] = y;
+    }
+  }
+  if (FUSED) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) s += (double)sh[0][c];
+      partial[row] = s;
+    }
+  }
+}
+
+// multi-rank second half: q = Hd p - y (y all-reduced), per-row partial of p.q
+template <typename T, int D>
+__global__ void pcg_apply_diag_kernel(int n_cam, const T* __restrict__ Hd, const T* __restrict__ p,
+                                      const T* __restrict__ y, T* __restrict__ q, double* __restrict__ partial,
+                                      const PcgState* __restrict__ st) {
+  if (st->done) return;
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_cam) return;
+  const T* h = Hd + (size_t)row * (D * D);
+  const T* pi = p + (size_t)row * D;
+  double s = 0.0;
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+    T v = T(0);
+#pragma unroll
+    for (int c = 0; c < D; ++c) v += h[r * D + c] * pi[c];
+    v -= y[(size_t)row * D + r];
+    q[(size_t)row * D + r] = v;
+    s += (double)v * (double)pi[r];
+  }
+  partial[row] = s;
+}
+
+// r0 = b, x0 = 0, z0 = Minv r0, p0 = z0; partials of (r.z, b.b) per camera
+template <typename T, int D>
+__global__ void pcg_init_kernel(int n_cam, const T* __restrict__ b, const T* __restrict__ Minv, T* __restrict__ x,
+                                T* __restrict__ r, T* __restrict__ p, double* __restrict__ part_rz,
+                                double* __restrict__ part_bb) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_cam) return;
+  const T* m = Minv + (size_t)row * (D * D);
+  T rv[D];
+  double bb = 0.0, rz = 0.0;
+#pragma unroll
+  for (int c = 0; c < D; ++c) { rv[c] = b[(size_t)row * D + c]; bb += (double)rv[c] * (double)rv[c]; }
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    T z = T(0);
+#pragma unroll
+    for (int c = 0; c < D; ++c) z += m[k * D + c] * rv[c];
+    x[(size_t)row * D + k] = T(0);
+    r[(size_t)row * D + k] = rv[k];
+    p[(size_t)row * D + k] = z;
+    rz += (double)z * (double)rv[k];
+  }
+  part_rz[row] = rz;
+  part_bb[row] = bb;
+}
+
+template <int D>
+__global__ void pcg_init_state_kernel(int n, const double* __restrict__ part_rz, const double* __restrict__ part_bb,
+                                      PcgState* st) {
+  double rz = reduce_partials(part_rz, n);
+  double bb = reduce_partials(part_bb, n);
+  if (threadIdx.x == 0) {
+    st->rho[0] = rz; st->rho[1] = 0.0; st->bb = bb; st->rr = bb; st->iters = 0;
+    st->done = (bb == 0.0) ? 1 : ((isfinite(rz) && isfinite(bb)) ? 0 : 2);
+  }
+}
+
+// alpha = rho / (p.q); x += alpha p; r -= alpha q; z = Minv r; partials of r.z and r.r
+template <typename T, int D>
+__global__ void __launch_bounds__(PCG_TPB)
+pcg_update_kernel(int n_cam, int n_part_pq, int it, const double* __restrict__ part_pq, const T* __restrict__ Minv,
+                  const T* __restrict__ p, const T* __restrict__ q, T* __restrict__ x, T* __restrict__ r,
+                  T* __restrict__ z, double* __restrict__ part_rz, double* __restrict__ part_rr,
+                  const PcgState* __restrict__ st) {
+  if (st->done) return;
+  const double pq = reduce_partials(part_pq, n_part_pq);
+  const double alpha_d = st->rho[it & 1] / pq;
+  const T alpha = (T)alpha_d;
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  double rz = 0.0, rr = 0.0;
+  if (row < n_cam) {
+    const T* m = Minv + (size_t)row * (D * D);
+    T rv[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      size_t o = (size_t)row * D + c;
+      x[o] += alpha * p[o];
+      rv[c] = r[o] - alpha * q[o];
+      r[o] = rv[c];
+      rr += (double)rv[c] * (double)rv[c];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      T zz = T(0);
+#pragma unroll
+      for (int c = 0; c < D; ++c) zz += m[k * D + c] * rv[c];
+      z[(size_t)row * D + k] = zz;
+      rz += (double)zz * (double)rv[k];
+    }
+  }
+  rz = block_sum(rz);
+  rr = block_sum(rr);
+  if (threadIdx.x == 0) { part_rz[blockIdx.x] = rz; part_rr[blockIdx.x] = rr; }
+}
+
+// beta = rho_new / rho; p = z + beta p; block 0 publishes the new state
+template <typename T, int D>
+__global__ void __launch_bounds__(PCG_TPB)
+pcg_direction_kernel(int n_cam, int n_part, int n_part_pq, int it, double tol2, const double* __restrict__ part_rz,
+                     const double* __restrict__ part_rr, const double* __restrict__ part_pq,
+                     const T* __restrict__ z, T* __restrict__ p, PcgState* st) {
+  if (st->done) return;
+  const double rho_new = reduce_partials(part_rz, n_part);
+  const double rr = reduce_partials(part_rr, n_part);
+  const double rho = st->rho[it & 1];
+  const T beta = (T)(rho_new / rho);
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < n_cam) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      size_t o = (size_t)row * D + c;
+      p[o] = z[o] + beta * p[o];
+    }
+  }
+  if (blockIdx.x == 0) {
+    const double pq = reduce_partials(part_pq, n_part_pq);
+    if (threadIdx.x == 0) {
+      st->rho[(it + 1) & 1] = rho_new;
+      st->rr = rr;
+      st->iters = it + 1;
+      // `done` is read at kernel entry by every block of the NEXT launch only
+      if (!(isfinite(rho_new) && isfinite(rr)) || !(pq > 0.0)) st->done = 2;
+      else if (rr < tol2 * st->bb) st->done = 1;
+    }
+  }
+}
+
+template <typename T, int D>
+struct BlockPCG {
+  int n_cam = 0;
+  DeviceBuffer<T> x, r, z, p, q, y;
+  DeviceBuffer<double> part_pq, part_a, part_b;
+  DeviceBuffer<PcgState> state;
+  PcgState* h_state = nullptr;  // pinned
+
+  ~BlockPCG() { if (h_state) cudaFreeHost(h_state); }
+
+  void resize(int n) {
+    n_cam = n;
+    size_t len = (size_t)n * D;
+    x.alloc(len); r.alloc(len); z.alloc(len); p.alloc(len); q.alloc(len); y.alloc(len);
+    part_pq.alloc(n); part_a.alloc(n); part_b.alloc(n);
+    state.alloc(1);
+    if (!h_state) ISFM_CUDA(cudaMallocHost(&h_state, sizeof(PcgState)));
+  }
+
+  // Solves S x = b.  Returns iterations; result in x.  status: 1 converged, 0 hit max_iter,
+  // 2 breakdown.
+  int solve(const int32_t* row_ptr, const int32_t* col_idx, const T* E, const T* Hd, const T* Minv, const T* b,
+            double tol, int max_iter, isfm_comm* comm, cudaStream_t s, KernelTimers& kt, int* status_out) {
+    const int nb = div_up(n_cam, PCG_TPB);
+    const bool multi = comm_world(comm) > 1;
+    { TimerScope ts(kt, T_PCG_VEC);
+      pcg_init_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, b, Minv, x.get(), r.get(), p.get(), part_a.get(), part_b.get()); }
+    { TimerScope ts(kt, T_PCG_VEC);
+      pcg_init_state_kernel<D><<<1, 256, 0, s>>>(n_cam, part_a.get(), part_b.get(), state.get()); }
+    const int check_every = 8;
+    const double tol2 = tol * tol;
+    int it = 0;
+    h_state->done = 0; h_state->iters = 0;
+    while (it < max_iter) {
+      int chunk = std::min(check_every, max_iter - it);
+      for (int k = 0; k < chunk; ++k, ++it) {
+        if (!multi) {
+          TimerScope ts(kt, T_PCG_SPMV);
+          pcg_spmv_kernel<T, D, true><<<n_cam, PCG_TPB, 0, s>>>(row_ptr, col_idx, E, Hd, p.get(), q.get(), part_pq.get(), state.get());
+        } else {
+          { TimerScope ts(kt, T_PCG_SPMV);
+            pcg_spmv_kernel<T, D, false><<<n_cam, PCG_TPB, 0, s>>>(row_ptr, col_idx, E, Hd, p.get(), y.get(), part_pq.get(), state.get()); }
+          { TimerScope ts(kt, T_COMM);
+            comm_allreduce_sum(comm, y.get(), (size_t)n_cam * D, sizeof(T) == 8, s); }
+          { TimerScope ts(kt, T_PCG_VEC);
+            pcg_apply_diag_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, Hd, p.get(), y.get(), q.get(), part_pq.get(), state.get()); }
+        }
+        { TimerScope ts(kt, T_PCG_VEC);
+          pcg_update_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, n_cam, it, part_pq.get(), Minv, p.get(), q.get(), x.get(),
+                                                        r.get(), z.get(), part_a.get(), part_b.get(), state.get()); }
+        { TimerScope ts(kt, T_PCG_VEC);
+          pcg_direction_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, nb, n_cam, it, tol2, part_a.get(), part_b.get(),
+                                                           part_pq.get(), z.get(), p.get(), state.get()); }
+      }
+      ISFM_CUDA(cudaMemcpyAsync(h_state, state.get(), sizeof(PcgState), cudaMemcpyDeviceToHost, s));
+      ISFM_CUDA(cudaStreamSynchronize(s));
+      if (h_state->done) break;
+    }
+    ISFM_CUDA(cudaGetLastError());
+    if (status_out) *status_out = h_state->done;
+    return h_state->iters;
+  }
+};
+
+}  // namespace isfm

@@ -1,0 +1,280 @@
+"""GPU parity tests: the CUDA bundle-adjustment path, called through the C ABI, against the
+fp64 oracle on the same seeded inputs.  Tolerances: fp64 build ~1e-9 (same algorithm, same
+precision), fp32 product build 1e-4 relative (BASELINE.json north_star); integer structure
+bit-exact."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from instantsfm_b200.synthetic import make_ba_problem, N_INTR
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(a, dtype, **kw):
+    from instantsfm_b200.engine import BAEngine
+    eng = BAEngine(a.model_id, dtype=dtype, **kw)
+    eng.set_problem(a.camera_params, a.camera_pps, a.points_3d, a.points_2d, a.camera_indices, a.point_indices)
+    return eng
+
+
+def _oracle(a, **kw):
+    from oracle.ba import BAProblem
+    return BAProblem(a.model_id, a.camera_params, a.camera_pps, a.points_3d, a.points_2d, a.camera_indices,
+                     a.point_indices, **kw)
+
+
+def _shuffled(a, seed=0):
+    """Same problem with observations in random order (the library must sort them)."""
+    import copy
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(a.n_obs)
+    b = copy.copy(a)
+    b.points_2d, b.camera_indices, b.point_indices = a.points_2d[perm], a.camera_indices[perm], a.point_indices[perm]
+    return b
+
+
+def _weighted_blocks(pb, delta=1.0):
+    from oracle.lm import triggs_scale
+    r, Jc, Jp = pb.blocks()
+    w = triggs_scale(r, delta)
+    return r, r * w[:, None], Jc * w[:, None, None], Jp * w[:, None, None]
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def test_structure_bit_exact():
+    a = _shuffled(make_ba_problem(16, 700, 3500, seed=3), seed=1)
+    eng = _engine(a, np.float32)
+    s = eng.structure()
+    perm = np.argsort(a.point_indices, kind="stable")
+    assert np.array_equal(s["obs_perm"], perm.astype(np.int32))
+    assert np.array_equal(s["point_offsets"], np.searchsorted(a.point_indices[perm], np.arange(a.n_pt + 1)))
+    cam_sorted = a.camera_indices[perm]
+    cperm = np.argsort(cam_sorted, kind="stable")
+    assert np.array_equal(s["cam_perm"], cperm.astype(np.int32))
+    assert np.array_equal(s["cam_offsets"], np.searchsorted(cam_sorted[cperm], np.arange(a.n_cam + 1)))
+    # reduced-camera-system pattern == pattern of the co-visibility matrix
+    vis = sp.csr_matrix((np.ones(a.n_obs), (a.camera_indices, a.point_indices)), shape=(a.n_cam, a.n_pt))
+    cov = (vis @ vis.T).tocsr()
+    cov.sort_indices()
+    pat = eng.schur_pattern()
+    assert pat["nnzb"] == cov.nnz
+    assert np.array_equal(pat["row_ptr"], cov.indptr)
+    assert np.array_equal(pat["col_idx"], cov.indices)
+    k = np.bincount(a.point_indices, minlength=a.n_pt).astype(np.int64)
+    assert pat["n_pairs"] == int((k * (k - 1) // 2).sum())
+
+
+@pytest.mark.parametrize("model_id", sorted(N_INTR))
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 2e-4)])
+def test_linearize_all_models(model_id, dtype, tol):
+    a = _shuffled(make_ba_problem(8, 150, 600, seed=20 + model_id, model_id=model_id))
+    a.camera_pps = a.camera_pps + 2.5
+    if dtype == np.float32:  # compare at the fp32-rounded inputs
+        for f in ("camera_params", "camera_pps", "points_3d", "points_2d"):
+            setattr(a, f, getattr(a, f).astype(np.float32).astype(np.float64))
+    eng = _engine(a, dtype)
+    pb = _oracle(a)
+    r, R, Jc, Jp = _weighted_blocks(pb)
+    assert np.abs(eng.debug("residuals") - r).max() <= tol * max(1.0, np.abs(r).max()) * 50
+    assert _rel(eng.debug("jac_cam"), Jc) <= tol
+    assert _rel(eng.debug("jac_point"), Jp) <= tol
+    assert np.abs(eng.debug("weighted_res") - R).max() <= tol * max(1.0, np.abs(R).max()) * 50
+    rob, sq = eng.cost()
+    from oracle.lm import robust_cost
+    assert abs(rob - robust_cost(r, 1.0)) <= 10 * tol * robust_cost(r, 1.0)
+    assert abs(sq - (r * r).sum()) <= 10 * tol * (r * r).sum()
+
+
+def _normal_blocks(pb, mu, delta=1.0):
+    """Oracle-side Hpp, g_p, Hcc, g_c and the dense reduced system at damping mu."""
+    _, R, Jc, Jp = _weighted_blocks(pb, delta)
+    n_cam, n_pt, d = pb.n_cam, pb.n_pt, pb.d
+    Hpp = np.zeros((n_pt, 3, 3)); gp = np.zeros((n_pt, 3)); Hcc = np.zeros((n_cam, d, d)); gc = np.zeros((n_cam, d))
+    np.add.at(Hpp, pb.pi, np.einsum("nki,nkj->nij", Jp, Jp))
+    np.add.at(gp, pb.pi, np.einsum("nki,nk->ni", Jp, R))
+    np.add.at(Hcc, pb.ci, np.einsum("nki,nkj->nij", Jc, Jc))
+    np.add.at(gc, pb.ci, np.einsum("nki,nk->ni", Jc, R))
+    Hcp = np.einsum("nki,nkj->nij", Jc, Jp)   # [N, d, 3]
+
+    def damp(H):
+        H = H.copy()
+        idx = np.arange(H.shape[1])
+        H[:, idx, idx] = np.clip(H[:, idx, idx], 1e-6, 1e32) * mu
+        return H
+    Hpp_d, Hcc_d = damp(Hpp), damp(Hcc)
+    inv = np.linalg.inv(Hpp_d)
+    S = np.zeros((n_cam * d, n_cam * d))
+    for i in range(n_cam):
+        S[i * d:(i + 1) * d, i * d:(i + 1) * d] = Hcc_d[i]
+    W = np.einsum("nij,njk->nik", Hcp, inv[pb.pi])          # Hcp Hpp^-1
+    rhs = -gc.copy()
+    np.add.at(rhs, pb.ci, np.einsum("nij,nj->ni", W, gp[pb.pi]))
+    order = np.argsort(pb.pi, kind="stable")
+    off = np.searchsorted(pb.pi[order], np.arange(n_pt + 1))
+    for p in range(n_pt):
+        obs = order[off[p]:off[p + 1]]
+        for x in obs:
+            for y in obs:
+                i, j = pb.ci[x], pb.ci[y]
+                S[i * d:(i + 1) * d, j * d:(j + 1) * d] -= W[x] @ Hcp[y].T
+    return Hpp, gp, Hcc, gc, S, rhs.reshape(-1)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 2e-4)])
+def test_normal_equation_blocks_and_schur(dtype, tol):
+    a = _shuffled(make_ba_problem(7, 60, 260, seed=5))
+    if dtype == np.float32:
+        for f in ("camera_params", "camera_pps", "points_3d", "points_2d"):
+            setattr(a, f, getattr(a, f).astype(np.float32).astype(np.float64))
+    eng = _engine(a, dtype)
+    pb = _oracle(a)
+    mu = 1.0 + 1e-4
+    Hpp, gp, Hcc, gc, S, rhs = _normal_blocks(pb, mu)
+    hpp = eng.debug("hpp")
+    ref6 = np.stack([Hpp[:, 0, 0], Hpp[:, 0, 1], Hpp[:, 0, 2], Hpp[:, 1, 1], Hpp[:, 1, 2], Hpp[:, 2, 2]], 1)
+    assert _rel(hpp, ref6) <= tol
+    assert _rel(eng.debug("gp"), gp) <= tol
+    assert _rel(eng.debug("hcc"), Hcc) <= tol
+    assert _rel(eng.debug("gc"), gc) <= tol
+    # Schur complement entries cancel (S = Hcc - E): compare relative to |Hcc|
+    Sg = eng.debug("schur_dense")
+    assert np.abs(Sg - S).max() <= tol * np.abs(Hcc).max()
+    assert np.abs(Sg - Sg.T).max() <= tol * np.abs(Hcc).max()
+    assert np.abs(eng.debug("schur_rhs") - rhs).max() <= tol * max(np.abs(gc).max(), np.abs(rhs).max())
+
+
+def test_duplicate_camera_in_track_is_handled():
+    """A track that sees the same image twice contributes to the diagonal block twice."""
+    a = make_ba_problem(6, 40, 160, seed=9)
+    a.camera_indices = a.camera_indices.copy()
+    first = np.searchsorted(a.point_indices, np.arange(a.n_pt))
+    a.camera_indices[first[:10] + 1] = a.camera_indices[first[:10]]   # duplicate camera in 10 tracks
+    eng = _engine(a, np.float64)
+    pb = _oracle(a)
+    _, _, Hcc, _, S, rhs = _normal_blocks(pb, 1.0 + 1e-4)
+    assert np.abs(eng.debug("schur_dense") - S).max() <= 1e-9 * np.abs(Hcc).max()
+    assert np.abs(eng.debug("schur_rhs") - rhs).max() <= 1e-9 * np.abs(rhs).max()
+
+
+def test_first_step_matches_direct_solve_fp64():
+    from oracle.ba import make_optimizer
+    a = _shuffled(make_ba_problem(10, 300, 1500, seed=11))
+    eng = _engine(a, np.float64, pcg_tol=1e-13, pcg_max_iter=2000)
+    pb = _oracle(a)
+    opt = make_optimizer(pb, 1.0, solver="direct")
+    cam0, pts0 = pb.cam.copy(), pb.pts.copy()
+    ref_loss = opt.step()
+    loss, st = eng.step()
+    assert st["trials"] == len(opt.trace[0]["trials"])
+    assert abs(loss - ref_loss) <= 1e-9 * ref_loss
+    assert abs(st["loss_before"] - opt.trace[0]["loss_before"]) <= 1e-10 * ref_loss
+    cam, pts = eng.get_params()
+    assert np.abs(cam - pb.cam).max() <= 1e-8
+    assert np.abs(pts - pb.pts).max() <= 1e-7
+    assert abs(st["quality"] - opt.trace[0]["trials"][-1]["quality"]) <= 1e-6
+    # the step itself
+    Dp = eng.debug("step_point")
+    assert np.abs(Dp - (pb.pts - pts0)).max() <= 1e-7
+
+
+@pytest.mark.parametrize("dtype,tol,pcg_tol", [(np.float64, 1e-8, 1e-12), (np.float32, 1e-4, 1e-6)])
+def test_trajectory_matches_oracle(dtype, tol, pcg_tol):
+    from oracle.ba import make_optimizer
+    a = make_ba_problem(24, 1500, 8000, seed=13)
+    eng = _engine(a, dtype, pcg_tol=pcg_tol, pcg_max_iter=3000)
+    pb = _oracle(a)
+    opt = make_optimizer(pb, 1.0, solver="direct")
+    for it in range(12):
+        ref = opt.step()
+        loss, st = eng.step()
+        assert abs(loss - ref) <= tol * ref, (it, loss, ref)
+    cam, pts = eng.get_params()
+    rob, sq = eng.cost()
+    rmse = np.sqrt(sq / a.n_obs)
+    assert abs(rmse - pb.rmse()) <= tol * pb.rmse()
+    ptol = 1e-6 if dtype == np.float64 else 2e-3
+    assert np.abs(pts - pb.pts).max() <= ptol * np.abs(pb.pts).max()
+    assert np.abs(cam - pb.cam).max() <= ptol * np.abs(pb.cam).max()
+
+
+def test_reference_pcg_tolerance_stays_within_1e4():
+    """Product settings (fp32, PCG tol 1e-5 like the reference) vs the oracle run the
+    reference's way (full system, Jacobi PCG tol 1e-5)."""
+    from oracle.ba import make_optimizer
+    a = make_ba_problem(24, 1500, 8000, seed=17)
+    eng = _engine(a, np.float32)
+    pb = _oracle(a)
+    opt = make_optimizer(pb, 1.0, solver="pcg", pcg_tol=1e-5)
+    for it in range(10):
+        ref = opt.step()
+        loss, _ = eng.step()
+        assert abs(loss - ref) <= 1e-4 * ref, (it, loss, ref)
+
+
+def test_solve_loop_and_stop_rule():
+    from oracle.ba import solve_arrays
+    a = make_ba_problem(12, 500, 2600, seed=19)
+    opts = {"optimize_poses": True, "thres_loss_function": 1.0, "max_num_iterations": 60, "function_tolerance": 5e-4}
+    eng = _engine(a, np.float64, pcg_tol=1e-12)
+    hist = eng.solve(opts["max_num_iterations"], opts["function_tolerance"])
+    pb = _oracle(a)
+    ref_hist, _ = solve_arrays(pb, opts, solver="direct")
+    assert len(hist) == len(ref_hist)
+    np.testing.assert_allclose(hist, ref_hist, rtol=1e-7)
+
+
+def test_points_only_mode():
+    from oracle.ba import make_optimizer
+    a = make_ba_problem(10, 400, 2000, seed=23)
+    eng = _engine(a, np.float64, optimize_poses=False)
+    pb = _oracle(a, optimize_poses=False)
+    opt = make_optimizer(pb, 1.0, solver="direct")
+    for it in range(5):
+        ref = opt.step()
+        loss, st = eng.step()
+        assert abs(loss - ref) <= 1e-9 * ref
+        assert st["pcg_iters"] == 0
+    cam, pts = eng.get_params()
+    np.testing.assert_array_equal(cam, a.camera_params)
+    assert np.abs(pts - pb.pts).max() <= 1e-8
+
+
+def test_noise_free_problem_recovers_ground_truth():
+    a = make_ba_problem(12, 400, 2400, seed=29, noise_px=0.0, outlier_frac=0.0, perturb=0.3)
+    eng = _engine(a, np.float64, pcg_tol=1e-12)
+    hist = eng.solve(50, 1e-12)
+    rob, sq = eng.cost()
+    assert np.sqrt(sq / a.n_obs) < 1e-6
+    assert all(h2 <= h1 * (1 + 1e-12) for h1, h2 in zip(hist, hist[1:]))
+
+
+def test_device_tensors_accepted():
+    import torch
+    a = make_ba_problem(8, 200, 900, seed=31)
+    from instantsfm_b200.engine import BAEngine
+    dev = torch.device("cuda:0")
+    eng_d = BAEngine(a.model_id, dtype=np.float32)
+    eng_d.set_problem(*(torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in
+                        (a.camera_params, a.camera_pps, a.points_3d, a.points_2d, a.camera_indices, a.point_indices)))
+    eng_h = _engine(a, np.float32)
+    assert eng_d.step()[0] == eng_h.step()[0]
+
+
+def test_errors():
+    from instantsfm_b200.engine import BAEngine
+    from instantsfm_b200._lib import IsfmError
+    with pytest.raises(NotImplementedError):
+        BAEngine(7)
+    with pytest.raises(NotImplementedError):
+        BAEngine(10)
+    eng = BAEngine(3)
+    with pytest.raises(IsfmError):
+        eng.step()
+    a = make_ba_problem(8, 200, 900, seed=31)
+    bad = a.camera_indices.copy(); bad[5] = 99
+    with pytest.raises(IsfmError):
+        eng.set_problem(a.camera_params, a.camera_pps, a.points_3d, a.points_2d, bad, a.point_indices)
