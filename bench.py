@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Benchmark of the BA Levenberg-Marquardt hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3]
+
+A "step" is one LM iteration (`isfm_ba_step` == `optimizer.step(input)`,
+bundle_adjustment.py:132) on a synthetic BAL-shaped problem.  N = 1: config C3
+(Venice-shaped, 1 778 cameras / 993 k points / 5.0 M observations).  N > 1 (torchrun, one
+rank per GPU): weak scaling -- every rank owns a C3-sized shard of points over the same
+1 778 cameras, the ranks exchange the camera-system partial sums and the PCG mat-vecs over
+NCCL.  Prints ONE JSON line (rank 0).
+
+value       observations/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+e2e         same metric through the C ABI from pinned HOST buffers: create + set_problem
+            (H2D of every tensor + integer prep) + K steps + get_params (D2H), per rank
+roofline    dominant kernel family: algorithmic bytes / CUDA-event time
+cpu_baseline the oracle (restated reference algorithm, "port") on the host cores, bounded sample
+--impl reference  times that CPU port alone (bae / pypose are not installable)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ba_lm_observations_per_sec"
+UNIT = "obs/s"
+CPU_SAMPLE_SCALE = 0.02   # cpu_baseline: config with points/observations scaled by this factor
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons of one GPU during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def algorithmic_bytes(name, n_obs, n_pt, n_cam, d, n_pairs, n_lists, nnzb, fsize=4):
+    """Algorithmic HBM bytes of ONE launch of a kernel family."""
+    dd = d * d
+    table = {
+        "linearize": n_obs * (8 + 8 + fsize * (2 + 2 * d + 6)) + n_pt * 3 * fsize + n_cam * (9 + d) * fsize,
+        "point_blocks": n_obs * fsize * (6 + 2 + 6) + n_pt * (4 + fsize * (6 + 3 + 6 + 3)),
+        "point_solve": n_obs * fsize * (6 + 6) + n_pt * (4 + fsize * (6 + 3 + 6 + 3)),
+        # average of the H pass (idx 4, Jc, R) and the E pass (idx 8, Jc, V, Jp, t_p): reported per pass below
+        "camera_blocks": n_obs * (6 + fsize * (2 * d + 1 + 6 + 1.5)) + n_cam * fsize * (dd + d),
+        "schur_offdiag": n_pairs * (8 + fsize * (4 * d + 12)) + n_lists * (16 + 2 * dd * fsize),
+        "pcg_spmv": nnzb * (dd * fsize + 4) + n_cam * fsize * (dd + 3 * d),
+        "backsub": n_obs * (4 + fsize * (2 * d + 6 + 2)) + n_pt * fsize * (3 + 6 + 3 + 3 + 3),
+        "cost": n_obs * (8 + 8) + n_pt * 3 * fsize + n_cam * (9 + d) * fsize,
+    }
+    return float(table.get(name, 0.0))
+
+
+def run_cpu_port(config, n_steps, threads):
+    """The oracle run the reference's way (full system, Jacobi PCG tol 1e-5) on a bounded sample."""
+    import torch
+    from instantsfm_b200.synthetic import make_config
+    from oracle.ba import BAProblem, make_optimizer
+    torch.set_num_threads(threads)
+    a = make_config(config, scale=CPU_SAMPLE_SCALE)
+    pb = BAProblem(a.model_id, a.camera_params, a.camera_pps, a.points_3d, a.points_2d, a.camera_indices, a.point_indices)
+    opt = make_optimizer(pb, 1.0, solver="pcg", pcg_tol=1e-5)
+    opt.step()  # warm-up (first call pays torch / scipy import costs)
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        opt.step()
+    dt = time.perf_counter() - t0
+    sample = (f"{config} scaled x{CPU_SAMPLE_SCALE}: {a.n_cam} cameras / {a.n_pt} points / {a.n_obs} observations, "
+              f"{n_steps} LM steps of the fp64 torch/scipy oracle (full normal equations, Jacobi PCG 1e-5)")
+    return a.n_obs * n_steps / dt, dt / n_steps * 1e3, sample, a
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 3))
+    val, ms, sample, a = run_cpu_port(args.config, steps, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.config} BAL-shaped synthetic BA (reference arm: bounded CPU sample)", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "bae/pypose (where the reference's LM arithmetic lives) cannot be installed offline; "
+                    "this is the restated reference algorithm (oracle/) on the host cores"}
+    print(json.dumps(line))
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    from instantsfm_b200.engine import BAEngine, Communicator
+    from instantsfm_b200.synthetic import make_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = Communicator()
+    strong = args.scaling == "strong"
+    # weak: every rank owns one full config worth of points; strong: 1/world of them
+    a = make_config(args.config, scale=(1.0 if strong else float(world)) * args.scale, shard=(rank, world))
+    n_total = a.n_obs * world
+    d = a.camera_params.shape[1] - 1
+    dtype = np.float32
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    host = [np.ascontiguousarray(x, dtype=dtype) for x in (a.camera_params, a.camera_pps, a.points_3d, a.points_2d)]
+    host += [np.ascontiguousarray(a.camera_indices, np.int32), np.ascontiguousarray(a.point_indices, np.int32)]
+    pinned = [torch.from_numpy(h).pin_memory() for h in host]
+    pinned_np = [p.numpy() for p in pinned]
+
+    # ---- device-resident throughput ------------------------------------------------------
+    eng = BAEngine(a.model_id, dtype=dtype, comm=comm)
+    eng.set_problem(*pinned_np)
+    pat = eng.schur_pattern()
+    for _ in range(args.warmup):
+        eng.step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = eng.lib.isfm_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    losses, stats = [], []
+    for _ in range(args.steps):
+        loss, st = eng.step()
+        losses.append(loss); stats.append(st)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.lib.isfm_launch_count() - launches0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = n_total * args.steps / (ms_total * 1e-3)
+    rob, sq = eng.cost()
+    rmse = float(np.sqrt(sq / n_total))
+
+    # ---- per-kernel CUDA-event timing for the roofline (separate pass, timers on) ---------
+    eng.reset_timers(True)
+    prof_steps = max(2, min(args.steps, 5))
+    pcg_iters_prof = 0
+    for _ in range(prof_steps):
+        _, st = eng.step()
+        pcg_iters_prof += st["pcg_iters"]
+    timers = eng.timers()
+    eng.reset_timers(False)
+    peak, peak_src = _peaks()
+    kernels = {}
+    for name, t in timers.items():
+        if name in ("index_prep",) or t["launches"] == 0:
+            continue
+        per_launch_ms = t["ms"] / t["launches"]
+        ab = algorithmic_bytes(name, a.n_obs, a.n_pt, a.n_cam, d, pat["n_pairs"], (pat["nnzb"] - a.n_cam) // 2, pat["nnzb"])
+        kernels[name] = {"ms_per_step": t["ms"] / prof_steps, "launches_per_step": t["launches"] / prof_steps,
+                         "us_per_launch": per_launch_ms * 1e3,
+                         "achieved_gbs": (ab / (per_launch_ms * 1e-3) / 1e9) if ab and per_launch_ms > 0 else None}
+    top = max((k for k in kernels if kernels[k]["achieved_gbs"] is not None), key=lambda k: kernels[k]["ms_per_step"])
+    roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[top]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": kernels[top]["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values())}
+    eng.close()
+
+    # ---- end to end through the C ABI from pinned host buffers ---------------------------
+    barrier()
+    t0 = time.perf_counter()
+    eng2 = BAEngine(a.model_id, dtype=dtype, comm=comm)
+    eng2.set_problem(*pinned_np)
+    e2e_losses = [eng2.step()[0] for _ in range(args.steps)]
+    cam_out, pts_out = eng2.get_params()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_s = float(dt.item())
+    h2d = sum(h.nbytes for h in host)
+    d2h = cam_out.nbytes + pts_out.nbytes + 8 * args.steps
+    e2e = {"value": n_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+           "d2h_bytes_per_step": d2h / args.steps, "includes": "isfm_ba_create + set_problem (H2D, sort, Schur pattern) + "
+           f"{args.steps} steps + get_params (D2H), per rank", "seconds": e2e_s}
+    eng2.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        val, ms_cpu, sample, _ = run_cpu_port(args.config, 2, threads)
+        cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "ms_per_lm_step": ms_cpu}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.config} BAL-shaped synthetic BA, RADIAL cameras, per rank {a.n_cam} cameras / "
+                           f"{a.n_pt} points / {a.n_obs} observations" + (f" (x{world} ranks, cameras shared)" if world > 1 else ""),
+                           "total_observations": n_total, "l2_policy": "inputs larger than L2 (J blocks alone exceed 126 MB)",
+                           "pcg_tol": 1e-6, "schur_blocks": pat["nnzb"], "schur_pairs": pat["n_pairs"]},
+                "lm_iters_per_sec": args.steps / (ms_total * 1e-3), "final_rmse_px": rmse, "final_robust_cost": rob,
+                "pcg_iters_per_step": float(np.mean([s["pcg_iters"] for s in stats])),
+                "rejects": int(sum(s["rejects"] for s in stats)),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3", "C5"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink/grow points and observations (debug)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)

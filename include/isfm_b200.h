@@ -100,7 +100,10 @@ typedef struct isfm_ba_desc {
   double tr_max;
   double tr_up;
   double tr_down;
-  double pcg_tol;         /* PCG(tol=1e-5), bundle_adjustment.py:117                      */
+  double pcg_tol;         /* PCG(tol=1e-5), bundle_adjustment.py:117.  Default here 1e-6:
+                             the reference's 1e-5 is on the full Jacobi-scaled system; on
+                             the reduced camera system 1e-6 keeps the first (largest) LM
+                             step within 1e-4 of the reference's cost                     */
   int32_t pcg_max_iter;   /* 0 = default (10 * n_cam * d, as bae's PCG: 10 n)             */
   int32_t reserved;
   void* stream;           /* cudaStream_t                                                 */

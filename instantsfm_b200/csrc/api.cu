@@ -52,7 +52,7 @@ void isfm_ba_default_desc(isfm_ba_desc* d) {
   memset(d, 0, sizeof *d);
   d->dtype = 0; d->model_id = 3; d->optimize_poses = 1; d->reject = 30;
   d->huber_delta = 1.0; d->tr_radius = 1e4; d->tr_max = 1e10; d->tr_up = 2.0; d->tr_down = 0.0625;
-  d->pcg_tol = 1e-5; d->pcg_max_iter = 0;
+  d->pcg_tol = 1e-6; d->pcg_max_iter = 0;
 }
 
 int isfm_ba_create(const isfm_ba_desc* desc, isfm_ba** out) {
@@ -153,7 +153,7 @@ void isfm_gp_default_desc(isfm_gp_desc* d) {
   if (!d) return;
   memset(d, 0, sizeof *d);
   d->dtype = 0; d->reject = 30; d->huber_delta = 0.1; d->tr_radius = 1e3; d->tr_max = 1e8; d->tr_up = 2.0;
-  d->tr_down = 0.0625; d->pcg_tol = 1e-5; d->pcg_max_iter = 0; d->optimize_scales = 1;
+  d->tr_down = 0.0625; d->pcg_tol = 1e-6; d->pcg_max_iter = 0; d->optimize_scales = 1;
 }
 
 int isfm_gp_create(const isfm_gp_desc* desc, isfm_gp** out) {

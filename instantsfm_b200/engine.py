@@ -133,7 +133,7 @@ class BAEngine(_EngineBase):
     """Bundle adjustment LM (replaces ``bae.optim.LM`` over ``ReprojNonBatched``)."""
     _prefix = "ba"
 
-    def __init__(self, model_id, optimize_poses=True, huber_delta=1.0, dtype=np.float32, pcg_tol=1e-5,
+    def __init__(self, model_id, optimize_poses=True, huber_delta=1.0, dtype=np.float32, pcg_tol=1e-6,
                  pcg_max_iter=0, tr_radius=1e4, tr_max=1e10, tr_up=2.0, tr_down=0.5 ** 4, reject=30,
                  comm=None, stream=None):
         self.lib = _lib.load()
@@ -211,7 +211,7 @@ class GPEngine(_EngineBase):
     """Global positioning LM (replaces ``bae.optim.LM`` over ``PairwiseNonBatched``)."""
     _prefix = "gp"
 
-    def __init__(self, huber_delta=0.1, dtype=np.float32, pcg_tol=1e-5, pcg_max_iter=0, tr_radius=1e3, tr_max=1e8,
+    def __init__(self, huber_delta=0.1, dtype=np.float32, pcg_tol=1e-6, pcg_max_iter=0, tr_radius=1e3, tr_max=1e8,
                  tr_up=2.0, tr_down=0.5 ** 4, reject=30, optimize_scales=True, comm=None, stream=None):
         self.lib = _lib.load()
         self.dtype = np.dtype(dtype)

@@ -181,8 +181,11 @@ def _visibility(rng, n_cam, n_pt, n_obs, window, kmin=2):
 
 
 def make_ba_problem(n_cam, n_pt, n_obs, window=None, seed=0, model_id=3, noise_px=0.5,
-                    outlier_frac=0.01, perturb=1.0):
-    """Build a BAL-shaped problem; ``perturb`` scales the initial-state perturbation."""
+                    outlier_frac=0.01, perturb=1.0, point_seed=None):
+    """Build a BAL-shaped problem; ``perturb`` scales the initial-state perturbation.
+
+    ``point_seed``: draw points / visibility / noise from their own stream, so that several
+    ranks can generate disjoint point shards over the SAME cameras (multi-GPU bench)."""
     rng = np.random.default_rng(seed)
     window = n_cam if window is None else window
     pose_gt, _ = _orbit_cameras(rng, n_cam)
@@ -194,6 +197,14 @@ def make_ba_problem(n_cam, n_pt, n_obs, window=None, seed=0, model_id=3, noise_p
         intr_gt[:, nf:] = rng.normal(size=(n_cam, ni - nf)) * scales
     cam_gt = np.concatenate([pose_gt, intr_gt], 1)
     pps = np.zeros((n_cam, 2))                          # BAL convention
+    # perturbed initial cameras: rotation 0.5 deg rms, translation 1 % of scene scale (30), focal 1 %
+    cam0 = cam_gt.copy()
+    dq = rotvec_to_quat(rng.normal(scale=perturb * np.deg2rad(0.5) / np.sqrt(3), size=(n_cam, 3)))
+    cam0[:, 3:7] = quat_mul(dq, cam_gt[:, 3:7])
+    cam0[:, :3] += rng.normal(scale=perturb * 0.3 / np.sqrt(3), size=(n_cam, 3))
+    cam0[:, 7:7 + nf] *= 1 + rng.normal(scale=perturb * 0.01, size=(n_cam, nf))
+    if point_seed is not None:
+        rng = np.random.default_rng(point_seed)
     # points in a ball of radius 10 around the origin
     X = rng.normal(size=(n_pt, 3))
     X *= (10.0 * rng.uniform(0, 1, (n_pt, 1)) ** (1 / 3)) / np.linalg.norm(X, axis=1, keepdims=True)
@@ -205,24 +216,24 @@ def make_ba_problem(n_cam, n_pt, n_obs, window=None, seed=0, model_id=3, noise_p
     if n_out:
         which = rng.choice(obs.shape[0], size=n_out, replace=False)
         obs[which] += rng.uniform(-20, 20, size=(n_out, 2))
-    # perturbed initial state: rotation 0.5 deg rms, translation 1 % of scene scale (30),
-    # points 2 % of depth, focal 1 %
-    cam0 = cam_gt.copy()
-    dq = rotvec_to_quat(rng.normal(scale=perturb * np.deg2rad(0.5) / np.sqrt(3), size=(n_cam, 3)))
-    cam0[:, 3:7] = quat_mul(dq, cam_gt[:, 3:7])
-    cam0[:, :3] += rng.normal(scale=perturb * 0.3 / np.sqrt(3), size=(n_cam, 3))
-    cam0[:, 7:7 + nf] *= 1 + rng.normal(scale=perturb * 0.01, size=(n_cam, nf))
-    X0 = X + rng.normal(scale=perturb * 0.6 / np.sqrt(3), size=X.shape)
+    X0 = X + rng.normal(scale=perturb * 0.6 / np.sqrt(3), size=X.shape)   # 2 % of depth
     return BAArrays(model_id, cam0, pps, X0, obs, ci, pi, cam_gt, X)
 
 
-def make_config(name, scale=1.0, model_id=3):
-    """BASELINE.json config by name ('C1','C2','C3','C5'); ``scale`` < 1 shrinks points/obs."""
+def make_config(name, scale=1.0, model_id=3, shard=None):
+    """BASELINE.json config by name ('C1','C2','C3','C5'); ``scale`` shrinks / grows points and
+    observations (cameras fixed).  ``shard = (rank, world)``: this rank's share of the points
+    (1/world of them, own random stream) over the common cameras."""
     n_cam, n_pt, n_obs, window, seed = CONFIGS[name]
     if scale != 1.0:
         n_pt = max(int(n_pt * scale), 16)
         n_obs = max(int(n_obs * scale), 2 * n_pt)
-    return make_ba_problem(n_cam, n_pt, n_obs, window, seed, model_id)
+    point_seed = None
+    if shard is not None:
+        rank, world = shard
+        n_pt, n_obs = n_pt // world, n_obs // world
+        point_seed = seed * 7919 + 1 + rank
+    return make_ba_problem(n_cam, n_pt, n_obs, window, seed, model_id, point_seed=point_seed)
 
 
 @dataclass

@@ -99,6 +99,8 @@ def pcg_jacobi(A, b, tol=1e-5, maxiter=None):
 
 def direct_solve(A, b):
     """Exact sparse solve of the damped normal equations (ground truth for parity)."""
+    if A.shape[0] <= 3000:
+        return np.linalg.solve(A.toarray(), b), 0
     lu = spla.splu(A.tocsc(), permc_spec="COLAMD", diag_pivot_thresh=0.0,
                    options=dict(SymmetricMode=True))
     return lu.solve(b), 0

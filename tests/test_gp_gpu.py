@@ -1,0 +1,90 @@
+"""GPU parity tests: CUDA global positioning through the C ABI vs the fp64 oracle
+(oracle/gp.py solves the full [centres, points, scales] system; the CUDA path eliminates
+scales and points first -- the same damped normal equations)."""
+import numpy as np
+import pytest
+
+from instantsfm_b200.synthetic import make_gp_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(g, dtype, scale_fixed=None, **kw):
+    from instantsfm_b200.engine import GPEngine
+    eng = GPEngine(dtype=dtype, **kw)
+    eng.set_problem(g.camera_translations, g.points_3d, g.scales, g.translations, g.camera_indices, g.point_indices,
+                    g.is_calibrated, scale_fixed)
+    return eng
+
+
+def _oracle(g, scale_fixed=None, depth_only=False):
+    from oracle.gp import GPProblem
+    return GPProblem(g.camera_translations, g.points_3d, g.scales, g.translations, g.camera_indices, g.point_indices,
+                     g.is_calibrated, scale_fixed, depth_only)
+
+
+def _shuffle(g, seed=0):
+    import copy
+    perm = np.random.default_rng(seed).permutation(g.translations.shape[0])
+    h = copy.copy(g)
+    h.translations, h.camera_indices, h.point_indices, h.scales = (g.translations[perm], g.camera_indices[perm],
+                                                                   g.point_indices[perm], g.scales[perm])
+    return h
+
+
+def test_cost_matches_oracle():
+    from oracle.lm import robust_cost
+    g = _shuffle(make_gp_problem(10, 150, 600, seed=2))
+    r = _oracle(g).residuals()
+    for dtype, tol in [(np.float64, 1e-12), (np.float32, 1e-5)]:
+        rob, sq = _engine(g, dtype).cost()
+        assert abs(rob - robust_cost(r, 0.1)) <= tol * robust_cost(r, 0.1)
+        assert abs(sq - (r * r).sum()) <= tol * (r * r).sum()
+
+
+@pytest.mark.parametrize("mode", ["free", "mixed", "depth_only"])
+def test_steps_match_direct_solve_fp64(mode):
+    from oracle.gp import make_optimizer
+    g = _shuffle(make_gp_problem(10, 150, 600, seed=3))
+    rng = np.random.default_rng(1)
+    fixed = None
+    if mode == "mixed":
+        fixed = rng.uniform(size=g.translations.shape[0]) < 0.4
+        g.scales = np.where(fixed[:, None], rng.uniform(0.02, 0.1, g.scales.shape), 1.0)
+    if mode == "depth_only":
+        g.scales = rng.uniform(0.02, 0.1, g.scales.shape)
+    eng = _engine(g, np.float64, scale_fixed=fixed, pcg_tol=1e-13, pcg_max_iter=3000, optimize_scales=(mode != "depth_only"))
+    pb = _oracle(g, fixed, depth_only=(mode == "depth_only"))
+    opt = make_optimizer(pb, 0.1, solver="direct")
+    for it in range(8):
+        ref = opt.step()
+        loss, st = eng.step()
+        assert abs(loss - ref) <= 1e-8 * ref, (it, loss, ref)
+        assert st["trials"] == len(opt.trace[it]["trials"])
+    c, X, s = eng.get_params()
+    assert np.abs(c - pb.c).max() <= 1e-6 * np.abs(pb.c).max()
+    assert np.abs(X - pb.X).max() <= 1e-6 * np.abs(pb.X).max()
+    assert np.abs(s - pb.s).max() <= 1e-6 * max(1.0, np.abs(pb.s).max())
+
+
+def test_fp32_first_steps_within_1e4():
+    from oracle.gp import make_optimizer
+    g = make_gp_problem(16, 400, 1800, seed=5)
+    eng = _engine(g, np.float32, pcg_tol=1e-7, pcg_max_iter=3000)
+    pb = _oracle(g)
+    opt = make_optimizer(pb, 0.1, solver="direct")
+    for it in range(4):
+        ref = opt.step()
+        loss, _ = eng.step()
+        assert abs(loss - ref) <= 1e-4 * ref, (it, loss, ref)
+
+
+def test_solve_converges_to_ground_truth_up_to_similarity():
+    g = make_gp_problem(24, 800, 4000, seed=7, ray_noise_deg=0.0, outlier_frac=0.0)
+    eng = _engine(g, np.float64, pcg_tol=1e-10)
+    hist = eng.solve(100, 1e-9)
+    assert hist[-1] < 1e-3 * hist[0]
+    c, X, s = eng.get_params()
+    # rays are exact: every observation satisfies d = s (X - c) up to the common similarity
+    r = g.translations - s * (X[g.point_indices] - c[g.camera_indices])
+    assert np.abs(r).max() < 0.05
