@@ -1,0 +1,50 @@
+"""Shared host-side helpers of the drop-in processors."""
+import numpy as np
+
+WINDOW = 4  # bundle_adjustment.py:128 / global_positioning.py:172
+
+
+def device_index(device):
+    """'cuda:0' / 'cuda' / torch.device / int -> CUDA ordinal.  There is no CPU path."""
+    if isinstance(device, int):
+        return device
+    s = str(device)
+    if not s.startswith("cuda"):
+        raise RuntimeError(f"instantsfm_b200 runs on CUDA devices only (got device={device!r}); "
+                           "the CPU restatement lives in oracle/ and is test infrastructure")
+    return int(s.split(":")[1]) if ":" in s else 0
+
+
+def should_stop(history, function_tolerance, identical_test):
+    """Windowed relative-improvement stop rule, bundle_adjustment.py:134-141."""
+    if len(history) < 2 * WINDOW:
+        return False
+    recent = np.mean(history[-WINDOW:])
+    previous = np.mean(history[-2 * WINDOW:-WINDOW])
+    improvement = (previous - recent) / previous
+    if abs(improvement) < function_tolerance:
+        return True
+    return identical_test and history[-1] == history[-2]
+
+
+def concat_features(images, attr):
+    """One [sum n_i, k] array of every image's `attr` rows + per-image offsets, so that
+    (image_id, feature_id) pairs can be looked up with a single fancy index."""
+    counts = np.array([len(getattr(img, attr)) for img in images], dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(counts)])
+    rows = [np.asarray(getattr(img, attr), dtype=np.float64) for img in images if len(getattr(img, attr))]
+    table = np.concatenate(rows, axis=0) if rows else np.zeros((0, 2))
+    return table, offsets
+
+
+def flatten_observations(tracks, track_ids):
+    """Concatenated (image_id, feature_id, position-in-track_ids) of the given tracks, in the
+    order of the reference's nested loops (bundle_adjustment.py:88-96)."""
+    obs_list = [np.asarray(tracks[t].observations).reshape(-1, 2) for t in track_ids]
+    lengths = np.array([o.shape[0] for o in obs_list], dtype=np.int64)
+    if lengths.sum() == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z, z
+    obs = np.concatenate(obs_list, axis=0).astype(np.int64)
+    which = np.repeat(np.arange(len(track_ids), dtype=np.int64), lengths)
+    return obs[:, 0], obs[:, 1], which

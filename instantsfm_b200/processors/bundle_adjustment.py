@@ -1,0 +1,122 @@
+"""Drop-in for instantsfm/processors/bundle_adjustment.py: same class, same signatures, same
+in-place mutation of ``cameras`` / ``images`` / ``tracks`` -- the LM solve runs in the CUDA
+library (include/isfm_b200.h) instead of bae + pypose.
+
+Differences a caller can observe: (i) arithmetic is fp32 by default (``dtype=np.float64``
+selects the validation build), (ii) the O(N_obs) Python loops of the reference
+(:85-100, :29-36) are vectorised numpy producing the identical tensors, (iii) the linear
+system is solved by Schur complement + block-Jacobi PCG (tolerance 1e-6 on the reduced
+system) instead of full-system Jacobi PCG (1e-5).
+"""
+import numpy as np
+
+from ..engine import BAEngine
+from ..geometry import matrices_to_pose7, pose7_to_matrices, transform_points
+from ._common import concat_features, device_index, flatten_observations, should_stop
+
+# CameraModelId.value -> principal-point indices inside Camera.params (scene/defs.py:115-140).
+# FOV (7) and THIN_PRISM_FISHEYE (10) are listed by the reference but their cost functions
+# raise NotImplementedError (utils/cost_function.py:128,182).
+_PP = {0: [1, 2], 1: [2, 3], 2: [1, 2], 3: [1, 2], 4: [2, 3], 5: [2, 3], 6: [2, 3], 8: [1, 2], 9: [1, 2]}
+
+
+def _model_value(model_id):
+    return model_id.value if hasattr(model_id, "value") else int(model_id)
+
+
+def update(cameras, images, tracks, track_keys, unique_cameras, unique_points, remaining_indices, pp_indices,
+           camera_params, camera_pps, points_3d):
+    """bundle_adjustment.py:18-36: write the optimised tensors back into the scene objects
+    (images sharing a camera overwrite each other's intrinsics; the last one wins)."""
+    full = np.zeros((camera_params.shape[0], camera_params.shape[1] + 2))
+    full[:, remaining_indices] = camera_params
+    full[:, pp_indices] = camera_pps
+    pose_matrices = pose7_to_matrices(full[:, :7])
+    for i, original_idx in enumerate(unique_points.tolist()):
+        tracks[track_keys[original_idx]].xyz = points_3d[i]
+    for i, image_id in enumerate(unique_cameras.tolist()):
+        image = images[image_id]
+        image.world2cam = pose_matrices[i]
+        cameras[image.cam_id].set_params(full[i, 7:])
+
+
+class TorchBA:
+    def __init__(self, visualizer=None, device="cuda:0", dtype=np.float32):
+        self.device = device
+        self.visualizer = visualizer
+        self.dtype = dtype
+        self.loss_history = []
+        self.last_stats = []
+
+    # -- tensor set-up, bundle_adjustment.py:66-113 ---------------------------------------
+    def _build(self, cameras, images, tracks, options, model_value):
+        track_keys = list(tracks.keys())
+        track_lengths = np.array([len(tracks[k].observations) for k in track_keys])
+        is_track_valid = track_lengths >= options["min_num_view_per_track"]
+        registered = np.array([img.is_registered for img in images], dtype=bool)
+
+        poses = np.tile(np.array([0, 0, 0, 0, 0, 0, 1.0]), (len(images), 1))        # pp.identity_SE3()
+        if registered.any():
+            mats = np.stack([images[i].world2cam for i in np.flatnonzero(registered)], 0)
+            poses[registered] = matrices_to_pose7(mats)
+        intr = np.stack([np.asarray(cameras[img.cam_id].params, dtype=np.float64) for img in images], 0)
+        camera_params = np.concatenate([poses, intr], axis=1)
+        pp_indices = np.array(_PP[model_value]) + 7
+        remaining = np.array([i for i in range(camera_params.shape[1]) if i not in pp_indices])
+        camera_pps = camera_params[:, pp_indices]
+        camera_params = camera_params[:, remaining]
+        points_3d = np.stack([np.asarray(t.xyz, dtype=np.float64) for t in tracks.values()], 0)
+
+        valid_ids = np.flatnonzero(is_track_valid)
+        image_id, feature_id, which = flatten_observations(tracks, [track_keys[i] for i in valid_ids])
+        keep = registered[image_id] if image_id.size else np.zeros(0, bool)
+        image_id, feature_id, point_idx = image_id[keep], feature_id[keep], valid_ids[which[keep]]
+        table, offsets = concat_features(images, "features")
+        points_2d = table[offsets[image_id] + feature_id].reshape(-1, 2)
+
+        # cheirality, evaluated once before the solve (:102-107)
+        y = transform_points(camera_params[image_id, :7], points_3d[point_idx])
+        valid = y[:, 2] > 0.1
+        points_2d, image_id, point_idx = points_2d[valid], image_id[valid], point_idx[valid]
+        unique_cameras, cam_inv = np.unique(image_id, return_inverse=True)             # torch.unique(sorted=True)
+        unique_points, pt_inv = np.unique(point_idx, return_inverse=True)
+        return {"track_keys": track_keys, "unique_cameras": unique_cameras, "unique_points": unique_points,
+                "remaining": remaining, "pp_indices": pp_indices,
+                "camera_params": camera_params[unique_cameras], "camera_pps": camera_pps[unique_cameras],
+                "points_3d": points_3d[unique_points], "points_2d": points_2d,
+                "camera_indices": cam_inv.astype(np.int32), "point_indices": pt_inv.astype(np.int32)}
+
+    def Solve(self, cameras, images, tracks, BUNDLE_ADJUSTER_OPTIONS):
+        self.camera_model = cameras[0].model_id  # assume all cameras are under the same model
+        model_value = _model_value(self.camera_model)
+        if model_value not in _PP:
+            raise NotImplementedError("Unsupported camera model")
+        opts = BUNDLE_ADJUSTER_OPTIONS
+        t = self._build(cameras, images, tracks, opts, model_value)
+        if t["points_2d"].shape[0] == 0:
+            return
+
+        import torch
+        with torch.cuda.device(device_index(self.device)):
+            engine = BAEngine(model_value, optimize_poses=opts["optimize_poses"],
+                              huber_delta=opts["thres_loss_function"], dtype=self.dtype)
+            engine.set_problem(t["camera_params"], t["camera_pps"], t["points_3d"], t["points_2d"],
+                               t["camera_indices"], t["point_indices"])
+
+            def write_back():
+                cam, pts = engine.get_params()
+                update(cameras, images, tracks, t["track_keys"], t["unique_cameras"], t["unique_points"],
+                       t["remaining"], t["pp_indices"], cam.astype(np.float64), t["camera_pps"], pts.astype(np.float64))
+
+            self.loss_history, self.last_stats = [], []
+            for _ in range(opts["max_num_iterations"]):
+                loss, stats = engine.step()
+                self.loss_history.append(loss)
+                self.last_stats.append(stats)
+                if should_stop(self.loss_history, opts["function_tolerance"], identical_test=True):
+                    break
+                if self.visualizer:
+                    write_back()
+                    self.visualizer.add_step(cameras, images, tracks, "bundle_adjustment")
+            write_back()
+            engine.close()

@@ -278,3 +278,80 @@ def make_gp_config(name="C4", scale=1.0):
         n_pt = max(int(n_pt * scale), 16)
         n_obs = max(int(n_obs * scale), 3 * n_pt)
     return make_gp_problem(n_cam, n_pt, n_obs, window, seed)
+
+
+# ---------------------------------------------------------------------------------------
+# scene objects (cameras / images / tracks) for the drop-in processors
+# ---------------------------------------------------------------------------------------
+_PP_IDX = {0: [1, 2], 1: [2, 3], 2: [1, 2], 3: [1, 2], 4: [2, 3], 5: [2, 3], 6: [2, 3], 8: [1, 2], 9: [1, 2]}
+
+
+def ba_arrays_to_scene(a, unregistered=(), short_track_every=0, rng=None):
+    """cameras (one per image), images, tracks for TorchBA.Solve from a flat problem.
+
+    ``unregistered``: image ids flagged is_registered=False (their observations must be
+    skipped); ``short_track_every``: every n-th track is cut to one observation (must be
+    dropped by min_num_view_per_track).  Track keys are deliberately not 0..n-1."""
+    from .geometry import pose7_to_matrices
+    from .scene.defs import Camera, CameraModelId, Image, Track
+    model = CameraModelId(a.model_id)
+    n_full = a.camera_params.shape[1] - 7 + 2
+    pp_idx = _PP_IDX[a.model_id]
+    rest = [i for i in range(n_full) if i not in pp_idx]
+    mats = pose7_to_matrices(a.camera_params[:, :7])
+    cameras, images = [], []
+    feat_id = np.zeros(a.n_obs, dtype=np.int64)
+    order = np.argsort(a.camera_indices, kind="stable")
+    cam_sorted = a.camera_indices[order]
+    starts = np.searchsorted(cam_sorted, np.arange(a.n_cam + 1))
+    feat_id[order] = np.arange(a.n_obs) - starts[cam_sorted]
+    for i in range(a.n_cam):
+        full = np.zeros(n_full)
+        full[rest] = a.camera_params[i, 7:]
+        full[pp_idx] = a.camera_pps[i]
+        cameras.append(Camera(id=i, model_id=model, params=full, has_prior_focal_length=True))
+        feats = a.points_2d[order[starts[i]:starts[i + 1]]]
+        images.append(Image(id=i, cam_id=i, is_registered=i not in set(unregistered), world2cam=mats[i].copy(),
+                            features=feats.copy()))
+    tracks = {}
+    pt_starts = np.searchsorted(a.point_indices, np.arange(a.n_pt + 1))
+    for p in range(a.n_pt):
+        sl = slice(pt_starts[p], pt_starts[p + 1])
+        obs = np.stack([a.camera_indices[sl].astype(np.int64), feat_id[sl]], axis=1)
+        if short_track_every and p % short_track_every == 0:
+            obs = obs[:1]
+        tracks[10 + 3 * p] = Track(id=10 + 3 * p, xyz=a.points_3d[p].copy(), observations=obs)
+    return cameras, images, tracks
+
+
+def gp_arrays_to_scene(g, seed=0):
+    """cameras, images (random rotations, features_undist = R d), tracks for TorchGP.Optimize."""
+    from .geometry import quat_to_mat
+    from .scene.defs import Camera, CameraModelId, Image, Track
+    rng = np.random.default_rng(seed)
+    n_cam, n_obs = g.camera_translations.shape[0], g.translations.shape[0]
+    q = rng.normal(size=(n_cam, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    R = quat_to_mat(q)
+    order = np.argsort(g.camera_indices, kind="stable")
+    cam_sorted = g.camera_indices[order]
+    starts = np.searchsorted(cam_sorted, np.arange(n_cam + 1))
+    feat_id = np.zeros(n_obs, dtype=np.int64)
+    feat_id[order] = np.arange(n_obs) - starts[cam_sorted]
+    cameras, images = [], []
+    for i in range(n_cam):
+        cameras.append(Camera(id=i, model_id=CameraModelId.SIMPLE_PINHOLE, params=[1000.0, 0.0, 0.0],
+                              has_prior_focal_length=bool(g.is_calibrated[i])))
+        M = np.eye(4)
+        M[:3, :3] = R[i]
+        M[:3, 3] = g.camera_translations[i]          # holds the camera CENTRE at this stage (:31-35)
+        d = g.translations[order[starts[i]:starts[i + 1]]]
+        images.append(Image(id=i, cam_id=i, is_registered=True, world2cam=M, features_undist=d @ R[i].T))
+    tracks = {}
+    n_pt = g.points_3d.shape[0]
+    pt_starts = np.searchsorted(g.point_indices, np.arange(n_pt + 1))
+    for p in range(n_pt):
+        sl = slice(pt_starts[p], pt_starts[p + 1])
+        tracks[5 + 2 * p] = Track(id=5 + 2 * p, xyz=g.points_3d[p].copy(),
+                                  observations=np.stack([g.camera_indices[sl].astype(np.int64), feat_id[sl]], axis=1))
+    return cameras, images, tracks

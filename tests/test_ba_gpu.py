@@ -7,6 +7,7 @@ import pytest
 import scipy.sparse as sp
 
 from instantsfm_b200.synthetic import make_ba_problem, N_INTR
+from tests.helpers import normal_blocks as _normal_blocks, weighted_blocks as _weighted_blocks
 
 pytestmark = pytest.mark.gpu
 
@@ -32,13 +33,6 @@ def _shuffled(a, seed=0):
     b = copy.copy(a)
     b.points_2d, b.camera_indices, b.point_indices = a.points_2d[perm], a.camera_indices[perm], a.point_indices[perm]
     return b
-
-
-def _weighted_blocks(pb, delta=1.0):
-    from oracle.lm import triggs_scale
-    r, Jc, Jp = pb.blocks()
-    w = triggs_scale(r, delta)
-    return r, r * w[:, None], Jc * w[:, None, None], Jp * w[:, None, None]
 
 
 def _rel(a, b):
@@ -87,41 +81,6 @@ def test_linearize_all_models(model_id, dtype, tol):
     from oracle.lm import robust_cost
     assert abs(rob - robust_cost(r, 1.0)) <= 10 * tol * robust_cost(r, 1.0)
     assert abs(sq - (r * r).sum()) <= 10 * tol * (r * r).sum()
-
-
-def _normal_blocks(pb, mu, delta=1.0):
-    """Oracle-side Hpp, g_p, Hcc, g_c and the dense reduced system at damping mu."""
-    _, R, Jc, Jp = _weighted_blocks(pb, delta)
-    n_cam, n_pt, d = pb.n_cam, pb.n_pt, pb.d
-    Hpp = np.zeros((n_pt, 3, 3)); gp = np.zeros((n_pt, 3)); Hcc = np.zeros((n_cam, d, d)); gc = np.zeros((n_cam, d))
-    np.add.at(Hpp, pb.pi, np.einsum("nki,nkj->nij", Jp, Jp))
-    np.add.at(gp, pb.pi, np.einsum("nki,nk->ni", Jp, R))
-    np.add.at(Hcc, pb.ci, np.einsum("nki,nkj->nij", Jc, Jc))
-    np.add.at(gc, pb.ci, np.einsum("nki,nk->ni", Jc, R))
-    Hcp = np.einsum("nki,nkj->nij", Jc, Jp)   # [N, d, 3]
-
-    def damp(H):
-        H = H.copy()
-        idx = np.arange(H.shape[1])
-        H[:, idx, idx] = np.clip(H[:, idx, idx], 1e-6, 1e32) * mu
-        return H
-    Hpp_d, Hcc_d = damp(Hpp), damp(Hcc)
-    inv = np.linalg.inv(Hpp_d)
-    S = np.zeros((n_cam * d, n_cam * d))
-    for i in range(n_cam):
-        S[i * d:(i + 1) * d, i * d:(i + 1) * d] = Hcc_d[i]
-    W = np.einsum("nij,njk->nik", Hcp, inv[pb.pi])          # Hcp Hpp^-1
-    rhs = -gc.copy()
-    np.add.at(rhs, pb.ci, np.einsum("nij,nj->ni", W, gp[pb.pi]))
-    order = np.argsort(pb.pi, kind="stable")
-    off = np.searchsorted(pb.pi[order], np.arange(n_pt + 1))
-    for p in range(n_pt):
-        obs = order[off[p]:off[p + 1]]
-        for x in obs:
-            for y in obs:
-                i, j = pb.ci[x], pb.ci[y]
-                S[i * d:(i + 1) * d, j * d:(j + 1) * d] -= W[x] @ Hcp[y].T
-    return Hpp, gp, Hcc, gc, S, rhs.reshape(-1)
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 2e-4)])
