@@ -5,9 +5,12 @@
 //   cam   [n_cam][7+NI]   t, q_xyzw, intrinsics (pp removed)      pp  [n_cam][2]
 //   pts   [n_pt][3]                                               obs [n_obs][2]   (sorted)
 //   R     [n_obs][2]      Triggs-weighted residual
-//   JC    [n_obs][2*D]    weighted camera block, row-major 2 x D  (D = 6 + NI)
-//   JP    [n_obs][6]      weighted point block, 2 x 3
-//   V     [n_obs][6]      JP * Hpp^-1 (2 x 3), per trial
+//   OBS   [n_obs][REC]    one 16-byte-aligned record per observation (128 B for D = 9, fp32):
+//                           [0, 2D)        Jc  weighted camera block, row-major 2 x D (D = 6 + NI)
+//                           [2D, 2D+6)     Jp  weighted point block, 2 x 3
+//                           [2D+6, 2D+12)  V = Jp * Hpp^-1 (2 x 3), rewritten per trial
+//                         so that every gather of an observation is one or two full lines
+//                         fetched with 128-bit loads
 //   HPP   [n_pt][6]  GPT [n_pt][3]  HPPINV [n_pt][6]  TP [n_pt][3] = Hpp^-1 g_p
 //   HCC   [n_cam][D*D]  GC [n_cam][D]   (undamped, all ranks' sum)
 //   E     [nnzb][D*D]     BSR values of sum_p Hcp Hpp^-1 Hcp^T; S = damp(Hcc) - E
@@ -22,6 +25,51 @@ namespace isfm {
 constexpr int BA_TPB = 256;
 constexpr int RED_BLOCKS = 148 * 4;  // grid of the grid-stride reduction kernels (4 CTAs / SM)
 
+// per-observation record geometry
+template <int D> struct ObsRec {
+  static constexpr int JP = 2 * D;                       // offset of Jp
+  static constexpr int V = 2 * D + 6;                    // offset of V
+  static constexpr int REC = (2 * D + 12 + 3) / 4 * 4;   // stride in elements, multiple of 4
+};
+
+// 128-bit loads / stores of "quads" (4 consecutive elements; two double2 for T = double)
+template <typename T> struct QuadIO;
+template <> struct QuadIO<float> {
+  static __device__ __forceinline__ void ld(const float* p, float* d) {
+    float4 v = *reinterpret_cast<const float4*>(p); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  static __device__ __forceinline__ void ldg(const float* p, float* d) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p)); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* d) {
+    *reinterpret_cast<float4*>(p) = make_float4(d[0], d[1], d[2], d[3]);
+  }
+};
+template <> struct QuadIO<double> {
+  static __device__ __forceinline__ void ld(const double* p, double* d) {
+    double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+  }
+  static __device__ __forceinline__ void ldg(const double* p, double* d) {
+    double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p + 2));
+    d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+  }
+  static __device__ __forceinline__ void st(double* p, const double* d) {
+    *reinterpret_cast<double2*>(p) = make_double2(d[0], d[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(d[2], d[3]);
+  }
+};
+// loads quads [Q0, Q1) of a record into dst[0 .. 4 (Q1 - Q0)); element e of the record is
+// dst[e - 4 Q0].  READONLY selects the non-coherent path.
+template <typename T, int Q0, int Q1, bool READONLY>
+__device__ __forceinline__ void load_quads(const T* __restrict__ rec, T* dst) {
+#pragma unroll
+  for (int q = Q0; q < Q1; ++q) {
+    if (READONLY) QuadIO<T>::ldg(rec + 4 * q, dst + 4 * (q - Q0));
+    else QuadIO<T>::ld(rec + 4 * q, dst + 4 * (q - Q0));
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // K1: residual + Huber weight + Jacobian blocks per observation; cost partials per block.
 // ---------------------------------------------------------------------------------------
@@ -29,30 +77,35 @@ template <typename T, int MODEL>
 __global__ void __launch_bounds__(BA_TPB)
 linearize_kernel(int64_t n_obs, const T* __restrict__ cam, const T* __restrict__ pp, const T* __restrict__ pts,
                  const T* __restrict__ obs, const int32_t* __restrict__ cam_of, const int32_t* __restrict__ pt_of,
-                 T delta, T* __restrict__ R, T* __restrict__ JC, T* __restrict__ JP,
+                 T delta, T* __restrict__ R, T* __restrict__ OBS,
                  double* __restrict__ part_rho, double* __restrict__ part_sq) {
   constexpr int NI = ModelTraits<MODEL>::NI;
   constexpr int D = 6 + NI;
   constexpr int CW = 7 + NI;
+  constexpr int REC = ObsRec<D>::REC;
+  constexpr int NQ = (2 * D + 6 + 3) / 4;   // quads covering Jc | Jp (may spill into V, rewritten later)
   double rho_sum = 0.0, sq_sum = 0.0;
   for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < n_obs; a += (int64_t)gridDim.x * blockDim.x) {
     const int c = cam_of[a], p = pt_of[a];
-    T cr[CW], ppv[2], X[3], o[2], r[2], jc[2 * D], jp[6];
+    T cr[CW], ppv[2], X[3], o[2], r[2], rec[4 * NQ];
 #pragma unroll
     for (int i = 0; i < CW; ++i) cr[i] = __ldg(cam + (size_t)c * CW + i);
     ppv[0] = __ldg(pp + 2 * (size_t)c); ppv[1] = __ldg(pp + 2 * (size_t)c + 1);
 #pragma unroll
     for (int i = 0; i < 3; ++i) X[i] = __ldg(pts + 3 * (size_t)p + i);
     o[0] = obs[2 * a]; o[1] = obs[2 * a + 1];
-    ba_linearize<MODEL, T>(cr, ppv, X, o, r, jc, jp);
+#pragma unroll
+    for (int i = 2 * D + 6; i < 4 * NQ; ++i) rec[i] = T(0);
+    ba_linearize<MODEL, T>(cr, ppv, X, o, r, rec, rec + 2 * D);
     T s = r[0] * r[0] + r[1] * r[1], rho, w;
     huber(s, delta, rho, w);
     rho_sum += (double)rho; sq_sum += (double)s;
     R[2 * a] = w * r[0]; R[2 * a + 1] = w * r[1];
 #pragma unroll
-    for (int i = 0; i < 2 * D; ++i) JC[(size_t)a * (2 * D) + i] = w * jc[i];
+    for (int i = 0; i < 2 * D + 6; ++i) rec[i] *= w;
+    T* dst = OBS + (size_t)a * REC;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) JP[(size_t)a * 6 + i] = w * jp[i];
+    for (int q = 0; q < NQ; ++q) QuadIO<T>::st(dst + 4 * q, rec + 4 * q);
   }
   rho_sum = block_sum(rho_sum);
   sq_sum = block_sum(sq_sum);
@@ -111,14 +164,16 @@ static __global__ void reduce_scalars_kernel(const double* __restrict__ p0, cons
 }
 
 // ---------------------------------------------------------------------------------------
-// K2 (point side) + K3 (3x3): one thread per point over its contiguous observations.
+// K2 (point side) + K3 (3x3): one thread per point over its contiguous observation records.
 // BUILD: accumulate Hpp = sum Jp^T Jp and g_p = sum Jp^T R.  Always: damp, invert, TP, V.
+// D = 0 selects the points-only layout (record = Jp only is not used: the record keeps its
+// full geometry, only V is skipped when WRITE_V is false).
 // ---------------------------------------------------------------------------------------
-template <typename T, bool BUILD>
+template <typename T, int D, bool BUILD, bool WRITE_V>
 __global__ void __launch_bounds__(BA_TPB)
-point_solve_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const T* __restrict__ JP, const T* __restrict__ R,
-                   T mu, T* __restrict__ HPP, T* __restrict__ GPT, T* __restrict__ HPPINV, T* __restrict__ TP,
-                   T* __restrict__ V) {
+point_solve_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, T* __restrict__ OBS, const T* __restrict__ R,
+                   T mu, T* __restrict__ HPP, T* __restrict__ GPT, T* __restrict__ HPPINV, T* __restrict__ TP) {
+  constexpr int REC = ObsRec<D>::REC, OJP = ObsRec<D>::JP, OV = ObsRec<D>::V;
   int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (p >= n_pt) return;
   const int beg = pt_off[p], end = pt_off[p + 1];
@@ -128,7 +183,7 @@ point_solve_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const T* __
     for (int i = 0; i < 6; ++i) h[i] = T(0);
     g[0] = g[1] = g[2] = T(0);
     for (int a = beg; a < end; ++a) {
-      const T* j = JP + (size_t)a * 6;
+      const T* j = OBS + (size_t)a * REC + OJP;
       T j0 = j[0], j1 = j[1], j2 = j[2], j3 = j[3], j4 = j[4], j5 = j[5];
       T r0 = R[2 * (size_t)a], r1 = R[2 * (size_t)a + 1];
       h[0] += j0 * j0 + j3 * j3; h[1] += j0 * j1 + j3 * j4; h[2] += j0 * j2 + j3 * j5;
@@ -153,10 +208,11 @@ point_solve_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const T* __
   TP[(size_t)p * 3 + 0] = iv[0] * g[0] + iv[1] * g[1] + iv[2] * g[2];
   TP[(size_t)p * 3 + 1] = iv[1] * g[0] + iv[3] * g[1] + iv[4] * g[2];
   TP[(size_t)p * 3 + 2] = iv[2] * g[0] + iv[4] * g[1] + iv[5] * g[2];
-  if (V) {
+  if (WRITE_V) {
     for (int a = beg; a < end; ++a) {
-      const T* j = JP + (size_t)a * 6;
-      T* v = V + (size_t)a * 6;
+      T* rec = OBS + (size_t)a * REC;
+      const T* j = rec + OJP;
+      T* v = rec + OV;
 #pragma unroll
       for (int row = 0; row < 2; ++row) {
         T a0 = j[3 * row], a1 = j[3 * row + 1], a2 = j[3 * row + 2];
@@ -169,18 +225,19 @@ point_solve_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const T* __
 }
 
 // points-only BA (optimize_poses = False): D_p = -Hpp^-1 g_p, trial points, model term
-template <typename T>
+template <typename T, int D>
 __global__ void __launch_bounds__(BA_TPB)
-point_only_step_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const T* __restrict__ JP,
+point_only_step_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const T* __restrict__ OBS,
                        const T* __restrict__ R, const T* __restrict__ TP, const T* __restrict__ pts,
                        T* __restrict__ pts_trial, T* __restrict__ DP, double* __restrict__ part_m) {
+  constexpr int REC = ObsRec<D>::REC, OJP = ObsRec<D>::JP;
   double msum = 0.0;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_pt; p += (int64_t)gridDim.x * blockDim.x) {
     T d0 = -TP[3 * p], d1 = -TP[3 * p + 1], d2 = -TP[3 * p + 2];
     DP[3 * p] = d0; DP[3 * p + 1] = d1; DP[3 * p + 2] = d2;
     pts_trial[3 * p] = pts[3 * p] + d0; pts_trial[3 * p + 1] = pts[3 * p + 1] + d1; pts_trial[3 * p + 2] = pts[3 * p + 2] + d2;
     for (int a = pt_off[p]; a < pt_off[p + 1]; ++a) {
-      const T* j = JP + (size_t)a * 6;
+      const T* j = OBS + (size_t)a * REC + OJP;
       T jd0 = j[0] * d0 + j[1] * d1 + j[2] * d2, jd1 = j[3] * d0 + j[4] * d1 + j[5] * d2;
       msum += (double)(jd0 * (2 * R[2 * (size_t)a] + jd0) + jd1 * (2 * R[2 * (size_t)a + 1] + jd1));
     }
@@ -190,19 +247,21 @@ point_only_step_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const T
 }
 
 // ---------------------------------------------------------------------------------------
-// K2 (camera side): one CTA per camera over its observations (camera-major list).
+// K2 (camera side): one CTA per camera over its observation records (camera-major list).
 // PASS_E = false: Hcc_i = sum Jc^T Jc, g_c = sum Jc^T R            (once per LM step)
 // PASS_E = true : E_ii  = sum Jc^T (V Jp^T) Jc, e_i = sum Jc^T (Jp t_p)   (once per trial)
-// Warp-shuffle + shared-memory reduction; no atomics.
+// Each record is fetched with 128-bit loads; warp-shuffle + shared-memory reduction, no atomics.
 // ---------------------------------------------------------------------------------------
 constexpr int CAM_TPB = 128;
 
 template <typename T, int D, bool PASS_E>
 __global__ void __launch_bounds__(CAM_TPB)
 camera_blocks_kernel(const int32_t* __restrict__ cam_off, const int32_t* __restrict__ cam_perm,
-                     const int32_t* __restrict__ pt_of, const T* __restrict__ JC, const T* __restrict__ R,
-                     const T* __restrict__ JP, const T* __restrict__ V, const T* __restrict__ TP,
-                     T* __restrict__ out_blocks, const int32_t* __restrict__ out_slot, T* __restrict__ out_vec) {
+                     const int32_t* __restrict__ pt_of, const T* __restrict__ OBS, const T* __restrict__ R,
+                     const T* __restrict__ TP, T* __restrict__ out_blocks, const int32_t* __restrict__ out_slot,
+                     T* __restrict__ out_vec) {
+  constexpr int REC = ObsRec<D>::REC, OJP = ObsRec<D>::JP, OV = ObsRec<D>::V;
+  constexpr int NQ = PASS_E ? REC / 4 : (2 * D + 3) / 4;
   constexpr int NU = D * (D + 1) / 2;
   constexpr int NACC = NU + D;
   constexpr int NW = CAM_TPB / 32;
@@ -214,13 +273,13 @@ camera_blocks_kernel(const int32_t* __restrict__ cam_off, const int32_t* __restr
   for (int i = 0; i < NACC; ++i) acc[i] = T(0);
   for (int k = beg + threadIdx.x; k < end; k += CAM_TPB) {
     const int a = cam_perm[k];
-    T jc[2 * D];
-#pragma unroll
-    for (int i = 0; i < 2 * D; ++i) jc[i] = JC[(size_t)a * (2 * D) + i];
+    T rec[4 * NQ];
+    load_quads<T, 0, NQ, true>(OBS + (size_t)a * REC, rec);
+    const T* jc = rec;
     T m00, m01, m10, m11, s0, s1;
-    if (PASS_E) {
-      const T* v = V + (size_t)a * 6;
-      const T* j = JP + (size_t)a * 6;
+    if constexpr (PASS_E) {
+      const T* v = rec + OV;
+      const T* j = rec + OJP;
       const T* t = TP + 3 * (size_t)pt_of[a];
       m00 = v[0] * j[0] + v[1] * j[1] + v[2] * j[2]; m01 = v[0] * j[3] + v[1] * j[4] + v[2] * j[5];
       m10 = v[3] * j[0] + v[4] * j[1] + v[5] * j[2]; m11 = v[3] * j[3] + v[4] * j[4] + v[5] * j[5];
@@ -271,76 +330,61 @@ camera_blocks_kernel(const int32_t* __restrict__ cam_off, const int32_t* __restr
 }
 
 // ---------------------------------------------------------------------------------------
-// K2 (Schur off-diagonal): one warp per list of observation pairs (a, b) of block (i, j),
-// i <= j.  E_ij = sum Jc_a^T (V_a Jp_b^T) Jc_b.  Lanes stride over the pairs with the whole
-// D x CT tile in registers, then a warp xor-reduction; block (j, i) gets the transpose.
-// Diagonal lists (same camera twice in a track) add onto E_ii written by the camera pass.
+// K2 (Schur off-diagonal): E_ij = sum over the pair list of block (i, j), i <= j, of
+// Jc_a^T (V_a Jp_b^T) Jc_b.  A group of D lanes owns one list; lane c owns column c of the
+// D x D block (D accumulators), so every pair costs 12 + 4 + 2D FMAs per lane and nothing is
+// reduced across lanes.  Records are fetched with 128-bit loads that broadcast inside the
+// group.  Block (j, i) gets the transpose; diagonal lists (same camera twice in a track) add
+// onto E_ii written by the camera pass.  No atomics.
 // ---------------------------------------------------------------------------------------
-template <int D> struct SchurTile { static constexpr int CT = (D <= 9) ? D : D / 2; };
+template <int D> struct SchurGroup { static constexpr int PER_WARP = 32 / D; };
+constexpr int SCHUR_TPB = 128;
 
 template <typename T, int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SCHUR_TPB)
 schur_offdiag_kernel(int64_t n_lists, const int64_t* __restrict__ list_off, const uint64_t* __restrict__ pairs,
                      const int32_t* __restrict__ list_slot, const int32_t* __restrict__ list_slot_t,
-                     const T* __restrict__ JC, const T* __restrict__ JP, const T* __restrict__ V, T* __restrict__ E) {
-  constexpr int CT = SchurTile<D>::CT;
+                     const T* __restrict__ OBS, T* __restrict__ E) {
+  constexpr int REC = ObsRec<D>::REC, OJP = ObsRec<D>::JP, OV = ObsRec<D>::V;
+  constexpr int GPW = SchurGroup<D>::PER_WARP;
+  constexpr int QJ = (2 * D + 3) / 4;                 // quads covering Jc
+  constexpr int QV0 = OV / 4, QV1 = (OV + 6 + 3) / 4; // quads covering V
+  constexpr int QP0 = OJP / 4, QP1 = (OJP + 6 + 3) / 4;
   const int lane = threadIdx.x & 31;
-  const int64_t u = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (u >= n_lists) return;
-  const int c0 = blockIdx.y * CT;
-  T acc[D * CT];
+  const int grp = lane / D, c = lane % D;
+  const int64_t warp = blockIdx.x * (int64_t)(SCHUR_TPB / 32) + (threadIdx.x >> 5);
+  const int64_t u = warp * GPW + grp;
+  if (grp >= GPW || u >= n_lists) return;
+  T acc[D];
 #pragma unroll
-  for (int i = 0; i < D * CT; ++i) acc[i] = T(0);
+  for (int r = 0; r < D; ++r) acc[r] = T(0);
   const int64_t beg = list_off[u], end = list_off[u + 1];
-  for (int64_t t = beg + lane; t < end; t += 32) {
-    const uint64_t ab = pairs[t];
-    const uint32_t a = (uint32_t)(ab >> 32), b = (uint32_t)ab;
-    const T* va = V + (size_t)a * 6;
-    const T* jb = JP + (size_t)b * 6;
-    T m00 = va[0] * jb[0] + va[1] * jb[1] + va[2] * jb[2], m01 = va[0] * jb[3] + va[1] * jb[4] + va[2] * jb[5];
-    T m10 = va[3] * jb[0] + va[4] * jb[1] + va[5] * jb[2], m11 = va[3] * jb[3] + va[4] * jb[4] + va[5] * jb[5];
-    const T* ja = JC + (size_t)a * (2 * D);
-    const T* jcb = JC + (size_t)b * (2 * D);
-    T t0[CT], t1[CT];
+  for (int64_t t = beg; t < end; ++t) {
+    const uint64_t ab = __ldg(pairs + t);
+    const T* ra = OBS + (size_t)(uint32_t)(ab >> 32) * REC;
+    const T* rb = OBS + (size_t)(uint32_t)ab * REC;
+    T ja[4 * QJ], va[4 * (QV1 - QV0)], pb[4 * (QP1 - QP0)];
+    load_quads<T, 0, QJ, true>(ra, ja);
+    load_quads<T, QV0, QV1, true>(ra, va);
+    load_quads<T, QP0, QP1, true>(rb, pb);
+    const T b0 = __ldg(rb + c), b1 = __ldg(rb + D + c);
+    const T* v = va + (OV - 4 * QV0);
+    const T* j = pb + (OJP - 4 * QP0);
+    const T m00 = v[0] * j[0] + v[1] * j[1] + v[2] * j[2], m01 = v[0] * j[3] + v[1] * j[4] + v[2] * j[5];
+    const T m10 = v[3] * j[0] + v[4] * j[1] + v[5] * j[2], m11 = v[3] * j[3] + v[4] * j[4] + v[5] * j[5];
+    const T t0 = m00 * b0 + m01 * b1, t1 = m10 * b0 + m11 * b1;
 #pragma unroll
-    for (int c = 0; c < CT; ++c) {
-      T b0 = jcb[c0 + c], b1 = jcb[D + c0 + c];
-      t0[c] = m00 * b0 + m01 * b1;
-      t1[c] = m10 * b0 + m11 * b1;
-    }
-#pragma unroll
-    for (int r = 0; r < D; ++r) {
-      T a0 = ja[r], a1 = ja[D + r];
-#pragma unroll
-      for (int c = 0; c < CT; ++c) acc[r * CT + c] += a0 * t0[c] + a1 * t1[c];
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < D * CT; ++i) {
-    T v = acc[i];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    acc[i] = v;
+    for (int r = 0; r < D; ++r) acc[r] += ja[r] * t0 + ja[D + r] * t1;
   }
   const int slot = list_slot[u], slot_t = list_slot_t[u];
   T* blk = E + (size_t)slot * (D * D);
   if (slot_t >= 0) {
     T* blk_t = E + (size_t)slot_t * (D * D);
 #pragma unroll
-    for (int i = 0; i < D * CT; ++i) {
-      if (lane == (i & 31)) {
-        const int r = i / CT, c = c0 + i % CT;
-        blk[r * D + c] = acc[i];
-        blk_t[c * D + r] = acc[i];
-      }
-    }
+    for (int r = 0; r < D; ++r) { blk[r * D + c] = acc[r]; blk_t[c * D + r] = acc[r]; }
   } else {
 #pragma unroll
-    for (int i = 0; i < D * CT; ++i) {
-      if (lane == (i & 31)) {
-        const int r = i / CT, c = c0 + i % CT;
-        blk[r * D + c] += acc[i];
-      }
-    }
+    for (int r = 0; r < D; ++r) blk[r * D + c] += acc[r];
   }
 }
 
@@ -380,26 +424,34 @@ __global__ void precond_kernel(int n_cam, const T* __restrict__ HCC, const T* __
 
 // ---------------------------------------------------------------------------------------
 // K5: back-substitution D_p = -Hpp^-1 (g_p + sum Jp^T (Jc D_c)), trial points, and the
-// trust-region model term sum (JD)^T (2R + JD).  One thread per point.
+// trust-region model term sum (JD)^T (2R + JD).  One thread per point; Jc D_c of up to KEEP
+// observations stays in registers between the two sweeps.
 // ---------------------------------------------------------------------------------------
 template <typename T, int D>
 __global__ void __launch_bounds__(BA_TPB)
 backsub_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const int32_t* __restrict__ cam_of,
-               const T* __restrict__ JC, const T* __restrict__ JP, const T* __restrict__ R, const T* __restrict__ GPT,
+               const T* __restrict__ OBS, const T* __restrict__ R, const T* __restrict__ GPT,
                const T* __restrict__ HPPINV, const T* __restrict__ DC, const T* __restrict__ pts,
                T* __restrict__ pts_trial, T* __restrict__ DP, double* __restrict__ part_m) {
+  constexpr int REC = ObsRec<D>::REC, OJP = ObsRec<D>::JP;
+  constexpr int NQ = (2 * D + 6 + 3) / 4;
+  constexpr int KEEP = 8;
   double msum = 0.0;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_pt; p += (int64_t)gridDim.x * blockDim.x) {
     const int beg = pt_off[p], end = pt_off[p + 1];
     T u0 = GPT[3 * p], u1 = GPT[3 * p + 1], u2 = GPT[3 * p + 2];
+    T kw0[KEEP], kw1[KEEP];
     for (int a = beg; a < end; ++a) {
-      const T* jc = JC + (size_t)a * (2 * D);
+      T rec[4 * NQ];
+      load_quads<T, 0, NQ, true>(OBS + (size_t)a * REC, rec);
       const T* dc = DC + (size_t)cam_of[a] * D;
       T w0 = T(0), w1 = T(0);
 #pragma unroll
-      for (int c = 0; c < D; ++c) { T d = dc[c]; w0 += jc[c] * d; w1 += jc[D + c] * d; }
-      const T* j = JP + (size_t)a * 6;
+      for (int c = 0; c < D; ++c) { T d = __ldg(dc + c); w0 += rec[c] * d; w1 += rec[D + c] * d; }
+      const T* j = rec + OJP;
       u0 += j[0] * w0 + j[3] * w1; u1 += j[1] * w0 + j[4] * w1; u2 += j[2] * w0 + j[5] * w1;
+#pragma unroll
+      for (int k = 0; k < KEEP; ++k) if (a - beg == k) { kw0[k] = w0; kw1[k] = w1; }
     }
     const T* iv = HPPINV + (size_t)p * 6;
     T d0 = -(iv[0] * u0 + iv[1] * u1 + iv[2] * u2);
@@ -408,12 +460,19 @@ backsub_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const int32_t* 
     DP[3 * p] = d0; DP[3 * p + 1] = d1; DP[3 * p + 2] = d2;
     pts_trial[3 * p] = pts[3 * p] + d0; pts_trial[3 * p + 1] = pts[3 * p + 1] + d1; pts_trial[3 * p + 2] = pts[3 * p + 2] + d2;
     for (int a = beg; a < end; ++a) {
-      const T* jc = JC + (size_t)a * (2 * D);
-      const T* dc = DC + (size_t)cam_of[a] * D;
+      const T* recp = OBS + (size_t)a * REC;
       T w0 = T(0), w1 = T(0);
+      if (a - beg < KEEP) {
 #pragma unroll
-      for (int c = 0; c < D; ++c) { T d = dc[c]; w0 += jc[c] * d; w1 += jc[D + c] * d; }
-      const T* j = JP + (size_t)a * 6;
+        for (int k = 0; k < KEEP; ++k) if (a - beg == k) { w0 = kw0[k]; w1 = kw1[k]; }
+      } else {
+        T rec[4 * ((2 * D + 3) / 4)];
+        load_quads<T, 0, (2 * D + 3) / 4, true>(recp, rec);
+        const T* dc = DC + (size_t)cam_of[a] * D;
+#pragma unroll
+        for (int c = 0; c < D; ++c) { T d = __ldg(dc + c); w0 += rec[c] * d; w1 += rec[D + c] * d; }
+      }
+      const T* j = recp + OJP;
       T jd0 = w0 + j[0] * d0 + j[1] * d1 + j[2] * d2, jd1 = w1 + j[3] * d0 + j[4] * d1 + j[5] * d2;
       msum += (double)(jd0 * (2 * R[2 * (size_t)a] + jd0) + jd1 * (2 * R[2 * (size_t)a + 1] + jd1));
     }

@@ -61,7 +61,8 @@ struct BASolver : BASolverBase {
   ObsIndex ix;
   SchurPattern sp;
   DeviceBuffer<T> cam[2], pts[2], pp, obs;
-  DeviceBuffer<T> R, JC, JP, V, HPP, GPT, HPPINV, TP, DP;
+  static constexpr int REC = ObsRec<D>::REC;
+  DeviceBuffer<T> R, OBS, HPP, GPT, HPPINV, TP, DP;
   DeviceBuffer<T> HCC_GC, HD, E, EG, RED, MINV, bvec;  // HCC_GC = [HCC | GC | cost] packed for one all-reduce
   DeviceBuffer<double> part_a, part_b, part_c, scalars;
   DeviceBuffer<int> fail;
@@ -104,15 +105,13 @@ struct BASolver : BASolverBase {
     obs.alloc((size_t)no * 2);
     { TimerScope ts(timers, T_INDEX_PREP);
       gather_rows_kernel<T><<<div_up(no * 2, BA_TPB), BA_TPB, 0, s>>>(no, 2, obs_raw.get(), ix.obs_perm.get(), obs.get()); }
-    R.alloc((size_t)no * 2); JP.alloc((size_t)no * 6);
+    R.alloc((size_t)no * 2); OBS.alloc((size_t)no * REC);
     HPP.alloc((size_t)np * 6); GPT.alloc((size_t)np * 3); HPPINV.alloc((size_t)np * 6); TP.alloc((size_t)np * 3);
     DP.alloc((size_t)np * 3);
     part_a.alloc(std::max<int64_t>(RED_BLOCKS, nc)); part_b.alloc(std::max<int64_t>(RED_BLOCKS, nc));
     part_c.alloc(std::max<int64_t>(RED_BLOCKS, nc));
     scalars.alloc(4); fail.alloc(1); fail.zero(s);
-    JC.alloc((size_t)no * 2 * D);  // also needed by points-only mode for nothing but kept simple
     if (desc.optimize_poses) {
-      V.alloc((size_t)no * 6);
       build_schur_pattern(sp, ix, s, timers);
       HCC_GC.alloc((size_t)nc * (D * D + D)); HD.alloc((size_t)nc * D * D);
       E.alloc((size_t)sp.nnzb * D * D); EG.alloc((size_t)nc * D); RED.alloc((size_t)nc * (D * D + D));
@@ -142,8 +141,8 @@ struct BASolver : BASolverBase {
     const int g = red_grid(n_obs);
     TimerScope ts(timers, T_LINEARIZE);
     linearize_kernel<T, MODEL><<<g, BA_TPB, 0, s>>>(n_obs, cam[cur].get(), pp.get(), pts[cur].get(), obs.get(),
-                                                    ix.cam_of.get(), ix.pt_of.get(), (T)desc.huber_delta, R.get(), JC.get(),
-                                                    JP.get(), part_a.get(), part_b.get());
+                                                    ix.cam_of.get(), ix.pt_of.get(), (T)desc.huber_delta, R.get(), OBS.get(),
+                                                    part_a.get(), part_b.get());
   }
 
   void run_cost(int which, double* robust, double* sq) {
@@ -160,19 +159,18 @@ struct BASolver : BASolverBase {
   void run_point_solve(bool build, T mu) {
     TimerScope ts(timers, build ? T_POINT_BLOCKS : T_POINT_SOLVE);
     const int g = div_up(n_pt, BA_TPB);
-    if (build)
-      point_solve_kernel<T, true><<<g, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), JP.get(), R.get(), mu, HPP.get(), GPT.get(),
-                                                       HPPINV.get(), TP.get(), V.get());
-    else
-      point_solve_kernel<T, false><<<g, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), JP.get(), R.get(), mu, HPP.get(), GPT.get(),
-                                                        HPPINV.get(), TP.get(), V.get());
+#define ISFM_PS(B, W)                                                                                              \
+  point_solve_kernel<T, D, B, W><<<g, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), OBS.get(), R.get(), mu, HPP.get(), GPT.get(), \
+                                                      HPPINV.get(), TP.get())
+    if (desc.optimize_poses) { if (build) ISFM_PS(true, true); else ISFM_PS(false, true); }
+    else { if (build) ISFM_PS(true, false); else ISFM_PS(false, false); }
+#undef ISFM_PS
   }
 
   void run_camera_hessian() {
     { TimerScope ts(timers, T_CAMERA_BLOCKS);
       camera_blocks_kernel<T, D, false><<<(int)n_cam, CAM_TPB, 0, s>>>(ix.cam_off.get(), ix.cam_perm.get(), ix.pt_of.get(),
-                                                                      JC.get(), R.get(), JP.get(), nullptr, nullptr, HCC(),
-                                                                      nullptr, GC()); }
+                                                                      OBS.get(), R.get(), nullptr, HCC(), nullptr, GC()); }
     if (comm_world(comm) > 1) {
       TimerScope ts(timers, T_COMM);
       comm_allreduce_sum(comm, HCC_GC.get(), (size_t)n_cam * (D * D + D), sizeof(T) == 8, s);
@@ -183,13 +181,13 @@ struct BASolver : BASolverBase {
   int run_schur_and_pcg(T mu, int* pcg_status) {
     { TimerScope ts(timers, T_CAMERA_BLOCKS);
       camera_blocks_kernel<T, D, true><<<(int)n_cam, CAM_TPB, 0, s>>>(ix.cam_off.get(), ix.cam_perm.get(), ix.pt_of.get(),
-                                                                     JC.get(), R.get(), JP.get(), V.get(), TP.get(), E.get(),
-                                                                     sp.diag_slot.get(), EG.get()); }
+                                                                     OBS.get(), R.get(), TP.get(), E.get(), sp.diag_slot.get(),
+                                                                     EG.get()); }
     if (sp.n_lists > 0) {
       TimerScope ts(timers, T_SCHUR_OFFDIAG);
-      dim3 grid(div_up(sp.n_lists, 4), D / SchurTile<D>::CT);
-      schur_offdiag_kernel<T, D><<<grid, 128, 0, s>>>(sp.n_lists, sp.list_off.get(), sp.pairs.get(), sp.list_slot.get(),
-                                                      sp.list_slot_t.get(), JC.get(), JP.get(), V.get(), E.get());
+      const int lists_per_cta = SchurGroup<D>::PER_WARP * (SCHUR_TPB / 32);
+      schur_offdiag_kernel<T, D><<<div_up(sp.n_lists, lists_per_cta), SCHUR_TPB, 0, s>>>(
+          sp.n_lists, sp.list_off.get(), sp.pairs.get(), sp.list_slot.get(), sp.list_slot_t.get(), OBS.get(), E.get());
     }
     { TimerScope ts(timers, T_PRECOND);
       gather_diag_kernel<T, D><<<div_up(n_cam * (D * D + D), BA_TPB), BA_TPB, 0, s>>>((int)n_cam, sp.diag_slot.get(), E.get(),
@@ -236,7 +234,7 @@ struct BASolver : BASolverBase {
         stats.pcg_iters += run_schur_and_pcg((T)mu, &pcg_status);
         { TimerScope ts(timers, T_BACKSUB);
           mterm_parts = red_grid(n_pt);
-          backsub_kernel<T, D><<<mterm_parts, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), ix.cam_of.get(), JC.get(), JP.get(), R.get(),
+          backsub_kernel<T, D><<<mterm_parts, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), ix.cam_of.get(), OBS.get(), R.get(),
                                                              GPT.get(), HPPINV.get(), pcg.x.get(), pts[cur].get(),
                                                              pts[trial].get(), DP.get(), part_c.get()); }
         { TimerScope ts(timers, T_UPDATE);
@@ -245,7 +243,7 @@ struct BASolver : BASolverBase {
       } else {
         TimerScope ts(timers, T_BACKSUB);
         mterm_parts = red_grid(n_pt);
-        point_only_step_kernel<T><<<mterm_parts, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), JP.get(), R.get(), TP.get(),
+        point_only_step_kernel<T, D><<<mterm_parts, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), OBS.get(), R.get(), TP.get(),
                                                                  pts[cur].get(), pts[trial].get(), DP.get(), part_c.get());
         ISFM_CUDA(cudaMemcpyAsync(cam[trial].get(), cam[cur].get(), (size_t)n_cam * CW * sizeof(T), cudaMemcpyDeviceToDevice, s));
       }
@@ -338,14 +336,15 @@ struct BASolver : BASolverBase {
     if (col_idx) { d2h(h, sp.col_idx.get(), (size_t)sp.nnzb, s); std::copy(h.begin(), h.end(), col_idx); }
   }
 
-  // copies a [n_obs, W] sorted-order buffer back in the caller's observation order
-  void unsort_rows(const T* dev, int W, void* dst) {
+  // copies columns [off, off + W) of a [n_obs, stride] sorted-order buffer back in the caller's
+  // observation order
+  void unsort_rows(const T* dev, int stride, int off, int W, void* dst) {
     std::vector<T> h; std::vector<int32_t> perm;
-    d2h(h, dev, (size_t)n_obs * W, s);
+    d2h(h, dev, (size_t)n_obs * stride, s);
     d2h(perm, ix.obs_perm.get(), (size_t)n_obs, s);
     T* out = static_cast<T*>(dst);
     for (int64_t a = 0; a < n_obs; ++a)
-      for (int k = 0; k < W; ++k) out[(size_t)perm[a] * W + k] = h[(size_t)a * W + k];
+      for (int k = 0; k < W; ++k) out[(size_t)perm[a] * W + k] = h[(size_t)a * stride + off + k];
   }
 
   void debug_get(int what, void* dst) override {
@@ -364,16 +363,16 @@ struct BASolver : BASolverBase {
       DeviceBuffer<T> tmp; tmp.alloc((size_t)n_obs * 2);
       residual_kernel<T, MODEL><<<div_up(n_obs, BA_TPB), BA_TPB, 0, s>>>(n_obs, cam[cur].get(), pp.get(), pts[cur].get(),
                                                                        obs.get(), ix.cam_of.get(), ix.pt_of.get(), tmp.get());
-      unsort_rows(tmp.get(), 2, dst);
+      unsort_rows(tmp.get(), 2, 0, 2, dst);
       return;
     }
     const T mu = (T)(1.0 + tr.damping);
     run_linearize();
     run_point_solve(true, mu);
     switch (what) {
-      case ISFM_BA_JAC_CAM: unsort_rows(JC.get(), 2 * D, dst); return;
-      case ISFM_BA_JAC_POINT: unsort_rows(JP.get(), 6, dst); return;
-      case ISFM_BA_WEIGHTED_RES: unsort_rows(R.get(), 2, dst); return;
+      case ISFM_BA_JAC_CAM: unsort_rows(OBS.get(), REC, 0, 2 * D, dst); return;
+      case ISFM_BA_JAC_POINT: unsort_rows(OBS.get(), REC, ObsRec<D>::JP, 6, dst); return;
+      case ISFM_BA_WEIGHTED_RES: unsort_rows(R.get(), 2, 0, 2, dst); return;
       case ISFM_BA_HPP: ISFM_CUDA(cudaMemcpyAsync(dst, HPP.get(), (size_t)n_pt * 6 * sizeof(T), cudaMemcpyDeviceToHost, s)); break;
       case ISFM_BA_GP: ISFM_CUDA(cudaMemcpyAsync(dst, GPT.get(), (size_t)n_pt * 3 * sizeof(T), cudaMemcpyDeviceToHost, s)); break;
       default: {

@@ -41,10 +41,11 @@ def update(cameras, images, tracks, track_keys, unique_cameras, unique_points, r
 
 
 class TorchBA:
-    def __init__(self, visualizer=None, device="cuda:0", dtype=np.float32):
+    def __init__(self, visualizer=None, device="cuda:0", dtype=np.float32, pcg_tol=1e-6):
         self.device = device
         self.visualizer = visualizer
         self.dtype = dtype
+        self.pcg_tol = pcg_tol
         self.loss_history = []
         self.last_stats = []
 
@@ -99,7 +100,7 @@ class TorchBA:
         import torch
         with torch.cuda.device(device_index(self.device)):
             engine = BAEngine(model_value, optimize_poses=opts["optimize_poses"],
-                              huber_delta=opts["thres_loss_function"], dtype=self.dtype)
+                              huber_delta=opts["thres_loss_function"], dtype=self.dtype, pcg_tol=self.pcg_tol)
             engine.set_problem(t["camera_params"], t["camera_pps"], t["points_3d"], t["points_2d"],
                                t["camera_indices"], t["point_indices"])
 

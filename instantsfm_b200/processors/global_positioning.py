@@ -7,10 +7,11 @@ from ._common import concat_features, device_index, flatten_observations, should
 
 
 class TorchGP:
-    def __init__(self, visualizer=None, device="cuda:0", dtype=np.float32):
+    def __init__(self, visualizer=None, device="cuda:0", dtype=np.float32, pcg_tol=1e-6):
         self.device = device
         self.visualizer = visualizer
         self.dtype = dtype
+        self.pcg_tol = pcg_tol
         self.loss_history = []
 
     def InitializeRandomPositions(self, cameras, images, tracks, depths=None):
@@ -85,7 +86,8 @@ class TorchGP:
 
         import torch
         with torch.cuda.device(device_index(self.device)):
-            engine = GPEngine(huber_delta=opts["thres_loss_function"], dtype=self.dtype, optimize_scales=not depth_only)
+            engine = GPEngine(huber_delta=opts["thres_loss_function"], dtype=self.dtype, optimize_scales=not depth_only,
+                              pcg_tol=self.pcg_tol)
             engine.set_problem(centres, points_3d, scales_t, translations, image_id2idx[image_id].astype(np.int32),
                                which.astype(np.int32), is_calibrated, fixed_t)
 
