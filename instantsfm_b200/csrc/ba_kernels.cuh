@@ -334,7 +334,7 @@ camera_blocks_kernel(const int32_t* __restrict__ cam_off, const int32_t* __restr
 // Jc_a^T (V_a Jp_b^T) Jc_b.  A group of D lanes owns one list; lane c owns column c of the
 // D x D block (D accumulators), so every pair costs 12 + 4 + 2D FMAs per lane and nothing is
 // reduced across lanes.  Records are fetched with 128-bit loads that broadcast inside the
-// group.  Block (j, i) gets the transpose; diagonal lists (same camera twice in a track) add
+// group.  Only the upper triangle is stored; diagonal lists (same camera twice in a track) add
 // onto E_ii written by the camera pass.  No atomics.
 // ---------------------------------------------------------------------------------------
 template <int D> struct SchurGroup { static constexpr int PER_WARP = 32 / D; };
@@ -343,7 +343,7 @@ constexpr int SCHUR_TPB = 128;
 template <typename T, int D>
 __global__ void __launch_bounds__(SCHUR_TPB)
 schur_offdiag_kernel(int64_t n_lists, const int64_t* __restrict__ list_off, const uint64_t* __restrict__ pairs,
-                     const int32_t* __restrict__ list_slot, const int32_t* __restrict__ list_slot_t,
+                     const int32_t* __restrict__ list_slot, const uint8_t* __restrict__ list_diag,
                      const T* __restrict__ OBS, T* __restrict__ E) {
   constexpr int REC = ObsRec<D>::REC, OJP = ObsRec<D>::JP, OV = ObsRec<D>::V;
   constexpr int GPW = SchurGroup<D>::PER_WARP;
@@ -376,12 +376,10 @@ schur_offdiag_kernel(int64_t n_lists, const int64_t* __restrict__ list_off, cons
 #pragma unroll
     for (int r = 0; r < D; ++r) acc[r] += ja[r] * t0 + ja[D + r] * t1;
   }
-  const int slot = list_slot[u], slot_t = list_slot_t[u];
-  T* blk = E + (size_t)slot * (D * D);
-  if (slot_t >= 0) {
-    T* blk_t = E + (size_t)slot_t * (D * D);
+  T* blk = E + (size_t)list_slot[u] * (D * D);
+  if (!list_diag[u]) {
 #pragma unroll
-    for (int r = 0; r < D; ++r) { blk[r * D + c] = acc[r]; blk_t[c * D + r] = acc[r]; }
+    for (int r = 0; r < D; ++r) blk[r * D + c] = acc[r];
   } else {
 #pragma unroll
     for (int r = 0; r < D; ++r) blk[r * D + c] += acc[r];

@@ -4,6 +4,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "ba_kernels.cuh"
 #include "comm.cuh"
@@ -114,9 +115,9 @@ struct BASolver : BASolverBase {
     if (desc.optimize_poses) {
       build_schur_pattern(sp, ix, s, timers);
       HCC_GC.alloc((size_t)nc * (D * D + D)); HD.alloc((size_t)nc * D * D);
-      E.alloc((size_t)sp.nnzb * D * D); EG.alloc((size_t)nc * D); RED.alloc((size_t)nc * (D * D + D));
+      E.alloc((size_t)sp.nnzu * D * D); EG.alloc((size_t)nc * D); RED.alloc((size_t)nc * (D * D + D));
       MINV.alloc((size_t)nc * D * D); bvec.alloc((size_t)nc * D);
-      pcg.resize((int)nc);
+      pcg.resize((int)nc, sp.n_off);
     }
     ISFM_CUDA(cudaStreamSynchronize(s));
     cur = 0; have_loss = false; has_problem = true;
@@ -187,7 +188,7 @@ struct BASolver : BASolverBase {
       TimerScope ts(timers, T_SCHUR_OFFDIAG);
       const int lists_per_cta = SchurGroup<D>::PER_WARP * (SCHUR_TPB / 32);
       schur_offdiag_kernel<T, D><<<div_up(sp.n_lists, lists_per_cta), SCHUR_TPB, 0, s>>>(
-          sp.n_lists, sp.list_off.get(), sp.pairs.get(), sp.list_slot.get(), sp.list_slot_t.get(), OBS.get(), E.get());
+          sp.n_lists, sp.list_off.get(), sp.pairs.get(), sp.list_slot.get(), sp.list_diag.get(), OBS.get(), E.get());
     }
     { TimerScope ts(timers, T_PRECOND);
       gather_diag_kernel<T, D><<<div_up(n_cam * (D * D + D), BA_TPB), BA_TPB, 0, s>>>((int)n_cam, sp.diag_slot.get(), E.get(),
@@ -200,8 +201,8 @@ struct BASolver : BASolverBase {
       precond_kernel<T, D><<<div_up(n_cam, 64), 64, 0, s>>>((int)n_cam, HCC(), GC(), RED.get(), mu, HD.get(), MINV.get(),
                                                             bvec.get(), fail.get()); }
     int max_iter = desc.pcg_max_iter > 0 ? desc.pcg_max_iter : (int)std::min<int64_t>(10 * n_cam * D, 5000);
-    return pcg.solve(sp.row_ptr.get(), sp.col_idx.get(), E.get(), HD.get(), MINV.get(), bvec.get(), desc.pcg_tol, max_iter,
-                     comm, s, timers, pcg_status);
+    return pcg.solve(sp.urow_ptr.get(), sp.ucol.get(), sp.tpos.get(), sp.lrow_ptr.get(), E.get(), HD.get(), MINV.get(),
+                     bvec.get(), desc.pcg_tol, max_iter, comm, s, timers, pcg_status);
   }
 
   void step(double* loss_out, isfm_step_stats* st) override {
@@ -225,7 +226,8 @@ struct BASolver : BASolverBase {
     int rejects = 0;
     const int trial = cur ^ 1;
     while (last <= loss) {
-      mu *= 1.0 + tr.damping;  // cumulative across rejected trials (pypose LM)
+      // cumulative across rejected trials (pypose LM); capped so that damped blocks stay finite in T
+      mu = std::min(mu * (1.0 + tr.damping), sizeof(T) == 4 ? 1e24 : 1e100);
       run_point_solve(!built, (T)mu);
       built = true;
       int mterm_parts;
@@ -259,6 +261,9 @@ struct BASolver : BASolverBase {
       stats.trials++;
       stats.model_term = -mterm;
       stats.quality = tr.update(last, new_loss, mterm);
+      if (getenv("ISFM_DEBUG"))
+        fprintf(stderr, "[isfm] trial %d mu %.3e last %.17g new %.17g mterm %.6e quality %.4f pcg_iters %d damping->%.3e\n",
+                stats.trials, mu, last, new_loss, mterm, stats.quality, stats.pcg_iters, tr.damping);
       const bool worse = !(new_loss <= last);  // NaN counts as worse (the reference would keep it)
       if (worse && rejects < desc.reject) {
         rejects++;
@@ -327,13 +332,27 @@ struct BASolver : BASolverBase {
     if (cam_off) { d2h(h, ix.cam_off.get(), (size_t)n_cam + 1, s); std::copy(h.begin(), h.end(), cam_off); }
   }
 
+  // full (both triangles) BSR pattern, rebuilt on the host from the stored upper triangle
   void get_schur_pattern(int64_t* nnzb, int64_t* n_pairs, int64_t* row_ptr, int32_t* col_idx) override {
     ISFM_REQUIRE(has_problem && desc.optimize_poses, ISFM_ESTATE, "no reduced camera system (optimize_poses = 0?)");
-    if (nnzb) *nnzb = sp.nnzb;
+    if (nnzb) *nnzb = sp.nnzu + sp.n_off;
     if (n_pairs) *n_pairs = sp.n_pairs;
-    std::vector<int32_t> h;
-    if (row_ptr) { d2h(h, sp.row_ptr.get(), (size_t)n_cam + 1, s); std::copy(h.begin(), h.end(), row_ptr); }
-    if (col_idx) { d2h(h, sp.col_idx.get(), (size_t)sp.nnzb, s); std::copy(h.begin(), h.end(), col_idx); }
+    if (!row_ptr && !col_idx) return;
+    std::vector<int32_t> up, uc;
+    d2h(up, sp.urow_ptr.get(), (size_t)n_cam + 1, s); d2h(uc, sp.ucol.get(), (size_t)sp.nnzu, s);
+    std::vector<std::vector<int32_t>> rows((size_t)n_cam);
+    for (int64_t i = 0; i < n_cam; ++i)
+      for (int e = up[i]; e < up[i + 1]; ++e) {
+        rows[i].push_back(uc[e]);
+        if (uc[e] != i) rows[uc[e]].push_back((int32_t)i);
+      }
+    int64_t pos = 0;
+    for (int64_t i = 0; i < n_cam; ++i) {
+      std::sort(rows[i].begin(), rows[i].end());
+      if (row_ptr) row_ptr[i] = pos;
+      for (int32_t c : rows[i]) { if (col_idx) col_idx[pos] = c; ++pos; }
+    }
+    if (row_ptr) row_ptr[n_cam] = pos;
   }
 
   // copies columns [off, off + W) of a [n_obs, stride] sorted-order buffer back in the caller's
@@ -385,8 +404,8 @@ struct BASolver : BASolverBase {
         run_schur_and_pcg(mu, &status);
         if (what == ISFM_BA_SCHUR_RHS) { ISFM_CUDA(cudaMemcpyAsync(dst, bvec.get(), (size_t)n_cam * D * sizeof(T), cudaMemcpyDeviceToHost, s)); break; }
         std::vector<T> hE, hHD; std::vector<int32_t> rp, ci;
-        d2h(hE, E.get(), (size_t)sp.nnzb * D * D, s); d2h(hHD, HD.get(), (size_t)n_cam * D * D, s);
-        d2h(rp, sp.row_ptr.get(), (size_t)n_cam + 1, s); d2h(ci, sp.col_idx.get(), (size_t)sp.nnzb, s);
+        d2h(hE, E.get(), (size_t)sp.nnzu * D * D, s); d2h(hHD, HD.get(), (size_t)n_cam * D * D, s);
+        d2h(rp, sp.urow_ptr.get(), (size_t)n_cam + 1, s); d2h(ci, sp.ucol.get(), (size_t)sp.nnzu, s);
         const size_t n = (size_t)n_cam * D;
         T* out = static_cast<T*>(dst);
         std::fill(out, out + n * n, T(0));
@@ -395,7 +414,11 @@ struct BASolver : BASolverBase {
             for (int c = 0; c < D; ++c) out[(i * D + r) * n + i * D + c] = hHD[(size_t)i * D * D + r * D + c];
           for (int e = rp[i]; e < rp[i + 1]; ++e)
             for (int r = 0; r < D; ++r)
-              for (int c = 0; c < D; ++c) out[(i * D + r) * n + (size_t)ci[e] * D + c] -= hE[(size_t)e * D * D + r * D + c];
+              for (int c = 0; c < D; ++c) {
+                const T v = hE[(size_t)e * D * D + r * D + c];
+                out[(i * D + r) * n + (size_t)ci[e] * D + c] -= v;
+                if (ci[e] != i) out[((size_t)ci[e] * D + c) * n + i * D + r] -= v;   // mirrored block
+              }
         }
         return;
       }

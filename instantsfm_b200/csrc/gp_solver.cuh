@@ -173,11 +173,11 @@ gp_camera_blocks_kernel(const int32_t* __restrict__ cam_off, const int32_t* __re
     out[(size_t)cam * GP_CAM_ACC + threadIdx.x] = sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x];
 }
 
-// warp per pair list: E_ij = sum W_a Q_b ; block (j, i) gets the transpose
+// warp per pair list: E_ij = sum W_a Q_b (upper triangle only)
 template <typename T>
 __global__ void __launch_bounds__(128)
 gp_schur_offdiag_kernel(int64_t n_lists, const int64_t* __restrict__ list_off, const uint64_t* __restrict__ pairs,
-                        const int32_t* __restrict__ list_slot, const int32_t* __restrict__ list_slot_t,
+                        const int32_t* __restrict__ list_slot, const uint8_t* __restrict__ list_diag,
                         const T* __restrict__ QW, T* __restrict__ E) {
   const int lane = threadIdx.x & 31;
   const int64_t u = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -196,13 +196,12 @@ gp_schur_offdiag_kernel(int64_t n_lists, const int64_t* __restrict__ list_off, c
 #pragma unroll
   for (int i = 0; i < 9; ++i)
     for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-  const int slot = list_slot[u], slot_t = list_slot_t[u];
+  const int slot = list_slot[u];
   if (lane < 9) {
-    const int r = lane / 3, c = lane % 3;
     T v = T(0);
 #pragma unroll
     for (int i = 0; i < 9; ++i) if (lane == i) v = acc[i];
-    if (slot_t >= 0) { E[(size_t)slot * 9 + lane] = v; E[(size_t)slot_t * 9 + 3 * c + r] = v; }
+    if (!list_diag[u]) E[(size_t)slot * 9 + lane] = v;
     else E[(size_t)slot * 9 + lane] += v;
   }
 }
@@ -369,11 +368,11 @@ struct GPSolver : GPSolverBase {
     A.alloc((size_t)no); JV.alloc((size_t)no * 3); RT.alloc((size_t)no * 3); QW.alloc((size_t)no * 15);
     HINV.alloc((size_t)np * 6); GX.alloc((size_t)np * 3); TP.alloc((size_t)np * 3);
     ACC.alloc((size_t)nc * GP_CAM_ACC); ACCSUM.alloc((size_t)nc * GP_CAM_ACC);
-    E.alloc((size_t)sp.nnzb * 9); HD.alloc((size_t)nc * 9); MINV.alloc((size_t)nc * 9); bvec.alloc((size_t)nc * 3);
+    E.alloc((size_t)sp.nnzu * 9); HD.alloc((size_t)nc * 9); MINV.alloc((size_t)nc * 9); bvec.alloc((size_t)nc * 3);
     part_a.alloc(std::max<int64_t>(RED_BLOCKS, nc)); part_b.alloc(std::max<int64_t>(RED_BLOCKS, nc));
     part_c.alloc(std::max<int64_t>(RED_BLOCKS, nc));
     scalars.alloc(4); fail.alloc(1); fail.zero(s);
-    pcg.resize((int)nc);
+    pcg.resize((int)nc, sp.n_off);
     ISFM_CUDA(cudaStreamSynchronize(s));
     cur = 0; have_loss = false; has_problem = true;
     tr.init(desc.tr_radius, desc.tr_max, desc.tr_up, desc.tr_down);
@@ -420,7 +419,7 @@ struct GPSolver : GPSolverBase {
     int rejects = 0;
     const int trial = cur ^ 1;
     while (last <= loss) {
-      mu *= 1.0 + tr.damping;
+      mu = std::min(mu * (1.0 + tr.damping), sizeof(T) == 4 ? 1e24 : 1e100);
       const T m = (T)mu;
       { TimerScope ts(timers, T_POINT_SOLVE);
         gp_point_solve_kernel<T><<<div_up(n_pt, GP_TPB), GP_TPB, 0, s>>>(n_pt, ix.pt_off.get(), ix.obs_perm.get(), fixed_ptr(),
@@ -441,13 +440,13 @@ struct GPSolver : GPSolverBase {
       if (sp.n_lists > 0) {
         TimerScope ts(timers, T_SCHUR_OFFDIAG);
         gp_schur_offdiag_kernel<T><<<div_up(sp.n_lists, 4), 128, 0, s>>>(sp.n_lists, sp.list_off.get(), sp.pairs.get(),
-                                                                        sp.list_slot.get(), sp.list_slot_t.get(), QW.get(),
+                                                                        sp.list_slot.get(), sp.list_diag.get(), QW.get(),
                                                                         E.get());
       }
       int pcg_status = 0;
       int max_iter = desc.pcg_max_iter > 0 ? desc.pcg_max_iter : (int)std::min<int64_t>(10 * n_cam * 3, 5000);
-      stats.pcg_iters += pcg.solve(sp.row_ptr.get(), sp.col_idx.get(), E.get(), HD.get(), MINV.get(), bvec.get(), desc.pcg_tol,
-                                   max_iter, comm, s, timers, &pcg_status);
+      stats.pcg_iters += pcg.solve(sp.urow_ptr.get(), sp.ucol.get(), sp.tpos.get(), sp.lrow_ptr.get(), E.get(), HD.get(),
+                                   MINV.get(), bvec.get(), desc.pcg_tol, max_iter, comm, s, timers, &pcg_status);
       const int mparts = red_grid(n_pt);
       { TimerScope ts(timers, T_BACKSUB);
         gp_backsub_kernel<T><<<mparts, GP_TPB, 0, s>>>(n_pt, ix.pt_off.get(), ix.cam_of.get(), ix.obs_perm.get(), fixed_ptr(),

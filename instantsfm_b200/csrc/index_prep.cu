@@ -67,25 +67,20 @@ __global__ void pair_fill_kernel(const int32_t* __restrict__ pt_of, const int32_
   }
 }
 
-// BSR entry keys: for each list u with i < j: (i, j) and (j, i); for each camera: (i, i).
-// tag: u*2 (upper) / u*2+1 (lower) for list entries, -(i+1) for diagonal entries.
-__global__ void bsr_keys_kernel(const uint64_t* __restrict__ list_key, int64_t n_lists, int64_t n_cam,
-                                uint64_t* keys, int64_t* tags) {
+// upper-BSR entry keys: every list (i <= j) and every camera's diagonal (i, i); tag = list id
+// or -(i + 1).  Diagonal lists and diagonal entries share a key: a later pass keeps one.
+__global__ void upper_keys_kernel(const uint64_t* __restrict__ list_key, int64_t n_lists, int64_t n_cam,
+                                  uint64_t* keys, int64_t* tags) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t < n_lists) {
     uint64_t k = list_key[t];
-    uint64_t i = k / (uint64_t)n_cam, j = k % (uint64_t)n_cam;
-    if (i != j) {
-      keys[2 * t] = k; tags[2 * t] = 2 * t;
-      keys[2 * t + 1] = j * (uint64_t)n_cam + i; tags[2 * t + 1] = 2 * t + 1;
-    } else {  // diagonal list: no BSR entry of its own (sorts past every real key, dropped)
-      keys[2 * t] = ~0ull; tags[2 * t] = 0;
-      keys[2 * t + 1] = ~0ull; tags[2 * t + 1] = 0;
-    }
+    bool diag = (k / (uint64_t)n_cam) == (k % (uint64_t)n_cam);
+    keys[t] = diag ? ~0ull : k;          // diagonal lists own no entry: dropped after the sort
+    tags[t] = t;
   } else if (t < n_lists + n_cam) {
     int64_t i = t - n_lists;
-    keys[n_lists + t] = (uint64_t)i * (uint64_t)n_cam + (uint64_t)i;
-    tags[n_lists + t] = -(i + 1);
+    keys[t] = (uint64_t)i * (uint64_t)n_cam + (uint64_t)i;
+    tags[t] = -(i + 1);
   }
 }
 
@@ -94,27 +89,45 @@ __global__ void count_valid_kernel(const uint64_t* __restrict__ keys, int64_t n,
   if (t < n && keys[t] != ~0ull) atomicAdd(count, 1ull);  // set-up only; integer, order-free
 }
 
-__global__ void bsr_scatter_kernel(const uint64_t* __restrict__ keys, const int64_t* __restrict__ tags, int64_t nnzb,
-                                   int64_t n_cam, int32_t* col_idx, int32_t* row_of, int32_t* list_slot,
-                                   int32_t* list_slot_t, int32_t* diag_slot) {
+__global__ void upper_scatter_kernel(const uint64_t* __restrict__ keys, const int64_t* __restrict__ tags, int64_t nnzu,
+                                     int64_t n_cam, int32_t* ucol, int32_t* row_of, int32_t* list_slot, int32_t* diag_slot) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= nnzb) return;
+  if (e >= nnzu) return;
   uint64_t k = keys[e];
-  col_idx[e] = (int32_t)(k % (uint64_t)n_cam);
+  ucol[e] = (int32_t)(k % (uint64_t)n_cam);
   row_of[e] = (int32_t)(k / (uint64_t)n_cam);
   int64_t tag = tags[e];
   if (tag < 0) diag_slot[-tag - 1] = (int32_t)e;
-  else if (tag & 1) list_slot_t[tag >> 1] = (int32_t)e;
-  else list_slot[tag >> 1] = (int32_t)e;
+  else list_slot[tag] = (int32_t)e;
 }
 
 __global__ void diag_list_slot_kernel(const uint64_t* __restrict__ list_key, int64_t n_lists, int64_t n_cam,
-                                      const int32_t* __restrict__ diag_slot, int32_t* list_slot, int32_t* list_slot_t) {
+                                      const int32_t* __restrict__ diag_slot, int32_t* list_slot, uint8_t* list_diag) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n_lists) return;
   uint64_t k = list_key[t];
   uint64_t i = k / (uint64_t)n_cam, j = k % (uint64_t)n_cam;
-  if (i == j) { list_slot[t] = diag_slot[i]; list_slot_t[t] = -1; }
+  list_diag[t] = (i == j) ? 1 : 0;
+  if (i == j) list_slot[t] = diag_slot[i];
+}
+
+// lower ordering: key (j, i) for each strictly-upper entry e = (i, j); diagonal entries get ~0
+__global__ void lower_keys_kernel(const int32_t* __restrict__ row_of, const int32_t* __restrict__ ucol, int64_t nnzu,
+                                  int64_t n_cam, uint64_t* keys, int32_t* vals) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nnzu) return;
+  int32_t i = row_of[e], j = ucol[e];
+  keys[e] = (i == j) ? ~0ull : (uint64_t)j * (uint64_t)n_cam + (uint64_t)i;
+  vals[e] = (int32_t)e;
+}
+
+__global__ void lower_scatter_kernel(const uint64_t* __restrict__ keys_sorted, const int32_t* __restrict__ vals_sorted,
+                                     int64_t nnzu, int64_t n_off, int64_t n_cam, int32_t* tpos, int32_t* lrow_of) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= nnzu) return;
+  int32_t e = vals_sorted[k];
+  if (k < n_off) { tpos[e] = (int32_t)k; lrow_of[k] = (int32_t)(keys_sorted[k] / (uint64_t)n_cam); }
+  else tpos[e] = -1;
 }
 
 int bits_for(uint64_t max_value) {
@@ -224,29 +237,42 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
     ISFM_CUDA(cudaMemsetAsync(sp.list_off.get(), 0, sizeof(int64_t), s));
   }
   sp.n_lists = n_lists;
-  // 4. BSR pattern: both triangles + all diagonal blocks
-  const int64_t n_ent = 2 * n_lists + n_cam;
+  // 4. upper BSR pattern: strictly-upper lists + every diagonal block
+  const int64_t n_ent = n_lists + n_cam;
   DeviceBuffer<uint64_t> ekeys, ekeys_s; DeviceBuffer<int64_t> etags, etags_s;
   ekeys.alloc(n_ent); ekeys_s.alloc(n_ent); etags.alloc(n_ent); etags_s.alloc(n_ent);
-  bsr_keys_kernel<<<div_up(n_lists + n_cam, TPB), TPB, 0, s>>>(list_key.get(), n_lists, n_cam, ekeys.get(), etags.get());
+  upper_keys_kernel<<<div_up(n_ent, TPB), TPB, 0, s>>>(list_key.get(), n_lists, n_cam, ekeys.get(), etags.get());
   sort_pairs(ekeys.get(), ekeys_s.get(), etags.get(), etags_s.get(), n_ent, 64, s);
   DeviceBuffer<unsigned long long> valid; valid.alloc(1); valid.zero(s);
   count_valid_kernel<<<div_up(n_ent, TPB), TPB, 0, s>>>(ekeys_s.get(), n_ent, valid.get());
-  unsigned long long nnzb = 0;
-  ISFM_CUDA(cudaMemcpyAsync(&nnzb, valid.get(), sizeof(nnzb), cudaMemcpyDeviceToHost, s));
+  unsigned long long nnzu = 0;
+  ISFM_CUDA(cudaMemcpyAsync(&nnzu, valid.get(), sizeof(nnzu), cudaMemcpyDeviceToHost, s));
   ISFM_CUDA(cudaStreamSynchronize(s));
-  ISFM_REQUIRE(nnzb < (1ull << 31), ISFM_EINVAL, "reduced camera system has too many blocks for int32 slots");
-  sp.nnzb = (int64_t)nnzb;
-  sp.col_idx.alloc(nnzb); sp.row_ptr.alloc(n_cam + 1); sp.diag_slot.alloc(n_cam);
-  sp.list_slot.alloc(n_lists); sp.list_slot_t.alloc(n_lists);
-  DeviceBuffer<int32_t> row_of; row_of.alloc(nnzb);
-  bsr_scatter_kernel<<<div_up(nnzb, TPB), TPB, 0, s>>>(ekeys_s.get(), etags_s.get(), (int64_t)nnzb, n_cam, sp.col_idx.get(),
-                                                       row_of.get(), sp.list_slot.get(), sp.list_slot_t.get(),
-                                                       sp.diag_slot.get());
-  lower_bound_kernel<<<div_up(n_cam + 1, TPB), TPB, 0, s>>>(row_of.get(), (int64_t)nnzb, sp.row_ptr.get(), n_cam);
+  ISFM_REQUIRE(nnzu < (1ull << 31), ISFM_EINVAL, "reduced camera system has too many blocks for int32 slots");
+  sp.nnzu = (int64_t)nnzu;
+  sp.n_off = sp.nnzu - n_cam;
+  sp.ucol.alloc(nnzu); sp.urow_ptr.alloc(n_cam + 1); sp.diag_slot.alloc(n_cam); sp.tpos.alloc(nnzu);
+  sp.lrow_ptr.alloc(n_cam + 1);
+  sp.list_slot.alloc(n_lists); sp.list_diag.alloc(n_lists);
+  DeviceBuffer<int32_t> row_of; row_of.alloc(nnzu);
+  upper_scatter_kernel<<<div_up(nnzu, TPB), TPB, 0, s>>>(ekeys_s.get(), etags_s.get(), (int64_t)nnzu, n_cam, sp.ucol.get(),
+                                                         row_of.get(), sp.list_slot.get(), sp.diag_slot.get());
+  lower_bound_kernel<<<div_up(n_cam + 1, TPB), TPB, 0, s>>>(row_of.get(), (int64_t)nnzu, sp.urow_ptr.get(), n_cam);
   if (n_lists > 0)
     diag_list_slot_kernel<<<div_up(n_lists, TPB), TPB, 0, s>>>(list_key.get(), n_lists, n_cam, sp.diag_slot.get(),
-                                                               sp.list_slot.get(), sp.list_slot_t.get());
+                                                               sp.list_slot.get(), sp.list_diag.get());
+  // 5. lower ordering of the strictly-upper entries
+  {
+    DeviceBuffer<uint64_t> lkeys, lkeys_s; DeviceBuffer<int32_t> lvals, lvals_s, lrow_of;
+    lkeys.alloc(nnzu); lkeys_s.alloc(nnzu); lvals.alloc(nnzu); lvals_s.alloc(nnzu); lrow_of.alloc(sp.n_off);
+    lower_keys_kernel<<<div_up(nnzu, TPB), TPB, 0, s>>>(row_of.get(), sp.ucol.get(), (int64_t)nnzu, n_cam, lkeys.get(), lvals.get());
+    sort_pairs(lkeys.get(), lkeys_s.get(), lvals.get(), lvals_s.get(), (int64_t)nnzu, 64, s);
+    lower_scatter_kernel<<<div_up(nnzu, TPB), TPB, 0, s>>>(lkeys_s.get(), lvals_s.get(), (int64_t)nnzu, sp.n_off, n_cam,
+                                                           sp.tpos.get(), lrow_of.get());
+    lower_bound_kernel<<<div_up(n_cam + 1, TPB), TPB, 0, s>>>(lrow_of.get(), sp.n_off, sp.lrow_ptr.get(), n_cam);
+    ISFM_CUDA(cudaGetLastError());
+    ISFM_CUDA(cudaStreamSynchronize(s));
+  }
   ISFM_CUDA(cudaGetLastError());
   ISFM_CUDA(cudaStreamSynchronize(s));
 }

@@ -20,17 +20,24 @@ struct ObsIndex {
   DeviceBuffer<int32_t> cam_off;    // [n_cam + 1]
 };
 
-// Reduced camera system pattern: lists of observation pairs grouped by upper block (i <= j).
+// Reduced camera system pattern.  E = sum_p Hcp Hpp^-1 Hcp^T is symmetric: only its upper
+// triangle (block (i, j), i <= j, every diagonal block included) is stored, as BSR sorted by
+// (i, j).  The lists of observation pairs feeding each block are grouped in the same order.
+// For the symmetric mat-vec every strictly-upper entry also has a position in the row-major
+// ordering of the LOWER triangle (`tpos`), where its transposed product is deposited.
 struct SchurPattern {
   int64_t n_pairs = 0;   // total (a, b) pairs
   int64_t n_lists = 0;   // unique (i, j), i <= j, with at least one pair
-  int64_t nnzb = 0;      // BSR blocks, both triangles + every diagonal block
+  int64_t nnzu = 0;      // stored blocks: strictly-upper blocks + n_cam diagonal blocks
+  int64_t n_off = 0;     // strictly-upper blocks (= lower-triangle entries)
   DeviceBuffer<uint64_t> pairs;      // [n_pairs] (a << 32) | b, cam(a) <= cam(b), grouped by list
   DeviceBuffer<int64_t> list_off;    // [n_lists + 1]
-  DeviceBuffer<int32_t> list_slot;   // [n_lists] BSR slot of block (i, j)
-  DeviceBuffer<int32_t> list_slot_t; // [n_lists] BSR slot of block (j, i), -1 for diagonal lists
-  DeviceBuffer<int32_t> row_ptr;     // [n_cam + 1]
-  DeviceBuffer<int32_t> col_idx;     // [nnzb]
+  DeviceBuffer<int32_t> list_slot;   // [n_lists] upper slot of block (i, j)
+  DeviceBuffer<uint8_t> list_diag;   // [n_lists] 1 if i == j (accumulate onto the camera pass)
+  DeviceBuffer<int32_t> urow_ptr;    // [n_cam + 1] upper BSR
+  DeviceBuffer<int32_t> ucol;        // [nnzu]
+  DeviceBuffer<int32_t> tpos;        // [nnzu] position in the lower ordering, -1 for diagonal blocks
+  DeviceBuffer<int32_t> lrow_ptr;    // [n_cam + 1] lower triangle, row-major
   DeviceBuffer<int32_t> diag_slot;   // [n_cam]
 };
 

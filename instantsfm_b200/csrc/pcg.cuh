@@ -24,33 +24,61 @@ struct PcgState {
 
 constexpr int PCG_TPB = 128;
 
-// y_i = sum_j E_ij p_j ; one CTA per block row.  FUSED (single rank): q_i = Hd_i p_i - y_i
-// and the per-row partial of p.q.
-template <typename T, int D, bool FUSED>
+// Symmetric mat-vec y = E p with only the upper triangle of E stored (BSR, sorted by (i, j)).
+// One CTA per block row i.  Each warp streams its share of the row's blocks through a private
+// shared-memory stage with fully coalesced loads (a 128-byte line per warp instruction; the
+// D x D blocks are 36-byte-row AoS, unfriendly to direct per-lane row loads), then
+//   lane (b, r): yup_i[r] += sum_c B[r][c] p_j[c]                 (row r of block b)
+//   lane (b, c): C[tpos(e)][c] = sum_r B[r][c] p_i[r]             (B^T p_i, deposited at the
+//                position of block (j, i) in the row-major order of the lower triangle)
+// A second kernel adds row j's deposits: no atomics, deterministic.
+template <typename T, int D> struct SpmvCfg {
+  static constexpr int NW = PCG_TPB / 32;
+  static constexpr int GPW = 32 / D;                                 // blocks per warp pass
+  static constexpr int WB = GPW * (sizeof(T) == 4 ? 4 : 2);          // blocks staged per warp
+};
+
+template <typename T, int D>
 __global__ void __launch_bounds__(PCG_TPB)
-pcg_spmv_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
-                const T* __restrict__ E, const T* __restrict__ Hd, const T* __restrict__ p, T* __restrict__ out,
-                double* __restrict__ partial, const PcgState* __restrict__ st) {
+pcg_spmv_upper_kernel(const int32_t* __restrict__ urow_ptr, const int32_t* __restrict__ ucol,
+                      const int32_t* __restrict__ tpos, const T* __restrict__ EU, const T* __restrict__ p,
+                      T* __restrict__ yup, T* __restrict__ C, const PcgState* __restrict__ st) {
   if (st->done) return;
-  constexpr int BPW = 32 / D;          // blocks per warp iteration
-  constexpr int NW = PCG_TPB / 32;
+  constexpr int NW = SpmvCfg<T, D>::NW, GPW = SpmvCfg<T, D>::GPW, WB = SpmvCfg<T, D>::WB, DD = D * D;
+  __shared__ T stage[NW][WB * DD];
   __shared__ T sh[NW][D];
   const int row = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int bl = lane / D, r = lane % D;
+  const int beg = urow_ptr[row], end = urow_ptr[row + 1];
+  T pi[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) pi[c] = p[(size_t)row * D + c];
   T acc = T(0);
-  if (bl < BPW) {
-    const int beg = row_ptr[row], end = row_ptr[row + 1];
-    for (int b = beg + w * BPW + bl; b < end; b += NW * BPW) {
-      const T* __restrict__ e = E + (size_t)b * (D * D) + r * D;
-      const T* __restrict__ pj = p + (size_t)col_idx[b] * D;
+  for (int base = beg + w * WB; base < end; base += NW * WB) {
+    const int nb = min(WB, end - base);
+    const T* __restrict__ src = EU + (size_t)base * DD;
+    for (int k = lane; k < nb * DD; k += 32) stage[w][k] = src[k];
+    __syncwarp();
 #pragma unroll
-      for (int c = 0; c < D; ++c) acc += e[c] * pj[c];
+    for (int pass = 0; pass < WB / GPW; ++pass) {
+      const int b = pass * GPW + bl;
+      if (bl < GPW && b < nb) {
+        const int e = base + b;
+        const int j = ucol[e];
+        const T* B = stage[w] + b * DD;
+        const T* __restrict__ pj = p + (size_t)j * D;
+        T t = T(0);
+#pragma unroll
+        for (int c = 0; c < D; ++c) { acc += B[r * D + c] * pj[c]; t += B[c * D + r] * pi[c]; }
+        if (j != row) C[(size_t)tpos[e] * D + r] = t;
+      }
     }
+    __syncwarp();
   }
-  // fold the BPW block lanes of this warp onto lanes 0..D-1
+  // fold the GPW block lanes of this warp onto lanes 0..D-1, then the warps
 #pragma unroll
-  for (int k = 1; k < BPW; ++k) {
+  for (int k = 1; k < GPW; ++k) {
     T o = __shfl_sync(0xffffffffu, acc, (lane + k * D) & 31);
     if (lane < D) acc += o;
   }
@@ -60,15 +88,42 @@ pcg_spmv_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__
     T y = T(0);
 #pragma unroll
     for (int k = 0; k < NW; ++k) y += sh[k][threadIdx.x];
+    yup[(size_t)row * D + threadIdx.x] = y;
+  }
+}
+
+// y_i = yup_i + sum of the deposits of row i (contiguous in C).  FUSED (single rank):
+// q_i = Hd_i p_i - y_i and the per-row partial of p.q; otherwise y is written for the all-reduce.
+template <typename T, int D, bool FUSED>
+__global__ void __launch_bounds__(PCG_TPB)
+pcg_combine_kernel(const int32_t* __restrict__ lrow_ptr, const T* __restrict__ yup, const T* __restrict__ C,
+                   const T* __restrict__ Hd, const T* __restrict__ p, T* __restrict__ out, double* __restrict__ partial,
+                   const PcgState* __restrict__ st) {
+  if (st->done) return;
+  constexpr int G = PCG_TPB / D;   // entry groups per CTA; threads >= G * D idle
+  __shared__ T sh[G][D];
+  __shared__ T qs[D];
+  const int row = blockIdx.x;
+  const int g = threadIdx.x / D, c = threadIdx.x % D;
+  T acc = T(0);
+  if (g < G) {
+    const int beg = lrow_ptr[row], end = lrow_ptr[row + 1];
+    for (int k = beg + g; k < end; k += G) acc += C[(size_t)k * D + c];
+    sh[g][c] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < D) {
+    T y = yup[(size_t)row * D + threadIdx.x];
+    for (int k = 0; k < G; ++k) y += sh[k][threadIdx.x];
     if (FUSED) {
       const T* __restrict__ h = Hd + (size_t)row * (D * D) + threadIdx.x * D;
       const T* __restrict__ pi = p + (size_t)row * D;
       T q = T(0);
 #pragma unroll
-      for (int c = 0; c < D; ++c) q += h[c] * pi[c];
+      for (int k = 0; k < D; ++k) q += h[k] * pi[k];
       q -= y;
       out[(size_t)row * D + threadIdx.x] = q;
-      sh[0][threadIdx.x] = q * pi[threadIdx.x];
+      qs[threadIdx.x] = q * pi[threadIdx.x];
     } else {
       out[(size_t)row * D + threadIdx.x] = y;
     }
@@ -78,7 +133,7 @@ pcg_spmv_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__
     if (threadIdx.x == 0) {
       double s = 0.0;
 #pragma unroll
-      for (int c = 0; c < D; ++c) s += (double)sh[0][c];
+      for (int k = 0; k < D; ++k) s += (double)qs[k];
       partial[row] = s;
     }
   }
@@ -217,17 +272,18 @@ pcg_direction_kernel(int n_cam, int n_part, int n_part_pq, int it, double tol2, 
 template <typename T, int D>
 struct BlockPCG {
   int n_cam = 0;
-  DeviceBuffer<T> x, r, z, p, q, y;
+  DeviceBuffer<T> x, r, z, p, q, y, yup, C;
   DeviceBuffer<double> part_pq, part_a, part_b;
   DeviceBuffer<PcgState> state;
   PcgState* h_state = nullptr;  // pinned
 
   ~BlockPCG() { if (h_state) cudaFreeHost(h_state); }
 
-  void resize(int n) {
+  void resize(int n, int64_t n_off) {
     n_cam = n;
     size_t len = (size_t)n * D;
-    x.alloc(len); r.alloc(len); z.alloc(len); p.alloc(len); q.alloc(len); y.alloc(len);
+    x.alloc(len); r.alloc(len); z.alloc(len); p.alloc(len); q.alloc(len); y.alloc(len); yup.alloc(len);
+    C.alloc((size_t)std::max<int64_t>(n_off, 1) * D);
     part_pq.alloc(n); part_a.alloc(n); part_b.alloc(n);
     state.alloc(1);
     if (!h_state) ISFM_CUDA(cudaMallocHost(&h_state, sizeof(PcgState)));
@@ -235,8 +291,9 @@ struct BlockPCG {
 
   // Solves S x = b.  Returns iterations; result in x.  status: 1 converged, 0 hit max_iter,
   // 2 breakdown.
-  int solve(const int32_t* row_ptr, const int32_t* col_idx, const T* E, const T* Hd, const T* Minv, const T* b,
-            double tol, int max_iter, isfm_comm* comm, cudaStream_t s, KernelTimers& kt, int* status_out) {
+  int solve(const int32_t* urow_ptr, const int32_t* ucol, const int32_t* tpos, const int32_t* lrow_ptr, const T* E,
+            const T* Hd, const T* Minv, const T* b, double tol, int max_iter, isfm_comm* comm, cudaStream_t s,
+            KernelTimers& kt, int* status_out) {
     const int nb = div_up(n_cam, PCG_TPB);
     const bool multi = comm_world(comm) > 1;
     { TimerScope ts(kt, T_PCG_VEC);
@@ -250,12 +307,14 @@ struct BlockPCG {
     while (it < max_iter) {
       int chunk = std::min(check_every, max_iter - it);
       for (int k = 0; k < chunk; ++k, ++it) {
+        { TimerScope ts(kt, T_PCG_SPMV);
+          pcg_spmv_upper_kernel<T, D><<<n_cam, PCG_TPB, 0, s>>>(urow_ptr, ucol, tpos, E, p.get(), yup.get(), C.get(), state.get()); }
         if (!multi) {
-          TimerScope ts(kt, T_PCG_SPMV);
-          pcg_spmv_kernel<T, D, true><<<n_cam, PCG_TPB, 0, s>>>(row_ptr, col_idx, E, Hd, p.get(), q.get(), part_pq.get(), state.get());
+          TimerScope ts(kt, T_PCG_VEC);
+          pcg_combine_kernel<T, D, true><<<n_cam, PCG_TPB, 0, s>>>(lrow_ptr, yup.get(), C.get(), Hd, p.get(), q.get(), part_pq.get(), state.get());
         } else {
-          { TimerScope ts(kt, T_PCG_SPMV);
-            pcg_spmv_kernel<T, D, false><<<n_cam, PCG_TPB, 0, s>>>(row_ptr, col_idx, E, Hd, p.get(), y.get(), part_pq.get(), state.get()); }
+          { TimerScope ts(kt, T_PCG_VEC);
+            pcg_combine_kernel<T, D, false><<<n_cam, PCG_TPB, 0, s>>>(lrow_ptr, yup.get(), C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get()); }
           { TimerScope ts(kt, T_COMM);
             comm_allreduce_sum(comm, y.get(), (size_t)n_cam * D, sizeof(T) == 8, s); }
           { TimerScope ts(kt, T_PCG_VEC);

@@ -208,7 +208,9 @@ def test_noise_free_problem_recovers_ground_truth():
     hist = eng.solve(50, 1e-12)
     rob, sq = eng.cost()
     assert np.sqrt(sq / a.n_obs) < 1e-6
-    assert all(h2 <= h1 * (1 + 1e-12) for h1, h2 in zip(hist, hist[1:]))
+    # monotone until the fp64 noise floor (there, after `reject` failed trials the reference's
+    # LM keeps the last trial even if it is worse)
+    assert all(h2 <= h1 * (1 + 1e-12) for h1, h2 in zip(hist, hist[1:]) if h1 > 1e-15)
 
 
 def test_device_tensors_accepted():
