@@ -100,8 +100,9 @@ def algorithmic_bytes(name, n_obs, n_pt, n_cam, d, n_pairs, n_lists, nnzb, fsize
         "point_solve": n_obs * fsize * (6 + 6) + n_pt * (4 + fsize * (6 + 3 + 6 + 3)),
         # average of the H pass (idx 4, Jc, R) and the E pass (idx 8, Jc, V, Jp, t_p): reported per pass below
         "camera_blocks": n_obs * (6 + fsize * (2 * d + 1 + 6 + 1.5)) + n_cam * fsize * (dd + d),
-        "schur_offdiag": n_pairs * (8 + fsize * (4 * d + 12)) + n_lists * (16 + 2 * dd * fsize),
-        "pcg_spmv": nnzb * (dd * fsize + 4) + n_cam * fsize * (dd + 3 * d),
+        "schur_offdiag": n_pairs * (8 + fsize * (4 * d + 12)) + n_lists * (16 + dd * fsize),
+        # upper triangle only: blocks + col/tpos indices, B^T p_i deposits written, p gathered
+        "pcg_spmv": ((nnzb + n_cam) // 2) * (dd * fsize + 8) + ((nnzb - n_cam) // 2) * d * fsize + n_cam * d * fsize,
         "backsub": n_obs * (4 + fsize * (2 * d + 6 + 2)) + n_pt * fsize * (3 + 6 + 3 + 3 + 3),
         "cost": n_obs * (8 + 8) + n_pt * 3 * fsize + n_cam * (9 + d) * fsize,
     }

@@ -73,6 +73,7 @@ struct BASolver : BASolverBase {
   bool have_loss = false;
   double loss = 0.0;
   double mu_last = 1.0;
+  double min_damping = 0.0;   // floor on the LM damping used to build the systems (see DESIGN.md, fp32 conditioning)
 
   explicit BASolver(const isfm_ba_desc& d) : desc(d) {
     s = static_cast<cudaStream_t>(d.stream);
@@ -80,6 +81,7 @@ struct BASolver : BASolverBase {
     timers.stream = s;
     tr.init(d.tr_radius, d.tr_max, d.tr_up, d.tr_down);
     ISFM_CUDA(cudaMallocHost(&h_scalars, 4 * sizeof(double)));
+    if (const char* e = getenv("ISFM_MIN_DAMPING")) min_damping = atof(e);
   }
   ~BASolver() override { if (h_scalars) cudaFreeHost(h_scalars); }
 
@@ -117,7 +119,7 @@ struct BASolver : BASolverBase {
       HCC_GC.alloc((size_t)nc * (D * D + D)); HD.alloc((size_t)nc * D * D);
       E.alloc((size_t)sp.nnzu * D * D); EG.alloc((size_t)nc * D); RED.alloc((size_t)nc * (D * D + D));
       MINV.alloc((size_t)nc * D * D); bvec.alloc((size_t)nc * D);
-      pcg.resize((int)nc, sp.n_off);
+      pcg.resize((int)nc, sp.n_off, sp.n_chunks);
     }
     ISFM_CUDA(cudaStreamSynchronize(s));
     cur = 0; have_loss = false; has_problem = true;
@@ -201,7 +203,7 @@ struct BASolver : BASolverBase {
       precond_kernel<T, D><<<div_up(n_cam, 64), 64, 0, s>>>((int)n_cam, HCC(), GC(), RED.get(), mu, HD.get(), MINV.get(),
                                                             bvec.get(), fail.get()); }
     int max_iter = desc.pcg_max_iter > 0 ? desc.pcg_max_iter : (int)std::min<int64_t>(10 * n_cam * D, 5000);
-    return pcg.solve(sp.urow_ptr.get(), sp.ucol.get(), sp.tpos.get(), sp.lrow_ptr.get(), E.get(), HD.get(), MINV.get(),
+    return pcg.solve(sp, E.get(), HD.get(), MINV.get(),
                      bvec.get(), desc.pcg_tol, max_iter, comm, s, timers, pcg_status);
   }
 
@@ -227,7 +229,7 @@ struct BASolver : BASolverBase {
     const int trial = cur ^ 1;
     while (last <= loss) {
       // cumulative across rejected trials (pypose LM); capped so that damped blocks stay finite in T
-      mu = std::min(mu * (1.0 + tr.damping), sizeof(T) == 4 ? 1e24 : 1e100);
+      mu = std::min(mu * (1.0 + std::max(tr.damping, min_damping)), sizeof(T) == 4 ? 1e24 : 1e100);
       run_point_solve(!built, (T)mu);
       built = true;
       int mterm_parts;

@@ -372,7 +372,7 @@ struct GPSolver : GPSolverBase {
     part_a.alloc(std::max<int64_t>(RED_BLOCKS, nc)); part_b.alloc(std::max<int64_t>(RED_BLOCKS, nc));
     part_c.alloc(std::max<int64_t>(RED_BLOCKS, nc));
     scalars.alloc(4); fail.alloc(1); fail.zero(s);
-    pcg.resize((int)nc, sp.n_off);
+    pcg.resize((int)nc, sp.n_off, sp.n_chunks);
     ISFM_CUDA(cudaStreamSynchronize(s));
     cur = 0; have_loss = false; has_problem = true;
     tr.init(desc.tr_radius, desc.tr_max, desc.tr_up, desc.tr_down);
@@ -445,7 +445,7 @@ struct GPSolver : GPSolverBase {
       }
       int pcg_status = 0;
       int max_iter = desc.pcg_max_iter > 0 ? desc.pcg_max_iter : (int)std::min<int64_t>(10 * n_cam * 3, 5000);
-      stats.pcg_iters += pcg.solve(sp.urow_ptr.get(), sp.ucol.get(), sp.tpos.get(), sp.lrow_ptr.get(), E.get(), HD.get(),
+      stats.pcg_iters += pcg.solve(sp, E.get(), HD.get(),
                                    MINV.get(), bvec.get(), desc.pcg_tol, max_iter, comm, s, timers, &pcg_status);
       const int mparts = red_grid(n_pt);
       { TimerScope ts(timers, T_BACKSUB);

@@ -1,5 +1,6 @@
 // index_prep.cu -- see index_prep.cuh.
 #include <cub/cub.cuh>
+#include <vector>
 
 #include "index_prep.cuh"
 
@@ -271,6 +272,23 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
                                                            sp.tpos.get(), lrow_of.get());
     lower_bound_kernel<<<div_up(n_cam + 1, TPB), TPB, 0, s>>>(lrow_of.get(), sp.n_off, sp.lrow_ptr.get(), n_cam);
     ISFM_CUDA(cudaGetLastError());
+    ISFM_CUDA(cudaStreamSynchronize(s));
+  }
+  // 6. mat-vec chunks (host: n_cam + 1 integers)
+  {
+    std::vector<int32_t> up((size_t)n_cam + 1), crow, cbeg, cptr((size_t)n_cam + 1);
+    ISFM_CUDA(cudaMemcpyAsync(up.data(), sp.urow_ptr.get(), up.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < n_cam; ++i) {
+      cptr[i] = (int32_t)crow.size();
+      for (int32_t b = up[i]; b < up[i + 1]; b += SPMV_CHUNK) { crow.push_back((int32_t)i); cbeg.push_back(b); }
+    }
+    cptr[n_cam] = (int32_t)crow.size();
+    sp.n_chunks = (int64_t)crow.size();
+    sp.chunk_row.alloc(crow.size()); sp.chunk_beg.alloc(cbeg.size()); sp.chunk_ptr.alloc(cptr.size());
+    ISFM_CUDA(cudaMemcpyAsync(sp.chunk_row.get(), crow.data(), crow.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    ISFM_CUDA(cudaMemcpyAsync(sp.chunk_beg.get(), cbeg.data(), cbeg.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    ISFM_CUDA(cudaMemcpyAsync(sp.chunk_ptr.get(), cptr.data(), cptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ISFM_CUDA(cudaStreamSynchronize(s));
   }
   ISFM_CUDA(cudaGetLastError());

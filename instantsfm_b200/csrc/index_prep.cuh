@@ -39,7 +39,14 @@ struct SchurPattern {
   DeviceBuffer<int32_t> tpos;        // [nnzu] position in the lower ordering, -1 for diagonal blocks
   DeviceBuffer<int32_t> lrow_ptr;    // [n_cam + 1] lower triangle, row-major
   DeviceBuffer<int32_t> diag_slot;   // [n_cam]
+  // mat-vec work units: every upper row is cut into chunks of <= SPMV_CHUNK blocks so that the
+  // long rows of a dense system do not serialise on one CTA
+  int64_t n_chunks = 0;
+  DeviceBuffer<int32_t> chunk_row;   // [n_chunks]
+  DeviceBuffer<int32_t> chunk_beg;   // [n_chunks] first upper slot of the chunk
+  DeviceBuffer<int32_t> chunk_ptr;   // [n_cam + 1] first chunk of each row
 };
+constexpr int SPMV_CHUNK = 96;
 
 // cam_idx / pt_idx: device int32 [n_obs] in the caller's order.
 void build_obs_index(ObsIndex& ix, int64_t n_cam, int64_t n_pt, int64_t n_obs, const int32_t* cam_idx,

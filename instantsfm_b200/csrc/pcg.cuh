@@ -3,7 +3,7 @@
 //   S p = Hd p - E p
 //
 // Hd: damped block diagonal Hcc (replicated on every rank), E: this rank's Schur
-// contribution sum_p Hcp Hpp^-1 Hcp^T as BSR (both triangles).  With several ranks the only
+// contribution sum_p Hcp Hpp^-1 Hcp^T, upper triangle as BSR.  With several ranks the only
 // communication per iteration is the all-reduce of y = E p; every rank holds the full
 // vectors and computes the dot products redundantly (bit-identical across ranks).
 // Replaces bae.utils.pysolvers.PCG (bundle_adjustment.py:117): x0 = 0, stop when
@@ -11,6 +11,7 @@
 #pragma once
 #include "comm.cuh"
 #include "common.cuh"
+#include "index_prep.cuh"
 
 namespace isfm {
 
@@ -40,17 +41,19 @@ template <typename T, int D> struct SpmvCfg {
 
 template <typename T, int D>
 __global__ void __launch_bounds__(PCG_TPB)
-pcg_spmv_upper_kernel(const int32_t* __restrict__ urow_ptr, const int32_t* __restrict__ ucol,
+pcg_spmv_upper_kernel(const int32_t* __restrict__ chunk_row, const int32_t* __restrict__ chunk_beg,
+                      const int32_t* __restrict__ urow_ptr, const int32_t* __restrict__ ucol,
                       const int32_t* __restrict__ tpos, const T* __restrict__ EU, const T* __restrict__ p,
-                      T* __restrict__ yup, T* __restrict__ C, const PcgState* __restrict__ st) {
+                      T* __restrict__ yup_part, T* __restrict__ C, const PcgState* __restrict__ st) {
   if (st->done) return;
   constexpr int NW = SpmvCfg<T, D>::NW, GPW = SpmvCfg<T, D>::GPW, WB = SpmvCfg<T, D>::WB, DD = D * D;
-  __shared__ T stage[NW][WB * DD];
+  constexpr int STAGE = WB * DD, NLD = (STAGE + 31) / 32;
+  __shared__ T stage[NW][STAGE];
   __shared__ T sh[NW][D];
-  const int row = blockIdx.x;
+  const int row = chunk_row[blockIdx.x];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int bl = lane / D, r = lane % D;
-  const int beg = urow_ptr[row], end = urow_ptr[row + 1];
+  const int beg = chunk_beg[blockIdx.x], end = min(beg + SPMV_CHUNK, urow_ptr[row + 1]);
   T pi[D];
 #pragma unroll
   for (int c = 0; c < D; ++c) pi[c] = p[(size_t)row * D + c];
@@ -58,7 +61,12 @@ pcg_spmv_upper_kernel(const int32_t* __restrict__ urow_ptr, const int32_t* __res
   for (int base = beg + w * WB; base < end; base += NW * WB) {
     const int nb = min(WB, end - base);
     const T* __restrict__ src = EU + (size_t)base * DD;
-    for (int k = lane; k < nb * DD; k += 32) stage[w][k] = src[k];
+    // all loads of the stage are issued before the first store: NLD independent requests per lane
+    T tmp[NLD];
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) { const int k = lane + 32 * q; tmp[q] = (k < nb * DD) ? src[k] : T(0); }
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) { const int k = lane + 32 * q; if (k < STAGE) stage[w][k] = tmp[q]; }
     __syncwarp();
 #pragma unroll
     for (int pass = 0; pass < WB / GPW; ++pass) {
@@ -88,16 +96,18 @@ pcg_spmv_upper_kernel(const int32_t* __restrict__ urow_ptr, const int32_t* __res
     T y = T(0);
 #pragma unroll
     for (int k = 0; k < NW; ++k) y += sh[k][threadIdx.x];
-    yup[(size_t)row * D + threadIdx.x] = y;
+    yup_part[(size_t)blockIdx.x * D + threadIdx.x] = y;
   }
 }
 
-// y_i = yup_i + sum of the deposits of row i (contiguous in C).  FUSED (single rank):
-// q_i = Hd_i p_i - y_i and the per-row partial of p.q; otherwise y is written for the all-reduce.
+// y_i = sum of row i's chunk partials + sum of the deposits of row i (contiguous in C).
+// FUSED (single rank): q_i = Hd_i p_i - y_i and the per-row partial of p.q; otherwise y is
+// written for the all-reduce.
 template <typename T, int D, bool FUSED>
 __global__ void __launch_bounds__(PCG_TPB)
-pcg_combine_kernel(const int32_t* __restrict__ lrow_ptr, const T* __restrict__ yup, const T* __restrict__ C,
-                   const T* __restrict__ Hd, const T* __restrict__ p, T* __restrict__ out, double* __restrict__ partial,
+pcg_combine_kernel(const int32_t* __restrict__ lrow_ptr, const int32_t* __restrict__ chunk_ptr,
+                   const T* __restrict__ yup_part, const T* __restrict__ C, const T* __restrict__ Hd,
+                   const T* __restrict__ p, T* __restrict__ out, double* __restrict__ partial,
                    const PcgState* __restrict__ st) {
   if (st->done) return;
   constexpr int G = PCG_TPB / D;   // entry groups per CTA; threads >= G * D idle
@@ -107,13 +117,14 @@ pcg_combine_kernel(const int32_t* __restrict__ lrow_ptr, const T* __restrict__ y
   const int g = threadIdx.x / D, c = threadIdx.x % D;
   T acc = T(0);
   if (g < G) {
+    for (int k = chunk_ptr[row] + g; k < chunk_ptr[row + 1]; k += G) acc += yup_part[(size_t)k * D + c];
     const int beg = lrow_ptr[row], end = lrow_ptr[row + 1];
     for (int k = beg + g; k < end; k += G) acc += C[(size_t)k * D + c];
     sh[g][c] = acc;
   }
   __syncthreads();
   if (threadIdx.x < D) {
-    T y = yup[(size_t)row * D + threadIdx.x];
+    T y = T(0);
     for (int k = 0; k < G; ++k) y += sh[k][threadIdx.x];
     if (FUSED) {
       const T* __restrict__ h = Hd + (size_t)row * (D * D) + threadIdx.x * D;
@@ -279,10 +290,11 @@ struct BlockPCG {
 
   ~BlockPCG() { if (h_state) cudaFreeHost(h_state); }
 
-  void resize(int n, int64_t n_off) {
+  void resize(int n, int64_t n_off, int64_t n_chunks) {
     n_cam = n;
     size_t len = (size_t)n * D;
-    x.alloc(len); r.alloc(len); z.alloc(len); p.alloc(len); q.alloc(len); y.alloc(len); yup.alloc(len);
+    x.alloc(len); r.alloc(len); z.alloc(len); p.alloc(len); q.alloc(len); y.alloc(len);
+    yup.alloc((size_t)std::max<int64_t>(n_chunks, 1) * D);
     C.alloc((size_t)std::max<int64_t>(n_off, 1) * D);
     part_pq.alloc(n); part_a.alloc(n); part_b.alloc(n);
     state.alloc(1);
@@ -291,7 +303,7 @@ struct BlockPCG {
 
   // Solves S x = b.  Returns iterations; result in x.  status: 1 converged, 0 hit max_iter,
   // 2 breakdown.
-  int solve(const int32_t* urow_ptr, const int32_t* ucol, const int32_t* tpos, const int32_t* lrow_ptr, const T* E,
+  int solve(const SchurPattern& sp, const T* E,
             const T* Hd, const T* Minv, const T* b, double tol, int max_iter, isfm_comm* comm, cudaStream_t s,
             KernelTimers& kt, int* status_out) {
     const int nb = div_up(n_cam, PCG_TPB);
@@ -308,13 +320,14 @@ struct BlockPCG {
       int chunk = std::min(check_every, max_iter - it);
       for (int k = 0; k < chunk; ++k, ++it) {
         { TimerScope ts(kt, T_PCG_SPMV);
-          pcg_spmv_upper_kernel<T, D><<<n_cam, PCG_TPB, 0, s>>>(urow_ptr, ucol, tpos, E, p.get(), yup.get(), C.get(), state.get()); }
+          pcg_spmv_upper_kernel<T, D><<<(int)sp.n_chunks, PCG_TPB, 0, s>>>(sp.chunk_row.get(), sp.chunk_beg.get(), sp.urow_ptr.get(), sp.ucol.get(),
+                                                                           sp.tpos.get(), E, p.get(), yup.get(), C.get(), state.get()); }
         if (!multi) {
           TimerScope ts(kt, T_PCG_VEC);
-          pcg_combine_kernel<T, D, true><<<n_cam, PCG_TPB, 0, s>>>(lrow_ptr, yup.get(), C.get(), Hd, p.get(), q.get(), part_pq.get(), state.get());
+          pcg_combine_kernel<T, D, true><<<n_cam, PCG_TPB, 0, s>>>(sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(), C.get(), Hd, p.get(), q.get(), part_pq.get(), state.get());
         } else {
           { TimerScope ts(kt, T_PCG_VEC);
-            pcg_combine_kernel<T, D, false><<<n_cam, PCG_TPB, 0, s>>>(lrow_ptr, yup.get(), C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get()); }
+            pcg_combine_kernel<T, D, false><<<n_cam, PCG_TPB, 0, s>>>(sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(), C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get()); }
           { TimerScope ts(kt, T_COMM);
             comm_allreduce_sum(comm, y.get(), (size_t)n_cam * D, sizeof(T) == 8, s); }
           { TimerScope ts(kt, T_PCG_VEC);
