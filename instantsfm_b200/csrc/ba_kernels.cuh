@@ -422,23 +422,21 @@ __global__ void precond_kernel(int n_cam, const T* __restrict__ HCC, const T* __
 
 // ---------------------------------------------------------------------------------------
 // K5: back-substitution D_p = -Hpp^-1 (g_p + sum Jp^T (Jc D_c)), trial points, and the
-// trust-region model term sum (JD)^T (2R + JD).  One thread per point; Jc D_c of up to KEEP
-// observations stays in registers between the two sweeps.
+// trust-region model term sum (JD)^T (2R + JD).  One thread per point, one sweep over its records.
 // ---------------------------------------------------------------------------------------
 template <typename T, int D>
 __global__ void __launch_bounds__(BA_TPB)
 backsub_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const int32_t* __restrict__ cam_of,
-               const T* __restrict__ OBS, const T* __restrict__ R, const T* __restrict__ GPT,
+               const T* __restrict__ OBS, const T* __restrict__ R, const T* __restrict__ GPT, const T* __restrict__ HPP,
                const T* __restrict__ HPPINV, const T* __restrict__ DC, const T* __restrict__ pts,
                T* __restrict__ pts_trial, T* __restrict__ DP, double* __restrict__ part_m) {
   constexpr int REC = ObsRec<D>::REC, OJP = ObsRec<D>::JP;
   constexpr int NQ = (2 * D + 6 + 3) / 4;
-  constexpr int KEEP = 8;
   double msum = 0.0;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_pt; p += (int64_t)gridDim.x * blockDim.x) {
     const int beg = pt_off[p], end = pt_off[p + 1];
     T u0 = GPT[3 * p], u1 = GPT[3 * p + 1], u2 = GPT[3 * p + 2];
-    T kw0[KEEP], kw1[KEEP];
+    T A = T(0);   // sum_a w_a . (2 R_a + w_a),  w_a = Jc_a D_c
     for (int a = beg; a < end; ++a) {
       T rec[4 * NQ];
       load_quads<T, 0, NQ, true>(OBS + (size_t)a * REC, rec);
@@ -448,8 +446,7 @@ backsub_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const int32_t* 
       for (int c = 0; c < D; ++c) { T d = __ldg(dc + c); w0 += rec[c] * d; w1 += rec[D + c] * d; }
       const T* j = rec + OJP;
       u0 += j[0] * w0 + j[3] * w1; u1 += j[1] * w0 + j[4] * w1; u2 += j[2] * w0 + j[5] * w1;
-#pragma unroll
-      for (int k = 0; k < KEEP; ++k) if (a - beg == k) { kw0[k] = w0; kw1[k] = w1; }
+      A += w0 * (2 * R[2 * (size_t)a] + w0) + w1 * (2 * R[2 * (size_t)a + 1] + w1);
     }
     const T* iv = HPPINV + (size_t)p * 6;
     T d0 = -(iv[0] * u0 + iv[1] * u1 + iv[2] * u2);
@@ -457,23 +454,12 @@ backsub_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const int32_t* 
     T d2 = -(iv[2] * u0 + iv[4] * u1 + iv[5] * u2);
     DP[3 * p] = d0; DP[3 * p + 1] = d1; DP[3 * p + 2] = d2;
     pts_trial[3 * p] = pts[3 * p] + d0; pts_trial[3 * p + 1] = pts[3 * p + 1] + d1; pts_trial[3 * p + 2] = pts[3 * p + 2] + d2;
-    for (int a = beg; a < end; ++a) {
-      const T* recp = OBS + (size_t)a * REC;
-      T w0 = T(0), w1 = T(0);
-      if (a - beg < KEEP) {
-#pragma unroll
-        for (int k = 0; k < KEEP; ++k) if (a - beg == k) { w0 = kw0[k]; w1 = kw1[k]; }
-      } else {
-        T rec[4 * ((2 * D + 3) / 4)];
-        load_quads<T, 0, (2 * D + 3) / 4, true>(recp, rec);
-        const T* dc = DC + (size_t)cam_of[a] * D;
-#pragma unroll
-        for (int c = 0; c < D; ++c) { T d = __ldg(dc + c); w0 += rec[c] * d; w1 += rec[D + c] * d; }
-      }
-      const T* j = recp + OJP;
-      T jd0 = w0 + j[0] * d0 + j[1] * d1 + j[2] * d2, jd1 = w1 + j[3] * d0 + j[4] * d1 + j[5] * d2;
-      msum += (double)(jd0 * (2 * R[2 * (size_t)a] + jd0) + jd1 * (2 * R[2 * (size_t)a + 1] + jd1));
-    }
+    // sum_a JD_a . (2 R_a + JD_a) with JD_a = w_a + Jp_a D_p
+    //   = A + 2 D_p . (g_p + sum Jp_a^T w_a) + D_p^T (sum Jp_a^T Jp_a) D_p = A + 2 D_p . u + D_p^T Hpp D_p
+    // (Hpp undamped) -- no second sweep over the observation records.
+    const T* h = HPP + (size_t)p * 6;
+    T hd0 = h[0] * d0 + h[1] * d1 + h[2] * d2, hd1 = h[1] * d0 + h[3] * d1 + h[4] * d2, hd2 = h[2] * d0 + h[4] * d1 + h[5] * d2;
+    msum += (double)A + 2.0 * ((double)d0 * u0 + (double)d1 * u1 + (double)d2 * u2) + ((double)d0 * hd0 + (double)d1 * hd1 + (double)d2 * hd2);
   }
   msum = block_sum(msum);
   if (threadIdx.x == 0) part_m[blockIdx.x] = msum;

@@ -117,7 +117,7 @@ struct BASolver : BASolverBase {
     if (desc.optimize_poses) {
       build_schur_pattern(sp, ix, s, timers);
       HCC_GC.alloc((size_t)nc * (D * D + D)); HD.alloc((size_t)nc * D * D);
-      E.alloc((size_t)sp.nnzu * D * D); EG.alloc((size_t)nc * D); RED.alloc((size_t)nc * (D * D + D));
+      E.alloc((size_t)sp.nnzu * D * D); E.zero(s);   // padding slots stay zero EG.alloc((size_t)nc * D); RED.alloc((size_t)nc * (D * D + D));
       MINV.alloc((size_t)nc * D * D); bvec.alloc((size_t)nc * D);
       pcg.resize((int)nc, sp.n_off, sp.n_chunks);
     }
@@ -239,7 +239,7 @@ struct BASolver : BASolverBase {
         { TimerScope ts(timers, T_BACKSUB);
           mterm_parts = red_grid(n_pt);
           backsub_kernel<T, D><<<mterm_parts, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), ix.cam_of.get(), OBS.get(), R.get(),
-                                                             GPT.get(), HPPINV.get(), pcg.x.get(), pts[cur].get(),
+                                                             GPT.get(), HPP.get(), HPPINV.get(), pcg.x.get(), pts[cur].get(),
                                                              pts[trial].get(), DP.get(), part_c.get()); }
         { TimerScope ts(timers, T_UPDATE);
           camera_update_kernel<T, NI><<<div_up(n_cam, 128), 128, 0, s>>>((int)n_cam, cam[cur].get(), pcg.x.get(),
@@ -337,7 +337,7 @@ struct BASolver : BASolverBase {
   // full (both triangles) BSR pattern, rebuilt on the host from the stored upper triangle
   void get_schur_pattern(int64_t* nnzb, int64_t* n_pairs, int64_t* row_ptr, int32_t* col_idx) override {
     ISFM_REQUIRE(has_problem && desc.optimize_poses, ISFM_ESTATE, "no reduced camera system (optimize_poses = 0?)");
-    if (nnzb) *nnzb = sp.nnzu + sp.n_off;
+    if (nnzb) *nnzb = sp.n_blocks + sp.n_off;
     if (n_pairs) *n_pairs = sp.n_pairs;
     if (!row_ptr && !col_idx) return;
     std::vector<int32_t> up, uc;
@@ -351,6 +351,7 @@ struct BASolver : BASolverBase {
     int64_t pos = 0;
     for (int64_t i = 0; i < n_cam; ++i) {
       std::sort(rows[i].begin(), rows[i].end());
+      rows[i].erase(std::unique(rows[i].begin(), rows[i].end()), rows[i].end());   // row-padding slots repeat (i, i)
       if (row_ptr) row_ptr[i] = pos;
       for (int32_t c : rows[i]) { if (col_idx) col_idx[pos] = c; ++pos; }
     }

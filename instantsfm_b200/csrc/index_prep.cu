@@ -131,6 +131,32 @@ __global__ void lower_scatter_kernel(const uint64_t* __restrict__ keys_sorted, c
   else tpos[e] = -1;
 }
 
+// Row padding: every upper row starts at a slot that is a multiple of 4 blocks, so that any
+// run of 4 blocks (4 D^2 elements) is 16-byte aligned for 128-bit streaming.
+__global__ void pad_remap_kernel(int64_t nnzu, const int32_t* __restrict__ row_of, const int32_t* __restrict__ up,
+                                 const int32_t* __restrict__ upp, const int32_t* __restrict__ ucol,
+                                 const int32_t* __restrict__ tpos, int32_t* ucol_p, int32_t* tpos_p, int32_t* slot_of) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nnzu) return;
+  const int32_t row = row_of[e];
+  const int32_t s = upp[row] + ((int32_t)e - up[row]);
+  ucol_p[s] = ucol[e];
+  tpos_p[s] = tpos[e];
+  slot_of[e] = s;
+}
+
+__global__ void pad_fill_kernel(int64_t n_cam, const int32_t* __restrict__ up, const int32_t* __restrict__ upp,
+                                int32_t* ucol_p, int32_t* tpos_p) {
+  int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= n_cam) return;
+  for (int32_t s = upp[row] + (up[row + 1] - up[row]); s < upp[row + 1]; ++s) { ucol_p[s] = (int32_t)row; tpos_p[s] = -1; }
+}
+
+__global__ void remap_slots_kernel(int64_t n, int32_t* slots, const int32_t* __restrict__ slot_of) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n) slots[t] = slot_of[slots[t]];
+}
+
 int bits_for(uint64_t max_value) {
   int b = 1;
   while (b < 64 && (max_value >> b) != 0) ++b;
@@ -274,11 +300,32 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
     ISFM_CUDA(cudaGetLastError());
     ISFM_CUDA(cudaStreamSynchronize(s));
   }
-  // 6. mat-vec chunks (host: n_cam + 1 integers)
+  // 6. pad every row to a multiple of 4 slots (padding slots: col = row, zero values, no deposit)
+  //    and cut the rows into mat-vec chunks (host: n_cam + 1 integers)
   {
-    std::vector<int32_t> up((size_t)n_cam + 1), crow, cbeg, cptr((size_t)n_cam + 1);
+    std::vector<int32_t> up((size_t)n_cam + 1), upp((size_t)n_cam + 1), crow, cbeg, cptr((size_t)n_cam + 1);
     ISFM_CUDA(cudaMemcpyAsync(up.data(), sp.urow_ptr.get(), up.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     ISFM_CUDA(cudaStreamSynchronize(s));
+    upp[0] = 0;
+    for (int64_t i = 0; i < n_cam; ++i) upp[i + 1] = upp[i] + (up[i + 1] - up[i] + 3) / 4 * 4;
+    const int64_t nnzp = upp[n_cam];
+    DeviceBuffer<int32_t> d_up, d_upp, ucol_p, tpos_p, slot_of;
+    d_up.alloc(n_cam + 1); d_upp.alloc(n_cam + 1); ucol_p.alloc(nnzp); tpos_p.alloc(nnzp); slot_of.alloc(nnzu);
+    ISFM_CUDA(cudaMemcpyAsync(d_up.get(), up.data(), up.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    ISFM_CUDA(cudaMemcpyAsync(d_upp.get(), upp.data(), upp.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    pad_remap_kernel<<<div_up(nnzu, TPB), TPB, 0, s>>>((int64_t)nnzu, row_of.get(), d_up.get(), d_upp.get(), sp.ucol.get(),
+                                                       sp.tpos.get(), ucol_p.get(), tpos_p.get(), slot_of.get());
+    pad_fill_kernel<<<div_up(n_cam, TPB), TPB, 0, s>>>(n_cam, d_up.get(), d_upp.get(), ucol_p.get(), tpos_p.get());
+    if (n_lists > 0) remap_slots_kernel<<<div_up(n_lists, TPB), TPB, 0, s>>>(n_lists, sp.list_slot.get(), slot_of.get());
+    remap_slots_kernel<<<div_up(n_cam, TPB), TPB, 0, s>>>(n_cam, sp.diag_slot.get(), slot_of.get());
+    ISFM_CUDA(cudaGetLastError());
+    ISFM_CUDA(cudaStreamSynchronize(s));
+    std::swap(sp.ucol.ptr, ucol_p.ptr); std::swap(sp.ucol.count, ucol_p.count);
+    std::swap(sp.tpos.ptr, tpos_p.ptr); std::swap(sp.tpos.count, tpos_p.count);
+    std::swap(sp.urow_ptr.ptr, d_upp.ptr); std::swap(sp.urow_ptr.count, d_upp.count);
+    sp.n_blocks = sp.nnzu;
+    sp.nnzu = nnzp;
+    up = upp;
     for (int64_t i = 0; i < n_cam; ++i) {
       cptr[i] = (int32_t)crow.size();
       for (int32_t b = up[i]; b < up[i + 1]; b += SPMV_CHUNK) { crow.push_back((int32_t)i); cbeg.push_back(b); }

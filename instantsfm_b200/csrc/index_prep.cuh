@@ -28,7 +28,9 @@ struct ObsIndex {
 struct SchurPattern {
   int64_t n_pairs = 0;   // total (a, b) pairs
   int64_t n_lists = 0;   // unique (i, j), i <= j, with at least one pair
-  int64_t nnzu = 0;      // stored blocks: strictly-upper blocks + n_cam diagonal blocks
+  int64_t nnzu = 0;      // stored slots: strictly-upper blocks + n_cam diagonal blocks + row padding
+                         // (each row padded to a multiple of 4 slots; padding: col = row, zeros)
+  int64_t n_blocks = 0;  // real blocks among them
   int64_t n_off = 0;     // strictly-upper blocks (= lower-triangle entries)
   DeviceBuffer<uint64_t> pairs;      // [n_pairs] (a << 32) | b, cam(a) <= cam(b), grouped by list
   DeviceBuffer<int64_t> list_off;    // [n_lists + 1]

@@ -36,8 +36,13 @@ constexpr int PCG_TPB = 128;
 template <typename T, int D> struct SpmvCfg {
   static constexpr int NW = PCG_TPB / 32;
   static constexpr int GPW = 32 / D;                                 // blocks per warp pass
-  static constexpr int WB = GPW * (sizeof(T) == 4 ? 4 : 2);          // blocks staged per warp
+  // blocks staged per warp: a multiple of 4 (16-byte alignment), bounded by 48 KB static smem
+  static constexpr int WB = (sizeof(T) == 8 && D > 9) ? 4 : GPW * 4;
+  static constexpr int PASSES = (WB + GPW - 1) / GPW;
 };
+template <typename T> struct SpmvVec;
+template <> struct SpmvVec<float> { typedef float4 type; };
+template <> struct SpmvVec<double> { typedef double2 type; };
 
 template <typename T, int D>
 __global__ void __launch_bounds__(PCG_TPB)
@@ -47,8 +52,12 @@ pcg_spmv_upper_kernel(const int32_t* __restrict__ chunk_row, const int32_t* __re
                       T* __restrict__ yup_part, T* __restrict__ C, const PcgState* __restrict__ st) {
   if (st->done) return;
   constexpr int NW = SpmvCfg<T, D>::NW, GPW = SpmvCfg<T, D>::GPW, WB = SpmvCfg<T, D>::WB, DD = D * D;
-  constexpr int STAGE = WB * DD, NLD = (STAGE + 31) / 32;
-  __shared__ T stage[NW][STAGE];
+  // staging in 16-byte vectors: rows start at multiples of 4 slots and WB % 4 == 0, so every
+  // stage source is 16-byte aligned and its length (nb DD elements, nb % 4 == 0) a multiple of 16 B
+  constexpr int VE = 16 / sizeof(T);                       // elements per vector
+  constexpr int NV = WB * DD / VE, NLD = (NV + 31) / 32;   // vectors per stage, per lane
+  typedef typename SpmvVec<T>::type VT;
+  __shared__ __align__(16) T stage[NW][NLD * 32 * VE];
   __shared__ T sh[NW][D];
   const int row = chunk_row[blockIdx.x];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -61,15 +70,19 @@ pcg_spmv_upper_kernel(const int32_t* __restrict__ chunk_row, const int32_t* __re
   for (int base = beg + w * WB; base < end; base += NW * WB) {
     const int nb = min(WB, end - base);
     const T* __restrict__ src = EU + (size_t)base * DD;
-    // all loads of the stage are issued before the first store: NLD independent requests per lane
-    T tmp[NLD];
+    // all loads of the stage are issued before the first store (NLD independent 128-bit
+    // requests per lane, no predicates: indices past the end are clamped onto the last vector)
+    const VT* __restrict__ vsrc = reinterpret_cast<const VT*>(src);
+    VT* vdst = reinterpret_cast<VT*>(stage[w]);
+    const int last = nb * DD / VE - 1;
+    VT tmp[NLD];
 #pragma unroll
-    for (int q = 0; q < NLD; ++q) { const int k = lane + 32 * q; tmp[q] = (k < nb * DD) ? src[k] : T(0); }
+    for (int q = 0; q < NLD; ++q) tmp[q] = vsrc[min(lane + 32 * q, last)];
 #pragma unroll
-    for (int q = 0; q < NLD; ++q) { const int k = lane + 32 * q; if (k < STAGE) stage[w][k] = tmp[q]; }
+    for (int q = 0; q < NLD; ++q) vdst[lane + 32 * q] = tmp[q];
     __syncwarp();
 #pragma unroll
-    for (int pass = 0; pass < WB / GPW; ++pass) {
+    for (int pass = 0; pass < SpmvCfg<T, D>::PASSES; ++pass) {
       const int b = pass * GPW + bl;
       if (bl < GPW && b < nb) {
         const int e = base + b;
@@ -119,7 +132,15 @@ pcg_combine_kernel(const int32_t* __restrict__ lrow_ptr, const int32_t* __restri
   if (g < G) {
     for (int k = chunk_ptr[row] + g; k < chunk_ptr[row + 1]; k += G) acc += yup_part[(size_t)k * D + c];
     const int beg = lrow_ptr[row], end = lrow_ptr[row + 1];
-    for (int k = beg + g; k < end; k += G) acc += C[(size_t)k * D + c];
+    int k = beg + g;
+    // four independent loads in flight per thread (rows of a dense system hold ~n_cam deposits)
+    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+    for (; k + 3 * G < end; k += 4 * G) {
+      a0 += C[(size_t)k * D + c]; a1 += C[(size_t)(k + G) * D + c];
+      a2 += C[(size_t)(k + 2 * G) * D + c]; a3 += C[(size_t)(k + 3 * G) * D + c];
+    }
+    for (; k < end; k += G) a0 += C[(size_t)k * D + c];
+    acc += (a0 + a1) + (a2 + a3);
     sh[g][c] = acc;
   }
   __syncthreads();
