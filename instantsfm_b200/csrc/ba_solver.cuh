@@ -117,7 +117,8 @@ struct BASolver : BASolverBase {
     if (desc.optimize_poses) {
       build_schur_pattern(sp, ix, s, timers);
       HCC_GC.alloc((size_t)nc * (D * D + D)); HD.alloc((size_t)nc * D * D);
-      E.alloc((size_t)sp.nnzu * D * D); E.zero(s);   // padding slots stay zero EG.alloc((size_t)nc * D); RED.alloc((size_t)nc * (D * D + D));
+      E.alloc((size_t)sp.nnzu * D * D); E.zero(s);   // padding slots stay zero
+      EG.alloc((size_t)nc * D); RED.alloc((size_t)nc * (D * D + D));
       MINV.alloc((size_t)nc * D * D); bvec.alloc((size_t)nc * D);
       pcg.resize((int)nc, sp.n_off, sp.n_chunks);
     }

@@ -368,7 +368,8 @@ struct GPSolver : GPSolverBase {
     A.alloc((size_t)no); JV.alloc((size_t)no * 3); RT.alloc((size_t)no * 3); QW.alloc((size_t)no * 15);
     HINV.alloc((size_t)np * 6); GX.alloc((size_t)np * 3); TP.alloc((size_t)np * 3);
     ACC.alloc((size_t)nc * GP_CAM_ACC); ACCSUM.alloc((size_t)nc * GP_CAM_ACC);
-    E.alloc((size_t)sp.nnzu * 9); E.zero(s);   // padding slots stay zero HD.alloc((size_t)nc * 9); MINV.alloc((size_t)nc * 9); bvec.alloc((size_t)nc * 3);
+    E.alloc((size_t)sp.nnzu * 9); E.zero(s);   // padding slots stay zero
+    HD.alloc((size_t)nc * 9); MINV.alloc((size_t)nc * 9); bvec.alloc((size_t)nc * 3);
     part_a.alloc(std::max<int64_t>(RED_BLOCKS, nc)); part_b.alloc(std::max<int64_t>(RED_BLOCKS, nc));
     part_c.alloc(std::max<int64_t>(RED_BLOCKS, nc));
     scalars.alloc(4); fail.alloc(1); fail.zero(s);
