@@ -48,7 +48,7 @@ struct SchurPattern {
   DeviceBuffer<int32_t> chunk_beg;   // [n_chunks] first upper slot of the chunk
   DeviceBuffer<int32_t> chunk_ptr;   // [n_cam + 1] first chunk of each row
 };
-constexpr int SPMV_CHUNK = 96;
+constexpr int SPMV_CHUNK = 48;   // slots per mat-vec work unit (one warp); multiple of 4
 
 // cam_idx / pt_idx: device int32 [n_obs] in the caller's order.
 void build_obs_index(ObsIndex& ix, int64_t n_cam, int64_t n_pt, int64_t n_obs, const int32_t* cam_idx,

@@ -34,83 +34,98 @@ constexpr int PCG_TPB = 128;
 //                position of block (j, i) in the row-major order of the lower triangle)
 // A second kernel adds row j's deposits: no atomics, deterministic.
 template <typename T, int D> struct SpmvCfg {
-  static constexpr int NW = PCG_TPB / 32;
+  static constexpr int NW = PCG_TPB / 32;                            // warps = work units per CTA
   static constexpr int GPW = 32 / D;                                 // blocks per warp pass
-  // blocks staged per warp: a multiple of 4 (16-byte alignment), bounded by 48 KB static smem
-  static constexpr int WB = (sizeof(T) == 8 && D > 9) ? 4 : GPW * 4;
+  // blocks per stage: a multiple of 4 (16-byte alignment of every stage source)
+  static constexpr int WB = sizeof(T) == 4 ? GPW * 4 : (GPW * 2 + 3) / 4 * 4;
   static constexpr int PASSES = (WB + GPW - 1) / GPW;
+  static constexpr int VE = 16 / sizeof(T);                          // elements per 16-byte vector
+  static constexpr int NV = WB * D * D / VE;                         // vectors per stage
+  static constexpr int NLD = (NV + 31) / 32;                         // cp.async per lane per stage
+  static constexpr int STG = NLD * 32 * VE;                          // elements per stage buffer
+  static constexpr size_t SMEM = (size_t)NW * 2 * STG * sizeof(T);   // double-buffered, per warp
 };
-template <typename T> struct SpmvVec;
-template <> struct SpmvVec<float> { typedef float4 type; };
-template <> struct SpmvVec<double> { typedef double2 type; };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One WARP per work unit (<= SPMV_CHUNK consecutive slots of one upper row), no CTA-wide
+// synchronisation.  The unit's blocks are streamed with cp.async (LDGSTS, 16 B, L2-only) into
+// a per-warp double buffer: stage k+1 is in flight while stage k is multiplied.
 template <typename T, int D>
 __global__ void __launch_bounds__(PCG_TPB)
-pcg_spmv_upper_kernel(const int32_t* __restrict__ chunk_row, const int32_t* __restrict__ chunk_beg,
+pcg_spmv_upper_kernel(int n_units, const int32_t* __restrict__ unit_row, const int32_t* __restrict__ unit_beg,
                       const int32_t* __restrict__ urow_ptr, const int32_t* __restrict__ ucol,
                       const int32_t* __restrict__ tpos, const T* __restrict__ EU, const T* __restrict__ p,
                       T* __restrict__ yup_part, T* __restrict__ C, const PcgState* __restrict__ st) {
   if (st->done) return;
-  constexpr int NW = SpmvCfg<T, D>::NW, GPW = SpmvCfg<T, D>::GPW, WB = SpmvCfg<T, D>::WB, DD = D * D;
-  // staging in 16-byte vectors: rows start at multiples of 4 slots and WB % 4 == 0, so every
-  // stage source is 16-byte aligned and its length (nb DD elements, nb % 4 == 0) a multiple of 16 B
-  constexpr int VE = 16 / sizeof(T);                       // elements per vector
-  constexpr int NV = WB * DD / VE, NLD = (NV + 31) / 32;   // vectors per stage, per lane
-  typedef typename SpmvVec<T>::type VT;
-  __shared__ __align__(16) T stage[NW][NLD * 32 * VE];
-  __shared__ T sh[NW][D];
-  const int row = chunk_row[blockIdx.x];
+  typedef SpmvCfg<T, D> Cfg;
+  constexpr int GPW = Cfg::GPW, WB = Cfg::WB, DD = D * D, VE = Cfg::VE, NLD = Cfg::NLD, STG = Cfg::STG;
+  extern __shared__ __align__(16) unsigned char spmv_smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int unit = blockIdx.x * Cfg::NW + w;
+  if (unit >= n_units) return;
+  T* buf = reinterpret_cast<T*>(spmv_smem) + (size_t)w * 2 * STG;
   const int bl = lane / D, r = lane % D;
-  const int beg = chunk_beg[blockIdx.x], end = min(beg + SPMV_CHUNK, urow_ptr[row + 1]);
+  const int row = unit_row[unit];
+  const int beg = unit_beg[unit], end = min(beg + SPMV_CHUNK, urow_ptr[row + 1]);
+  const int ns = (end - beg + WB - 1) / WB;
   T pi[D];
 #pragma unroll
   for (int c = 0; c < D; ++c) pi[c] = p[(size_t)row * D + c];
+
+  auto issue = [&](int k) {
+    const int base = beg + k * WB;
+    const int last = min(WB, end - base) * DD / VE - 1;   // indices past the end re-copy the last vector
+    const T* src = EU + (size_t)base * DD;
+    T* dst = buf + (size_t)(k & 1) * STG;
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) cp_async16(dst + (size_t)(lane + 32 * q) * VE, src + (size_t)min(lane + 32 * q, last) * VE);
+    cp_async_commit();
+  };
+
+  issue(0);
   T acc = T(0);
-  for (int base = beg + w * WB; base < end; base += NW * WB) {
+  for (int k = 0; k < ns; ++k) {
+    if (k + 1 < ns) issue(k + 1);
+    const int base = beg + k * WB;
     const int nb = min(WB, end - base);
-    const T* __restrict__ src = EU + (size_t)base * DD;
-    // all loads of the stage are issued before the first store (NLD independent 128-bit
-    // requests per lane, no predicates: indices past the end are clamped onto the last vector)
-    const VT* __restrict__ vsrc = reinterpret_cast<const VT*>(src);
-    VT* vdst = reinterpret_cast<VT*>(stage[w]);
-    const int last = nb * DD / VE - 1;
-    VT tmp[NLD];
+    int jj[Cfg::PASSES], tp[Cfg::PASSES];
 #pragma unroll
-    for (int q = 0; q < NLD; ++q) tmp[q] = vsrc[min(lane + 32 * q, last)];
-#pragma unroll
-    for (int q = 0; q < NLD; ++q) vdst[lane + 32 * q] = tmp[q];
-    __syncwarp();
-#pragma unroll
-    for (int pass = 0; pass < SpmvCfg<T, D>::PASSES; ++pass) {
+    for (int pass = 0; pass < Cfg::PASSES; ++pass) {
       const int b = pass * GPW + bl;
-      if (bl < GPW && b < nb) {
-        const int e = base + b;
-        const int j = ucol[e];
-        const T* B = stage[w] + b * DD;
+      const bool on = bl < GPW && b < nb;
+      jj[pass] = on ? ucol[base + b] : -1;
+      tp[pass] = on ? tpos[base + b] : -1;
+    }
+    if (k + 1 < ns) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncwarp();
+    const T* S = buf + (size_t)(k & 1) * STG;
+#pragma unroll
+    for (int pass = 0; pass < Cfg::PASSES; ++pass) {
+      const int j = jj[pass];
+      if (j >= 0) {
+        const T* B = S + (pass * GPW + bl) * DD;
         const T* __restrict__ pj = p + (size_t)j * D;
         T t = T(0);
 #pragma unroll
         for (int c = 0; c < D; ++c) { acc += B[r * D + c] * pj[c]; t += B[c * D + r] * pi[c]; }
-        if (j != row) C[(size_t)tpos[e] * D + r] = t;
+        if (tp[pass] >= 0) C[(size_t)tp[pass] * D + r] = t;
       }
     }
     __syncwarp();
   }
-  // fold the GPW block lanes of this warp onto lanes 0..D-1, then the warps
+  // fold the GPW block lanes onto lanes 0..D-1
 #pragma unroll
   for (int k = 1; k < GPW; ++k) {
     T o = __shfl_sync(0xffffffffu, acc, (lane + k * D) & 31);
     if (lane < D) acc += o;
   }
-  if (lane < D) sh[w][lane] = acc;
-  __syncthreads();
-  if (threadIdx.x < D) {
-    T y = T(0);
-#pragma unroll
-    for (int k = 0; k < NW; ++k) y += sh[k][threadIdx.x];
-    yup_part[(size_t)blockIdx.x * D + threadIdx.x] = y;
-  }
+  if (lane < D) yup_part[(size_t)unit * D + lane] = acc;
 }
 
 // y_i = sum of row i's chunk partials + sum of the deposits of row i (contiguous in C).
@@ -319,6 +334,8 @@ struct BlockPCG {
     C.alloc((size_t)std::max<int64_t>(n_off, 1) * D);
     part_pq.alloc(n); part_a.alloc(n); part_b.alloc(n);
     state.alloc(1);
+    ISFM_CUDA(cudaFuncSetAttribute(pcg_spmv_upper_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)SpmvCfg<T, D>::SMEM));
     if (!h_state) ISFM_CUDA(cudaMallocHost(&h_state, sizeof(PcgState)));
   }
 
@@ -341,7 +358,8 @@ struct BlockPCG {
       int chunk = std::min(check_every, max_iter - it);
       for (int k = 0; k < chunk; ++k, ++it) {
         { TimerScope ts(kt, T_PCG_SPMV);
-          pcg_spmv_upper_kernel<T, D><<<(int)sp.n_chunks, PCG_TPB, 0, s>>>(sp.chunk_row.get(), sp.chunk_beg.get(), sp.urow_ptr.get(), sp.ucol.get(),
+          pcg_spmv_upper_kernel<T, D><<<div_up(sp.n_chunks, SpmvCfg<T, D>::NW), PCG_TPB, SpmvCfg<T, D>::SMEM, s>>>(
+              (int)sp.n_chunks, sp.chunk_row.get(), sp.chunk_beg.get(), sp.urow_ptr.get(), sp.ucol.get(),
                                                                            sp.tpos.get(), E, p.get(), yup.get(), C.get(), state.get()); }
         if (!multi) {
           TimerScope ts(kt, T_PCG_VEC);
