@@ -42,13 +42,18 @@ template <typename T, int D> struct SpmvCfg {
   static constexpr int VE = 16 / sizeof(T);                          // elements per 16-byte vector
   static constexpr int NV = WB * D * D / VE;                         // vectors per stage
   static constexpr int NLD = (NV + 31) / 32;                         // cp.async per lane per stage
-  static constexpr int STG = NLD * 32 * VE;                          // elements per stage buffer
+  static constexpr int STG = NLD * 32 * VE + (WB * D + VE - 1) / VE * VE;   // elements per stage buffer: blocks | p_j of each block
+  static constexpr int POFF = NLD * 32 * VE;                         // offset of the p_j area inside a stage buffer
   static constexpr size_t SMEM = (size_t)NW * 2 * STG * sizeof(T);   // double-buffered, per warp
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+template <int BYTES> __device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -78,39 +83,39 @@ pcg_spmv_upper_kernel(int n_units, const int32_t* __restrict__ unit_row, const i
 #pragma unroll
   for (int c = 0; c < D; ++c) pi[c] = p[(size_t)row * D + c];
 
-  auto issue = [&](int k) {
+  // stage k: the blocks (16-byte cp.async, L2 only) and, per block, its p_j (element-wise
+  // cp.async) so that the multiply phase reads everything from shared memory
+  auto issue = [&](int k, int* jj, int* tp) {
     const int base = beg + k * WB;
-    const int last = min(WB, end - base) * DD / VE - 1;   // indices past the end re-copy the last vector
+    const int nb = min(WB, end - base);
+    const int last = nb * DD / VE - 1;   // indices past the end re-copy the last vector
     const T* src = EU + (size_t)base * DD;
     T* dst = buf + (size_t)(k & 1) * STG;
 #pragma unroll
     for (int q = 0; q < NLD; ++q) cp_async16(dst + (size_t)(lane + 32 * q) * VE, src + (size_t)min(lane + 32 * q, last) * VE);
-    cp_async_commit();
-  };
-
-  issue(0);
-  T acc = T(0);
-  for (int k = 0; k < ns; ++k) {
-    if (k + 1 < ns) issue(k + 1);
-    const int base = beg + k * WB;
-    const int nb = min(WB, end - base);
-    int jj[Cfg::PASSES], tp[Cfg::PASSES];
 #pragma unroll
     for (int pass = 0; pass < Cfg::PASSES; ++pass) {
       const int b = pass * GPW + bl;
       const bool on = bl < GPW && b < nb;
       jj[pass] = on ? ucol[base + b] : -1;
       tp[pass] = on ? tpos[base + b] : -1;
+      if (on) cp_async_small<sizeof(T)>(dst + Cfg::POFF + b * D + r, p + (size_t)jj[pass] * D + r);
     }
-    if (k + 1 < ns) cp_async_wait<1>(); else cp_async_wait<0>();
+    cp_async_commit();
+  };
+
+  int jj[Cfg::PASSES], tp[Cfg::PASSES], jn[Cfg::PASSES], tn[Cfg::PASSES];
+  issue(0, jj, tp);
+  T acc = T(0);
+  for (int k = 0; k < ns; ++k) {
+    if (k + 1 < ns) { issue(k + 1, jn, tn); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncwarp();
     const T* S = buf + (size_t)(k & 1) * STG;
 #pragma unroll
     for (int pass = 0; pass < Cfg::PASSES; ++pass) {
-      const int j = jj[pass];
-      if (j >= 0) {
+      if (jj[pass] >= 0) {
         const T* B = S + (pass * GPW + bl) * DD;
-        const T* __restrict__ pj = p + (size_t)j * D;
+        const T* pj = S + Cfg::POFF + (pass * GPW + bl) * D;
         T t = T(0);
 #pragma unroll
         for (int c = 0; c < D; ++c) { acc += B[r * D + c] * pj[c]; t += B[c * D + r] * pi[c]; }
@@ -118,6 +123,8 @@ pcg_spmv_upper_kernel(int n_units, const int32_t* __restrict__ unit_row, const i
       }
     }
     __syncwarp();
+#pragma unroll
+    for (int pass = 0; pass < Cfg::PASSES; ++pass) { jj[pass] = jn[pass]; tp[pass] = tn[pass]; }
   }
   // fold the GPW block lanes onto lanes 0..D-1
 #pragma unroll
