@@ -331,58 +331,98 @@ camera_blocks_kernel(const int32_t* __restrict__ cam_off, const int32_t* __restr
 
 // ---------------------------------------------------------------------------------------
 // K2 (Schur off-diagonal): E_ij = sum over the pair list of block (i, j), i <= j, of
-// Jc_a^T (V_a Jp_b^T) Jc_b.  A group of D lanes owns one list; lane c owns column c of the
-// D x D block (D accumulators), so every pair costs 12 + 4 + 2D FMAs per lane and nothing is
-// reduced across lanes.  Records are fetched with 128-bit loads that broadcast inside the
-// group.  Only the upper triangle is stored; diagonal lists (same camera twice in a track) add
-// onto E_ii written by the camera pass.  No atomics.
+// Jc_a^T (V_a Jp_b^T) Jc_b.  A group of ceil(D/2) lanes owns one list; each lane owns two
+// columns of the D x D block (2 D accumulators) and nothing is reduced across lanes.  The two 128-byte records of a pair are gathered with cp.async
+// (16 B per lane, L2 only) into a per-group ring in shared memory, a few pairs ahead
+// of the multiply: the dependent chain pair index -> record address -> record no longer
+// serialises the list.  All groups of a warp run the same trip count (lists are visited in
+// order of decreasing length) so the pipeline needs warp-level synchronisation only.  Only the upper triangle is
+// stored; diagonal lists (same camera twice in a track) add onto E_ii written by the camera
+// pass.  No atomics.
 // ---------------------------------------------------------------------------------------
-template <int D> struct SchurGroup { static constexpr int PER_WARP = 32 / D; };
+template <int D> struct SchurGroup {
+  static constexpr int COLS = 2;                       // columns of the block owned by one lane
+  static constexpr int LPL = (D + COLS - 1) / COLS;    // lanes per list
+  static constexpr int PER_WARP = 32 / LPL;            // lists per warp
+};
 constexpr int SCHUR_TPB = 128;
 
 template <typename T, int D>
 __global__ void __launch_bounds__(SCHUR_TPB)
-schur_offdiag_kernel(int64_t n_lists, const int64_t* __restrict__ list_off, const uint64_t* __restrict__ pairs,
-                     const int32_t* __restrict__ list_slot, const uint8_t* __restrict__ list_diag,
-                     const T* __restrict__ OBS, T* __restrict__ E) {
+schur_offdiag_kernel(int64_t n_lists, const int32_t* __restrict__ list_order, const int64_t* __restrict__ list_off,
+                     const uint64_t* __restrict__ pairs, const int32_t* __restrict__ list_slot,
+                     const uint8_t* __restrict__ list_diag, const T* __restrict__ OBS, T* __restrict__ E) {
   constexpr int REC = ObsRec<D>::REC, OJP = ObsRec<D>::JP, OV = ObsRec<D>::V;
-  constexpr int GPW = SchurGroup<D>::PER_WARP;
-  constexpr int QJ = (2 * D + 3) / 4;                 // quads covering Jc
-  constexpr int QV0 = OV / 4, QV1 = (OV + 6 + 3) / 4; // quads covering V
-  constexpr int QP0 = OJP / 4, QP1 = (OJP + 6 + 3) / 4;
-  const int lane = threadIdx.x & 31;
-  const int grp = lane / D, c = lane % D;
-  const int64_t warp = blockIdx.x * (int64_t)(SCHUR_TPB / 32) + (threadIdx.x >> 5);
-  const int64_t u = warp * GPW + grp;
-  if (grp >= GPW || u >= n_lists) return;
-  T acc[D];
+  constexpr int LPL = SchurGroup<D>::LPL, GPW = SchurGroup<D>::PER_WARP;
+  constexpr int DEPTH = sizeof(T) == 4 ? 4 : 3;   // pairs in flight per list (ring in shared memory)
+  constexpr int VE = 16 / sizeof(T);              // elements per 16-byte vector
+  constexpr int NVEC = REC / VE;                  // vectors per record
+  __shared__ __align__(16) T ring_all[SCHUR_TPB / 32][GPW][DEPTH][2][REC];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int grp = lane / LPL, gl = lane % LPL;
+  const int c0 = 2 * gl, c1 = min(2 * gl + 1, D - 1);      // the last lane of an odd D repeats column D-1
+  const int64_t warp = blockIdx.x * (int64_t)(SCHUR_TPB / 32) + w;
+  const int64_t slot_in_order = warp * GPW + grp;
+  const bool valid = grp < GPW && slot_in_order < n_lists;
+  // lists are visited in order of decreasing length, so the GPW lists of a warp have (almost)
+  // the same trip count
+  const int64_t u = valid ? list_order[slot_in_order] : 0;
+  const int64_t beg = valid ? list_off[u] : 0;
+  const int len = valid ? (int)(list_off[u + 1] - beg) : 0;
+  int maxlen = len;
 #pragma unroll
-  for (int r = 0; r < D; ++r) acc[r] = T(0);
-  const int64_t beg = list_off[u], end = list_off[u + 1];
-  for (int64_t t = beg; t < end; ++t) {
-    const uint64_t ab = __ldg(pairs + t);
-    const T* ra = OBS + (size_t)(uint32_t)(ab >> 32) * REC;
-    const T* rb = OBS + (size_t)(uint32_t)ab * REC;
-    T ja[4 * QJ], va[4 * (QV1 - QV0)], pb[4 * (QP1 - QP0)];
-    load_quads<T, 0, QJ, true>(ra, ja);
-    load_quads<T, QV0, QV1, true>(ra, va);
-    load_quads<T, QP0, QP1, true>(rb, pb);
-    const T b0 = __ldg(rb + c), b1 = __ldg(rb + D + c);
-    const T* v = va + (OV - 4 * QV0);
-    const T* j = pb + (OJP - 4 * QP0);
-    const T m00 = v[0] * j[0] + v[1] * j[1] + v[2] * j[2], m01 = v[0] * j[3] + v[1] * j[4] + v[2] * j[5];
-    const T m10 = v[3] * j[0] + v[4] * j[1] + v[5] * j[2], m11 = v[3] * j[3] + v[4] * j[4] + v[5] * j[5];
-    const T t0 = m00 * b0 + m01 * b1, t1 = m10 * b0 + m11 * b1;
+  for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+  T (*ring)[2][REC] = ring_all[w][grp < GPW ? grp : 0];
+
+  auto issue = [&](int t) {
+    if (t < len) {
+      const uint64_t ab = __ldg(pairs + beg + t);
+      const T* ra = OBS + (size_t)(uint32_t)(ab >> 32) * REC;
+      const T* rb = OBS + (size_t)(uint32_t)ab * REC;
+      T* da = ring[t % DEPTH][0];
+      T* db = ring[t % DEPTH][1];
+      for (int v = gl; v < NVEC; v += LPL) { cp_async16(da + v * VE, ra + v * VE); cp_async16(db + v * VE, rb + v * VE); }
+    }
+    cp_async_commit();   // committed even when empty: every lane keeps the same group count
+  };
+
+  T acc0[D], acc1[D];
 #pragma unroll
-    for (int r = 0; r < D; ++r) acc[r] += ja[r] * t0 + ja[D + r] * t1;
+  for (int r = 0; r < D; ++r) { acc0[r] = T(0); acc1[r] = T(0); }
+#pragma unroll
+  for (int t = 0; t < DEPTH - 1; ++t) issue(t);
+  for (int t = 0; t < maxlen; ++t) {
+    issue(t + DEPTH - 1);
+    cp_async_wait<DEPTH - 1>();
+    __syncwarp();
+    if (t < len) {
+      const T* ra = ring[t % DEPTH][0];
+      const T* rb = ring[t % DEPTH][1];
+      const T* v = ra + OV;
+      const T* j = rb + OJP;
+      const T m00 = v[0] * j[0] + v[1] * j[1] + v[2] * j[2], m01 = v[0] * j[3] + v[1] * j[4] + v[2] * j[5];
+      const T m10 = v[3] * j[0] + v[4] * j[1] + v[5] * j[2], m11 = v[3] * j[3] + v[4] * j[4] + v[5] * j[5];
+      const T b00 = rb[c0], b10 = rb[D + c0], b01 = rb[c1], b11 = rb[D + c1];
+      const T t00 = m00 * b00 + m01 * b10, t10 = m10 * b00 + m11 * b10;   // column c0 of M Jc_b
+      const T t01 = m00 * b01 + m01 * b11, t11 = m10 * b01 + m11 * b11;   // column c1
+#pragma unroll
+      for (int r = 0; r < D; ++r) {
+        const T a0 = ra[r], a1 = ra[D + r];
+        acc0[r] += a0 * t00 + a1 * t10;
+        acc1[r] += a0 * t01 + a1 * t11;
+      }
+    }
+    __syncwarp();
   }
+  if (!valid) return;
   T* blk = E + (size_t)list_slot[u] * (D * D);
+  const bool two = 2 * gl + 1 < D;
   if (!list_diag[u]) {
 #pragma unroll
-    for (int r = 0; r < D; ++r) blk[r * D + c] = acc[r];
+    for (int r = 0; r < D; ++r) { blk[r * D + c0] = acc0[r]; if (two) blk[r * D + c1] = acc1[r]; }
   } else {
 #pragma unroll
-    for (int r = 0; r < D; ++r) blk[r * D + c] += acc[r];
+    for (int r = 0; r < D; ++r) { blk[r * D + c0] += acc0[r]; if (two) blk[r * D + c1] += acc1[r]; }
   }
 }
 

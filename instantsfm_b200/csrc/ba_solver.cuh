@@ -191,7 +191,8 @@ struct BASolver : BASolverBase {
       TimerScope ts(timers, T_SCHUR_OFFDIAG);
       const int lists_per_cta = SchurGroup<D>::PER_WARP * (SCHUR_TPB / 32);
       schur_offdiag_kernel<T, D><<<div_up(sp.n_lists, lists_per_cta), SCHUR_TPB, 0, s>>>(
-          sp.n_lists, sp.list_off.get(), sp.pairs.get(), sp.list_slot.get(), sp.list_diag.get(), OBS.get(), E.get());
+          sp.n_lists, sp.list_order.get(), sp.list_off.get(), sp.pairs.get(), sp.list_slot.get(), sp.list_diag.get(), OBS.get(),
+          E.get());
     }
     { TimerScope ts(timers, T_PRECOND);
       gather_diag_kernel<T, D><<<div_up(n_cam * (D * D + D), BA_TPB), BA_TPB, 0, s>>>((int)n_cam, sp.diag_slot.get(), E.get(),

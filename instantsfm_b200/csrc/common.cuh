@@ -125,6 +125,19 @@ struct DeviceBuffer {
 inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 #ifdef __CUDACC__
+// Asynchronous global -> shared copies (LDGSTS): 16 bytes through L2 only for streamed data,
+// 4 / 8 bytes through L1 for gathered vector entries.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+template <int BYTES> __device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // block-wide sum in double; result valid in thread 0.  blockDim.x multiple of 32, <= 1024.
 __device__ __forceinline__ double block_sum(double v) {
   __shared__ double sh__[32];

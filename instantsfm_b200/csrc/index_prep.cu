@@ -157,6 +157,14 @@ __global__ void remap_slots_kernel(int64_t n, int32_t* slots, const int32_t* __r
   if (t < n) slots[t] = slot_of[slots[t]];
 }
 
+// key = ~length so that an ascending stable sort yields decreasing lengths
+__global__ void list_len_key_kernel(const int64_t* __restrict__ list_off, int64_t n_lists, uint32_t* key, int32_t* id) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_lists) return;
+  key[t] = ~(uint32_t)(list_off[t + 1] - list_off[t]);
+  id[t] = (int32_t)t;
+}
+
 int bits_for(uint64_t max_value) {
   int b = 1;
   while (b < 64 && (max_value >> b) != 0) ++b;
@@ -299,6 +307,14 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
     lower_bound_kernel<<<div_up(n_cam + 1, TPB), TPB, 0, s>>>(lrow_of.get(), sp.n_off, sp.lrow_ptr.get(), n_cam);
     ISFM_CUDA(cudaGetLastError());
     ISFM_CUDA(cudaStreamSynchronize(s));
+  }
+  // 5b. list visiting order: decreasing length, ties by list id (stable radix sort)
+  if (n_lists > 0) {
+    ISFM_REQUIRE(n_lists < (1ll << 31), ISFM_EINVAL, "too many pair lists");
+    DeviceBuffer<uint32_t> lkey, lkey_s; DeviceBuffer<int32_t> lid;
+    lkey.alloc(n_lists); lkey_s.alloc(n_lists); lid.alloc(n_lists); sp.list_order.alloc(n_lists);
+    list_len_key_kernel<<<div_up(n_lists, TPB), TPB, 0, s>>>(sp.list_off.get(), n_lists, lkey.get(), lid.get());
+    sort_pairs(lkey.get(), lkey_s.get(), lid.get(), sp.list_order.get(), n_lists, 32, s);
   }
   // 6. pad every row to a multiple of 4 slots (padding slots: col = row, zero values, no deposit)
   //    and cut the rows into mat-vec chunks (host: n_cam + 1 integers)

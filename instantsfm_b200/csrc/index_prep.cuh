@@ -36,6 +36,7 @@ struct SchurPattern {
   DeviceBuffer<int64_t> list_off;    // [n_lists + 1]
   DeviceBuffer<int32_t> list_slot;   // [n_lists] upper slot of block (i, j)
   DeviceBuffer<uint8_t> list_diag;   // [n_lists] 1 if i == j (accumulate onto the camera pass)
+  DeviceBuffer<int32_t> list_order;  // [n_lists] list ids by decreasing length (stable)
   DeviceBuffer<int32_t> urow_ptr;    // [n_cam + 1] upper BSR
   DeviceBuffer<int32_t> ucol;        // [nnzu]
   DeviceBuffer<int32_t> tpos;        // [nnzu] position in the lower ordering, -1 for diagonal blocks

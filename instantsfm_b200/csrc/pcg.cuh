@@ -47,17 +47,6 @@ template <typename T, int D> struct SpmvCfg {
   static constexpr size_t SMEM = (size_t)NW * 2 * STG * sizeof(T);   // double-buffered, per warp
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-template <int BYTES> __device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gmem_src) {
-  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // One WARP per work unit (<= SPMV_CHUNK consecutive slots of one upper row), no CTA-wide
 // synchronisation.  The unit's blocks are streamed with cp.async (LDGSTS, 16 B, L2-only) into
 // a per-warp double buffer: stage k+1 is in flight while stage k is multiplied.
