@@ -528,6 +528,131 @@ __global__ void camera_update_kernel(int n_cam, const T* __restrict__ cam, const
   if (threadIdx.x == 0) part_norm[blockIdx.x] = nrm;
 }
 
+// ---------------------------------------------------------------------------------------
+// K1 + K2 (point side) + K3 (3x3) fused for the first trial of an LM step.
+// A CTA owns a run of whole points with at most FUSED_TPB observations (greedy packing done
+// at set-up: `cta_pt` holds the point boundaries), one thread per observation:
+//   1. residual, Huber weight, weighted Jc / Jp in registers; the observation's contribution
+//      to Hpp (6) and g_p (3) goes to shared memory;
+//   2. one thread per point sums its (contiguous) contributions -- the segmented reduction
+//      over observations sorted by point --, writes Hpp / g_p, damps, inverts, t = Hpp^-1 g_p;
+//   3. V = Jp Hpp^-1 per observation; the complete 16-byte-aligned record (Jc | Jp | V) is
+//      staged in shared memory (odd quad stride: conflict-free) and the CTA's contiguous slab
+//      of OBS is written with fully coalesced 128-bit stores.
+// Replaces linearize_kernel + point_solve_kernel<BUILD> when no track exceeds FUSED_TPB
+// observations; rejected trials re-damp with point_solve_kernel<false>.
+// ---------------------------------------------------------------------------------------
+constexpr int FUSED_TPB = 256;
+template <typename T, int D> struct FusedCfg {
+  static constexpr int REC = ObsRec<D>::REC;
+  static constexpr int QR = REC / 4;            // quads per record
+  static constexpr int SQ = QR | 1;             // staged row stride in quads (odd)
+  static constexpr size_t SMEM = (size_t)FUSED_TPB * SQ * 4 * sizeof(T) + (size_t)FUSED_TPB * 6 * sizeof(T);
+};
+
+template <typename T, int MODEL>
+__global__ void __launch_bounds__(FUSED_TPB)
+fused_linearize_kernel(const int32_t* __restrict__ cta_pt, const int32_t* __restrict__ pt_off,
+                       const T* __restrict__ cam, const T* __restrict__ pp, const T* __restrict__ pts,
+                       const T* __restrict__ obs, const int32_t* __restrict__ cam_of, const int32_t* __restrict__ pt_of,
+                       T delta, T mu, T* __restrict__ R, T* __restrict__ OBS, T* __restrict__ HPP, T* __restrict__ GPT,
+                       T* __restrict__ HPPINV, T* __restrict__ TP, double* __restrict__ part_rho,
+                       double* __restrict__ part_sq) {
+  constexpr int NI = ModelTraits<MODEL>::NI;
+  constexpr int D = 6 + NI;
+  constexpr int CW = 7 + NI;
+  typedef FusedCfg<T, D> Cfg;
+  constexpr int REC = Cfg::REC, QR = Cfg::QR, SQ = Cfg::SQ, OJP = ObsRec<D>::JP, OV = ObsRec<D>::V;
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  T* stage = reinterpret_cast<T*>(fused_smem);                 // [FUSED_TPB][SQ * 4]; first used as contrib[FUSED_TPB][9]
+  T* hinv = stage + (size_t)FUSED_TPB * SQ * 4;                // [FUSED_TPB][6]
+  const int t = threadIdx.x;
+  const int p0 = cta_pt[blockIdx.x], p1 = cta_pt[blockIdx.x + 1];
+  const int o0 = pt_off[p0], n = pt_off[p1] - o0;
+  const int64_t a = (int64_t)o0 + t;
+  T rec[REC];
+  T rw0 = T(0), rw1 = T(0);
+  int lp = 0;
+  double rho_d = 0.0, sq_d = 0.0;
+  if (t < n) {
+    const int c = cam_of[a], p = pt_of[a];
+    lp = p - p0;
+    T cr[CW], ppv[2], X[3], o[2], r[2];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) cr[i] = __ldg(cam + (size_t)c * CW + i);
+    ppv[0] = __ldg(pp + 2 * (size_t)c); ppv[1] = __ldg(pp + 2 * (size_t)c + 1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) X[i] = __ldg(pts + 3 * (size_t)p + i);
+    o[0] = obs[2 * a]; o[1] = obs[2 * a + 1];
+    ba_linearize<MODEL, T>(cr, ppv, X, o, r, rec, rec + OJP);
+    T s = r[0] * r[0] + r[1] * r[1], rho, w;
+    huber(s, delta, rho, w);
+    rho_d = (double)rho; sq_d = (double)s;
+    rw0 = w * r[0]; rw1 = w * r[1];
+#pragma unroll
+    for (int i = 0; i < 2 * D + 6; ++i) rec[i] *= w;
+#pragma unroll
+    for (int i = OV + 6; i < REC; ++i) rec[i] = T(0);
+    const T* j = rec + OJP;
+    T* cb = stage + (size_t)t * 9;
+    cb[0] = j[0] * j[0] + j[3] * j[3]; cb[1] = j[0] * j[1] + j[3] * j[4]; cb[2] = j[0] * j[2] + j[3] * j[5];
+    cb[3] = j[1] * j[1] + j[4] * j[4]; cb[4] = j[1] * j[2] + j[4] * j[5]; cb[5] = j[2] * j[2] + j[5] * j[5];
+    cb[6] = j[0] * rw0 + j[3] * rw1; cb[7] = j[1] * rw0 + j[4] * rw1; cb[8] = j[2] * rw0 + j[5] * rw1;
+    R[2 * a] = rw0; R[2 * a + 1] = rw1;
+  }
+  __syncthreads();
+  if (t < p1 - p0) {
+    const int p = p0 + t;
+    const int kb = pt_off[p] - o0, ke = pt_off[p + 1] - o0;
+    T h[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    for (int k = kb; k < ke; ++k) {
+      const T* cb = stage + (size_t)k * 9;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) h[i] += cb[i];
+      g[0] += cb[6]; g[1] += cb[7]; g[2] += cb[8];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) HPP[(size_t)p * 6 + i] = h[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) GPT[(size_t)p * 3 + i] = g[i];
+    h[0] = damp_diag(h[0], mu); h[3] = damp_diag(h[3], mu); h[5] = damp_diag(h[5], mu);
+    T iv[6];
+    sym3_inverse(h, iv);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { HPPINV[(size_t)p * 6 + i] = iv[i]; hinv[t * 6 + i] = iv[i]; }
+    TP[(size_t)p * 3 + 0] = iv[0] * g[0] + iv[1] * g[1] + iv[2] * g[2];
+    TP[(size_t)p * 3 + 1] = iv[1] * g[0] + iv[3] * g[1] + iv[4] * g[2];
+    TP[(size_t)p * 3 + 2] = iv[2] * g[0] + iv[4] * g[1] + iv[5] * g[2];
+  }
+  __syncthreads();   // contributions consumed: the stage area is reused for the records
+  if (t < n) {
+    const T* iv = hinv + lp * 6;
+    const T* j = rec + OJP;
+    T* v = rec + OV;
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+      T a0 = j[3 * row], a1 = j[3 * row + 1], a2 = j[3 * row + 2];
+      v[3 * row + 0] = a0 * iv[0] + a1 * iv[1] + a2 * iv[2];
+      v[3 * row + 1] = a0 * iv[1] + a1 * iv[3] + a2 * iv[4];
+      v[3 * row + 2] = a0 * iv[2] + a1 * iv[4] + a2 * iv[5];
+    }
+    T* srow = stage + (size_t)t * SQ * 4;
+#pragma unroll
+    for (int q = 0; q < QR; ++q) QuadIO<T>::st(srow + 4 * q, rec + 4 * q);
+  }
+  __syncthreads();
+  // coalesced write of the CTA's slab: quad i of the slab = record i / QR, quad i % QR
+  T* dst = OBS + (size_t)o0 * REC;
+  for (int i = t; i < n * QR; i += FUSED_TPB) {
+    T q4[4];
+    QuadIO<T>::ld(stage + ((size_t)(i / QR) * SQ + (i % QR)) * 4, q4);
+    QuadIO<T>::st(dst + (size_t)i * 4, q4);
+  }
+  rho_d = block_sum(rho_d);
+  sq_d = block_sum(sq_d);
+  if (t == 0) { part_rho[blockIdx.x] = rho_d; part_sq[blockIdx.x] = sq_d; }
+}
+
 // gather rows: dst[i] = src[idx[i]] with row width W (set-up only)
 template <typename T>
 __global__ void gather_rows_kernel(int64_t n, int W, const T* __restrict__ src, const int32_t* __restrict__ idx, T* __restrict__ dst) {

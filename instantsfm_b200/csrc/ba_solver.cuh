@@ -73,6 +73,9 @@ struct BASolver : BASolverBase {
   bool have_loss = false;
   double loss = 0.0;
   double mu_last = 1.0;
+  bool fused_ok = false;      // every track fits one CTA of the fused K1 (<= FUSED_TPB observations)
+  int n_fused_cta = 0;
+  DeviceBuffer<int32_t> fused_cta_pt;
   double min_damping = 0.0;   // floor on the LM damping used to build the systems (see DESIGN.md, fp32 conditioning)
 
   explicit BASolver(const isfm_ba_desc& d) : desc(d) {
@@ -111,8 +114,10 @@ struct BASolver : BASolverBase {
     R.alloc((size_t)no * 2); OBS.alloc((size_t)no * REC);
     HPP.alloc((size_t)np * 6); GPT.alloc((size_t)np * 3); HPPINV.alloc((size_t)np * 6); TP.alloc((size_t)np * 3);
     DP.alloc((size_t)np * 3);
-    part_a.alloc(std::max<int64_t>(RED_BLOCKS, nc)); part_b.alloc(std::max<int64_t>(RED_BLOCKS, nc));
-    part_c.alloc(std::max<int64_t>(RED_BLOCKS, nc));
+    build_fused_partition();
+    if (getenv("ISFM_NO_FUSED")) fused_ok = false;
+    const int64_t n_part = std::max<int64_t>(std::max<int64_t>(RED_BLOCKS, nc), n_fused_cta);
+    part_a.alloc(n_part); part_b.alloc(n_part); part_c.alloc(n_part);
     scalars.alloc(4); fail.alloc(1); fail.zero(s);
     if (desc.optimize_poses) {
       build_schur_pattern(sp, ix, s, timers);
@@ -147,6 +152,38 @@ struct BASolver : BASolverBase {
     linearize_kernel<T, MODEL><<<g, BA_TPB, 0, s>>>(n_obs, cam[cur].get(), pp.get(), pts[cur].get(), obs.get(),
                                                     ix.cam_of.get(), ix.pt_of.get(), (T)desc.huber_delta, R.get(), OBS.get(),
                                                     part_a.get(), part_b.get());
+  }
+
+  // fused K1 + point solve of the first trial; returns the number of cost partials
+  int run_fused_linearize(T mu) {
+    TimerScope ts(timers, T_LINEARIZE);
+    fused_linearize_kernel<T, MODEL><<<n_fused_cta, FUSED_TPB, FusedCfg<T, D>::SMEM, s>>>(
+        fused_cta_pt.get(), ix.pt_off.get(), cam[cur].get(), pp.get(), pts[cur].get(), obs.get(), ix.cam_of.get(),
+        ix.pt_of.get(), (T)desc.huber_delta, mu, R.get(), OBS.get(), HPP.get(), GPT.get(), HPPINV.get(), TP.get(),
+        part_a.get(), part_b.get());
+    return n_fused_cta;
+  }
+
+  // greedy packing of whole points into CTAs of <= FUSED_TPB observations (host, one pass)
+  void build_fused_partition() {
+    std::vector<int32_t> off((size_t)n_pt + 1), cta;
+    ISFM_CUDA(cudaMemcpyAsync(off.data(), ix.pt_off.get(), off.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));
+    fused_ok = true;
+    cta.push_back(0);
+    int32_t start = 0;
+    for (int64_t p = 0; p < n_pt; ++p) {
+      if (off[p + 1] - off[p] > FUSED_TPB) { fused_ok = false; break; }
+      if (off[p + 1] - off[start] > FUSED_TPB) { cta.push_back((int32_t)p); start = (int32_t)p; }
+    }
+    cta.push_back((int32_t)n_pt);
+    if (!fused_ok) return;
+    n_fused_cta = (int)cta.size() - 1;
+    fused_cta_pt.alloc(cta.size());
+    ISFM_CUDA(cudaMemcpyAsync(fused_cta_pt.get(), cta.data(), cta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));
+    ISFM_CUDA(cudaFuncSetAttribute(fused_linearize_kernel<T, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)FusedCfg<T, D>::SMEM));
   }
 
   void run_cost(int which, double* robust, double* sq) {
@@ -211,10 +248,15 @@ struct BASolver : BASolverBase {
 
   void step(double* loss_out, isfm_step_stats* st) override {
     ISFM_REQUIRE(has_problem, ISFM_ESTATE, "isfm_ba_step before isfm_ba_set_problem");
-    // R, J at the current parameters (+ the initial loss on the first call: `self.loss`)
-    run_linearize();
+    // R, J at the current parameters (+ the initial loss on the first call: `self.loss`).
+    // The first trial's damping is known here, so the fused kernel also does the point solve.
+    const double mu_cap = sizeof(T) == 4 ? 1e24 : 1e100;
+    const double mu_first = std::min(1.0 + std::max(tr.damping, min_damping), mu_cap);
+    int lin_parts;
+    if (fused_ok) lin_parts = run_fused_linearize((T)mu_first);
+    else { run_linearize(); lin_parts = red_grid(n_obs); }
     if (!have_loss) {
-      const int g = red_grid(n_obs);
+      const int g = lin_parts;
       fetch_scalars(part_a.get(), g, part_b.get(), g, nullptr, 0, true);
       loss = h_scalars[0];
       have_loss = true;
@@ -231,8 +273,8 @@ struct BASolver : BASolverBase {
     const int trial = cur ^ 1;
     while (last <= loss) {
       // cumulative across rejected trials (pypose LM); capped so that damped blocks stay finite in T
-      mu = std::min(mu * (1.0 + std::max(tr.damping, min_damping)), sizeof(T) == 4 ? 1e24 : 1e100);
-      run_point_solve(!built, (T)mu);
+      mu = std::min(mu * (1.0 + std::max(tr.damping, min_damping)), mu_cap);
+      if (!(fused_ok && !built)) run_point_solve(!built, (T)mu);   // first trial: done by the fused kernel (mu == mu_first)
       built = true;
       int mterm_parts;
       if (desc.optimize_poses) {
