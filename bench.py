@@ -105,7 +105,9 @@ def algorithmic_bytes(name, n_obs, n_pt, n_cam, d, n_pairs, n_lists, nnzb, fsize
     """Algorithmic HBM bytes of ONE launch of a kernel family."""
     dd = d * d
     table = {
-        "linearize": n_obs * (8 + 8 + fsize * (2 + 2 * d + 6)) + n_pt * 3 * fsize + n_cam * (9 + d) * fsize,
+        # fused K1 + point solve: obs + indices read; R and the full record (Jc | Jp | V, padded) written;
+        # per point X read, Hpp | g_p | Hpp^-1 | t_p written; camera table read
+        "linearize": n_obs * (8 + 8 + fsize * (2 + (2 * d + 12 + 3) // 4 * 4)) + n_pt * (8 + fsize * (3 + 18)) + n_cam * (9 + d) * fsize,
         "point_blocks": n_obs * fsize * (6 + 2 + 6) + n_pt * (4 + fsize * (6 + 3 + 6 + 3)),
         "point_solve": n_obs * fsize * (6 + 6) + n_pt * (4 + fsize * (6 + 3 + 6 + 3)),
         # average of the H pass (idx 4, Jc, R) and the E pass (idx 8, Jc, V, Jp, t_p): reported per pass below

@@ -364,8 +364,8 @@ schur_offdiag_kernel(int64_t n_lists, const int32_t* __restrict__ list_order, co
   const int64_t warp = blockIdx.x * (int64_t)(SCHUR_TPB / 32) + w;
   const int64_t slot_in_order = warp * GPW + grp;
   const bool valid = grp < GPW && slot_in_order < n_lists;
-  // lists are visited in order of decreasing length, so the GPW lists of a warp have (almost)
-  // the same trip count
+  // lists are visited in row-major windows, by decreasing length inside a window: the GPW lists
+  // of a warp have (almost) the same trip count and stay in the same one or two block rows
   const int64_t u = valid ? list_order[slot_in_order] : 0;
   const int64_t beg = valid ? list_off[u] : 0;
   const int len = valid ? (int)(list_off[u + 1] - beg) : 0;
@@ -551,7 +551,7 @@ template <typename T, int D> struct FusedCfg {
 };
 
 template <typename T, int MODEL>
-__global__ void __launch_bounds__(FUSED_TPB)
+__global__ void __launch_bounds__(FUSED_TPB, sizeof(T) == 4 ? 4 : 1)
 fused_linearize_kernel(const int32_t* __restrict__ cta_pt, const int32_t* __restrict__ pt_off,
                        const T* __restrict__ cam, const T* __restrict__ pp, const T* __restrict__ pts,
                        const T* __restrict__ obs, const int32_t* __restrict__ cam_of, const int32_t* __restrict__ pt_of,
@@ -601,6 +601,8 @@ fused_linearize_kernel(const int32_t* __restrict__ cta_pt, const int32_t* __rest
     R[2 * a] = rw0; R[2 * a + 1] = rw1;
   }
   __syncthreads();
+  // one thread per point (measured faster than letting each point's first observation thread do
+  // it: the point threads then fill two warps densely instead of diverging all eight)
   if (t < p1 - p0) {
     const int p = p0 + t;
     const int kb = pt_off[p] - o0, ke = pt_off[p + 1] - o0;

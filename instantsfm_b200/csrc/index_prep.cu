@@ -157,11 +157,14 @@ __global__ void remap_slots_kernel(int64_t n, int32_t* slots, const int32_t* __r
   if (t < n) slots[t] = slot_of[slots[t]];
 }
 
-// key = ~length so that an ascending stable sort yields decreasing lengths
-__global__ void list_len_key_kernel(const int64_t* __restrict__ list_off, int64_t n_lists, uint32_t* key, int32_t* id) {
+// Visiting order of the pair lists: row-major windows of LIST_WINDOW lists (locality of the
+// a-side records), decreasing length inside a window (equal trip counts inside a warp).
+constexpr int LIST_WINDOW = 1 << 30;   // one window = plain sort by decreasing length (measured faster than row windows)
+__global__ void list_len_key_kernel(const int64_t* __restrict__ list_off, int64_t n_lists, uint64_t* key, int32_t* id) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n_lists) return;
-  key[t] = ~(uint32_t)(list_off[t + 1] - list_off[t]);
+  const uint64_t len = (uint64_t)(list_off[t + 1] - list_off[t]);
+  key[t] = ((uint64_t)(t / LIST_WINDOW) << 32) | (0xffffffffull - (len < 0xffffffffull ? len : 0xffffffffull));
   id[t] = (int32_t)t;
 }
 
@@ -308,13 +311,13 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
     ISFM_CUDA(cudaGetLastError());
     ISFM_CUDA(cudaStreamSynchronize(s));
   }
-  // 5b. list visiting order: decreasing length, ties by list id (stable radix sort)
+  // 5b. list visiting order (stable radix sort)
   if (n_lists > 0) {
     ISFM_REQUIRE(n_lists < (1ll << 31), ISFM_EINVAL, "too many pair lists");
-    DeviceBuffer<uint32_t> lkey, lkey_s; DeviceBuffer<int32_t> lid;
+    DeviceBuffer<uint64_t> lkey, lkey_s; DeviceBuffer<int32_t> lid;
     lkey.alloc(n_lists); lkey_s.alloc(n_lists); lid.alloc(n_lists); sp.list_order.alloc(n_lists);
     list_len_key_kernel<<<div_up(n_lists, TPB), TPB, 0, s>>>(sp.list_off.get(), n_lists, lkey.get(), lid.get());
-    sort_pairs(lkey.get(), lkey_s.get(), lid.get(), sp.list_order.get(), n_lists, 32, s);
+    sort_pairs(lkey.get(), lkey_s.get(), lid.get(), sp.list_order.get(), n_lists, 64, s);
   }
   // 6. pad every row to a multiple of 4 slots (padding slots: col = row, zero values, no deposit)
   //    and cut the rows into mat-vec chunks (host: n_cam + 1 integers)
