@@ -453,7 +453,14 @@ __global__ void precond_kernel(int n_cam, const T* __restrict__ HCC, const T* __
       HD[(size_t)cam * (D * D) + r * D + c] = v;
       M[r * D + c] = (double)v - (double)e[r * D + c];
     }
-  if (!spd_inverse<D>(M)) *fail = 1;
+  if (!spd_inverse<D>(M)) {
+    // Hd - E_ii lost positive definiteness to cancellation (degenerate points in fp32): fall back
+    // to the always-SPD damped Hcc block -- a weaker preconditioner, the system itself is unchanged
+    *fail = cam + 1;
+#pragma unroll 1
+    for (int k = 0; k < D * D; ++k) M[k] = (double)HD[(size_t)cam * (D * D) + k];
+    spd_inverse<D>(M);
+  }
 #pragma unroll 1
   for (int k = 0; k < D * D; ++k) MINV[(size_t)cam * (D * D) + k] = (T)M[k];
 #pragma unroll 1

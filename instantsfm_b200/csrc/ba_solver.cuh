@@ -280,6 +280,22 @@ struct BASolver : BASolverBase {
       if (desc.optimize_poses) {
         int pcg_status = 0;
         stats.pcg_iters += run_schur_and_pcg((T)mu, &pcg_status);
+        if (getenv("ISFM_DEBUG")) {
+          int h_fail = 0;
+          ISFM_CUDA(cudaMemcpyAsync(&h_fail, fail.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
+          ISFM_CUDA(cudaStreamSynchronize(s));
+          fprintf(stderr, "[isfm] pcg status %d (1 converged, 0 max_iter, 2 breakdown) precond_fail_cam %d bb %.6e rho0 %.6e\n",
+                  pcg_status, h_fail - 1, pcg.h_state->bb, pcg.h_state->rho[0]);
+          if (h_fail) {
+            const int c = h_fail - 1;
+            std::vector<T> hh((size_t)D * D), ee((size_t)D * D + D);
+            ISFM_CUDA(cudaMemcpy(hh.data(), HD.get() + (size_t)c * D * D, hh.size() * sizeof(T), cudaMemcpyDeviceToHost));
+            ISFM_CUDA(cudaMemcpy(ee.data(), RED.get() + (size_t)c * (D * D + D), ee.size() * sizeof(T), cudaMemcpyDeviceToHost));
+            for (int r = 0; r < D; ++r) fprintf(stderr, "[isfm]   cam %d diag %d: Hd %.9e  E %.9e  S %.9e\n", c, r, (double)hh[r * D + r],
+                                               (double)ee[r * D + r], (double)hh[r * D + r] - (double)ee[r * D + r]);
+            ISFM_CUDA(cudaMemsetAsync(fail.get(), 0, sizeof(int), s));
+          }
+        }
         { TimerScope ts(timers, T_BACKSUB);
           mterm_parts = red_grid(n_pt);
           backsub_kernel<T, D><<<mterm_parts, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), ix.cam_of.get(), OBS.get(), R.get(),

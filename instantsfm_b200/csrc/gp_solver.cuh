@@ -223,7 +223,12 @@ __global__ void gp_precond_kernel(int n_cam, const T* __restrict__ acc_local, co
   T hd[9] = {g[0] + dd, g[1], g[2], g[1], g[3] + dd, g[4], g[2], g[4], g[5] + dd};
   double M[9] = {(double)hd[0] - g[10], (double)hd[1] - g[11], (double)hd[2] - g[12], (double)hd[3] - g[11], (double)hd[4] - g[13],
                  (double)hd[5] - g[14], (double)hd[6] - g[12], (double)hd[7] - g[14], (double)hd[8] - g[15]};
-  if (!spd_inverse<3>(M)) *fail = 1;
+  if (!spd_inverse<3>(M)) {   // cancellation: fall back to the SPD block H'cc as preconditioner
+    *fail = cam + 1;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) M[k] = (double)hd[k];
+    spd_inverse<3>(M);
+  }
 #pragma unroll
   for (int k = 0; k < 9; ++k) { HD[(size_t)cam * 9 + k] = hd[k]; MINV[(size_t)cam * 9 + k] = (T)M[k]; }
 #pragma unroll

@@ -180,15 +180,45 @@ def _visibility(rng, n_cam, n_pt, n_obs, window, kmin=2):
     return cam.astype(np.int32), pt.astype(np.int32)
 
 
+def _street_cameras(rng, n_cam, window):
+    """Cameras along a closed street (ring of circumference n_cam * spacing) looking at the
+    facade ~30 units inside the ring.  `window` consecutive cameras span ~25 units, so the
+    tracks of a banded problem keep wide baselines (depth 15..40)."""
+    spacing = 25.0 / window
+    radius = n_cam * spacing / (2 * np.pi)
+    ang = 2 * np.pi * np.arange(n_cam) / n_cam
+    C = np.stack([radius * np.cos(ang), radius * np.sin(ang), rng.uniform(-1, 1, n_cam)], 1)
+    inward = -np.stack([np.cos(ang), np.sin(ang), np.zeros(n_cam)], 1)
+    z = inward * 30.0 + rng.normal(scale=1.5, size=(n_cam, 3))
+    z /= np.linalg.norm(z, axis=1, keepdims=True)
+    up = np.array([0.0, 0.0, 1.0])
+    x = np.cross(z, up)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    y = np.cross(z, x)
+    R = np.stack([x, y, z], axis=1)
+    M = np.zeros((n_cam, 4, 4))
+    M[:, :3, :3] = R
+    M[:, :3, 3] = -np.einsum("nij,nj->ni", R, C)
+    M[:, 3, 3] = 1
+    return matrices_to_pose7(M), radius, spacing
+
+
 def make_ba_problem(n_cam, n_pt, n_obs, window=None, seed=0, model_id=3, noise_px=0.5,
                     outlier_frac=0.01, perturb=1.0, point_seed=None):
     """Build a BAL-shaped problem; ``perturb`` scales the initial-state perturbation.
 
+    ``window >= n_cam``: object-centric orbit, every camera may see every point (dense reduced
+    camera system, BAL-like).  ``window < n_cam``: street geometry, a point is seen only from
+    ``window`` consecutive cameras (banded system, city-scale).
     ``point_seed``: draw points / visibility / noise from their own stream, so that several
     ranks can generate disjoint point shards over the SAME cameras (multi-GPU bench)."""
     rng = np.random.default_rng(seed)
     window = n_cam if window is None else window
-    pose_gt, _ = _orbit_cameras(rng, n_cam)
+    street = window < n_cam
+    if street:
+        pose_gt, radius, spacing = _street_cameras(rng, n_cam, window)
+    else:
+        pose_gt, _ = _orbit_cameras(rng, n_cam)
     ni, nf = N_INTR[model_id], N_FOCAL[model_id]
     intr_gt = np.empty((n_cam, ni))
     intr_gt[:, :nf] = rng.uniform(800, 1200, (n_cam, 1))
@@ -205,10 +235,23 @@ def make_ba_problem(n_cam, n_pt, n_obs, window=None, seed=0, model_id=3, noise_p
     cam0[:, 7:7 + nf] *= 1 + rng.normal(scale=perturb * 0.01, size=(n_cam, nf))
     if point_seed is not None:
         rng = np.random.default_rng(point_seed)
-    # points in a ball of radius 10 around the origin
-    X = rng.normal(size=(n_pt, 3))
-    X *= (10.0 * rng.uniform(0, 1, (n_pt, 1)) ** (1 / 3)) / np.linalg.norm(X, axis=1, keepdims=True)
     ci, pi = _visibility(rng, n_cam, n_pt, n_obs, window)
+    if street:
+        # a point sits on the facade opposite the middle of its camera window, 15..40 deep
+        first = np.searchsorted(pi, np.arange(n_pt))
+        k = np.diff(np.append(first, pi.shape[0]))
+        W = _prev_prime(min(window, n_cam))
+        mid = ci[first].astype(np.int64)                 # any camera of the track fixes the arc position
+        # circular mean of the track's cameras (they span < W << n_cam positions)
+        rel = ((ci.astype(np.int64) - mid[pi] + n_cam // 2) % n_cam) - n_cam // 2
+        centre = mid + np.round(np.bincount(pi, weights=rel, minlength=n_pt) / k)
+        theta = 2 * np.pi * (centre + rng.uniform(-0.5, 0.5, n_pt)) / n_cam
+        rad = radius - rng.uniform(15, 40, n_pt)
+        X = np.stack([rad * np.cos(theta), rad * np.sin(theta), rng.uniform(-6, 6, n_pt)], 1)
+    else:
+        # points in a ball of radius 10 around the origin
+        X = rng.normal(size=(n_pt, 3))
+        X *= (10.0 * rng.uniform(0, 1, (n_pt, 1)) ** (1 / 3)) / np.linalg.norm(X, axis=1, keepdims=True)
     obs, depth = project_numpy(model_id, X[pi], cam_gt[ci], pps[ci])
     assert depth.min() > 0.1
     obs += rng.normal(scale=noise_px, size=obs.shape)
