@@ -86,7 +86,10 @@ struct BASolver : BASolverBase {
     ISFM_CUDA(cudaMallocHost(&h_scalars, 4 * sizeof(double)));
     if (const char* e = getenv("ISFM_MIN_DAMPING")) min_damping = atof(e);
   }
-  ~BASolver() override { if (h_scalars) cudaFreeHost(h_scalars); }
+  ~BASolver() override {
+    cudaStreamSynchronize(s);   // buffers go back to the stream-ordered pool after all work has finished
+    if (h_scalars) cudaFreeHost(h_scalars);
+  }
 
   T* HCC() { return HCC_GC.get(); }
   T* GC() { return HCC_GC.get() + (size_t)n_cam * D * D; }

@@ -102,6 +102,22 @@ struct TimerScope {
   ~TimerScope() { t.end(); }
 };
 
+// Device memory comes from the device's default stream-ordered pool with an unlimited release
+// threshold: buffers freed by one handle are re-used by the next (the reference's pipeline
+// creates three BA solvers back to back) instead of going back to the driver.
+inline void ensure_pool_configured() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t threshold = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  done = true;
+}
+
 template <typename T>
 struct DeviceBuffer {
   T* ptr = nullptr;
@@ -110,12 +126,13 @@ struct DeviceBuffer {
   DeviceBuffer(const DeviceBuffer&) = delete;
   DeviceBuffer& operator=(const DeviceBuffer&) = delete;
   ~DeviceBuffer() { release(); }
-  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; count = 0; }
+  void release() { if (ptr) cudaFreeAsync(ptr, 0); ptr = nullptr; count = 0; }
   void alloc(size_t n) {
     if (n <= count && ptr) return;
     release();
     if (n == 0) n = 1;
-    ISFM_CUDA(cudaMalloc(&ptr, n * sizeof(T)));
+    ensure_pool_configured();
+    ISFM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ptr), n * sizeof(T), 0));
     count = n;
   }
   void zero(cudaStream_t s) { if (ptr) ISFM_CUDA(cudaMemsetAsync(ptr, 0, count * sizeof(T), s)); }

@@ -336,7 +336,10 @@ struct GPSolver : GPSolverBase {
     tr.init(d.tr_radius, d.tr_max, d.tr_up, d.tr_down);
     ISFM_CUDA(cudaMallocHost(&h_scalars, 4 * sizeof(double)));
   }
-  ~GPSolver() override { if (h_scalars) cudaFreeHost(h_scalars); }
+  ~GPSolver() override {
+    cudaStreamSynchronize(s);   // buffers go back to the stream-ordered pool after all work has finished
+    if (h_scalars) cudaFreeHost(h_scalars);
+  }
 
   template <typename U>
   void upload(DeviceBuffer<U>& dst, const void* src, size_t count) {

@@ -21,7 +21,28 @@ struct PcgState {
   double rr;       // ||r||^2 after the last completed iteration
   int done;        // 1: converged, 2: breakdown (non-finite / non-positive curvature)
   int iters;
+  double pq;       // p.q of the current iteration (published by the last CTA of the mat-vec tail)
+  unsigned int ticket;
 };
+
+// The CTA that finishes last sums the per-CTA partials in index order (deterministic) and
+// publishes the scalar: the next kernel reads one double instead of re-reducing n partials in
+// every CTA.  Integer ticket only; no floating-point atomics.
+__device__ __forceinline__ void publish_sum_last_cta(double cta_value, double* partial, unsigned int* ticket, double* out) {
+  __shared__ bool is_last__;
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = cta_value;
+    __threadfence();
+    is_last__ = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last__) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) v += __ldcg(partial + i);
+    v = block_sum(v);
+    if (threadIdx.x == 0) { *out = v; *ticket = 0u; }
+  }
+}
 
 constexpr int PCG_TPB = 128;
 
@@ -132,7 +153,7 @@ __global__ void __launch_bounds__(PCG_TPB)
 pcg_combine_kernel(const int32_t* __restrict__ lrow_ptr, const int32_t* __restrict__ chunk_ptr,
                    const T* __restrict__ yup_part, const T* __restrict__ C, const T* __restrict__ Hd,
                    const T* __restrict__ p, T* __restrict__ out, double* __restrict__ partial,
-                   const PcgState* __restrict__ st) {
+                   PcgState* __restrict__ st) {
   if (st->done) return;
   constexpr int G = PCG_TPB / D;   // entry groups per CTA; threads >= G * D idle
   __shared__ T sh[G][D];
@@ -173,36 +194,38 @@ pcg_combine_kernel(const int32_t* __restrict__ lrow_ptr, const int32_t* __restri
   }
   if (FUSED) {
     __syncthreads();
+    double s = 0.0;
     if (threadIdx.x == 0) {
-      double s = 0.0;
 #pragma unroll
       for (int k = 0; k < D; ++k) s += (double)qs[k];
-      partial[row] = s;
     }
+    publish_sum_last_cta(s, partial, &st->ticket, &st->pq);
   }
 }
 
 // multi-rank second half: q = Hd p - y (y all-reduced), per-row partial of p.q
 template <typename T, int D>
-__global__ void pcg_apply_diag_kernel(int n_cam, const T* __restrict__ Hd, const T* __restrict__ p,
-                                      const T* __restrict__ y, T* __restrict__ q, double* __restrict__ partial,
-                                      const PcgState* __restrict__ st) {
+__global__ void __launch_bounds__(PCG_TPB)
+pcg_apply_diag_kernel(int n_cam, const T* __restrict__ Hd, const T* __restrict__ p, const T* __restrict__ y,
+                      T* __restrict__ q, double* __restrict__ partial, PcgState* __restrict__ st) {
   if (st->done) return;
   int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n_cam) return;
-  const T* h = Hd + (size_t)row * (D * D);
-  const T* pi = p + (size_t)row * D;
   double s = 0.0;
+  if (row < n_cam) {
+    const T* h = Hd + (size_t)row * (D * D);
+    const T* pi = p + (size_t)row * D;
 #pragma unroll
-  for (int r = 0; r < D; ++r) {
-    T v = T(0);
+    for (int r = 0; r < D; ++r) {
+      T v = T(0);
 #pragma unroll
-    for (int c = 0; c < D; ++c) v += h[r * D + c] * pi[c];
-    v -= y[(size_t)row * D + r];
-    q[(size_t)row * D + r] = v;
-    s += (double)v * (double)pi[r];
+      for (int c = 0; c < D; ++c) v += h[r * D + c] * pi[c];
+      v -= y[(size_t)row * D + r];
+      q[(size_t)row * D + r] = v;
+      s += (double)v * (double)pi[r];
+    }
   }
-  partial[row] = s;
+  s = block_sum(s);
+  publish_sum_last_cta(s, partial, &st->ticket, &st->pq);
 }
 
 // r0 = b, x0 = 0, z0 = Minv r0, p0 = z0; partials of (r.z, b.b) per camera
@@ -237,7 +260,7 @@ __global__ void pcg_init_state_kernel(int n, const double* __restrict__ part_rz,
   double rz = reduce_partials(part_rz, n);
   double bb = reduce_partials(part_bb, n);
   if (threadIdx.x == 0) {
-    st->rho[0] = rz; st->rho[1] = 0.0; st->bb = bb; st->rr = bb; st->iters = 0;
+    st->rho[0] = rz; st->rho[1] = 0.0; st->bb = bb; st->rr = bb; st->iters = 0; st->pq = 0.0; st->ticket = 0u;
     st->done = (bb == 0.0) ? 1 : ((isfinite(rz) && isfinite(bb)) ? 0 : 2);
   }
 }
@@ -250,7 +273,7 @@ pcg_update_kernel(int n_cam, int n_part_pq, int it, const double* __restrict__ p
                   T* __restrict__ z, double* __restrict__ part_rz, double* __restrict__ part_rr,
                   const PcgState* __restrict__ st) {
   if (st->done) return;
-  const double pq = reduce_partials(part_pq, n_part_pq);
+  const double pq = st->pq;
   const double alpha_d = st->rho[it & 1] / pq;
   const T alpha = (T)alpha_d;
   int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,7 +323,7 @@ pcg_direction_kernel(int n_cam, int n_part, int n_part_pq, int it, double tol2, 
     }
   }
   if (blockIdx.x == 0) {
-    const double pq = reduce_partials(part_pq, n_part_pq);
+    const double pq = st->pq;
     if (threadIdx.x == 0) {
       st->rho[(it + 1) & 1] = rho_new;
       st->rr = rr;
