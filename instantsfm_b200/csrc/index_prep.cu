@@ -159,7 +159,7 @@ __global__ void remap_slots_kernel(int64_t n, int32_t* slots, const int32_t* __r
 
 // Visiting order of the pair lists: row-major windows of LIST_WINDOW lists (locality of the
 // a-side records), decreasing length inside a window (equal trip counts inside a warp).
-constexpr int LIST_WINDOW = 1 << 30;   // one window = plain sort by decreasing length (measured faster than row windows)
+constexpr int LIST_WINDOW = 4096;   // ~2 block rows of a 1.8 k-camera dense system
 __global__ void list_len_key_kernel(const int64_t* __restrict__ list_off, int64_t n_lists, uint64_t* key, int32_t* id) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n_lists) return;

@@ -265,73 +265,63 @@ __global__ void pcg_init_state_kernel(int n, const double* __restrict__ part_rz,
   }
 }
 
-// alpha = rho / (p.q); x += alpha p; r -= alpha q; z = Minv r; partials of r.z and r.r
+// alpha = rho / (p.q); x += alpha p; r -= alpha q; z = Minv r; partials of r.z and r.r.
+// D threads per camera (thread k owns component k and row k of Minv): 14 cameras per CTA at
+// D = 9 instead of one thread per camera, which left a 1.8 k-camera system on 14 CTAs.
 template <typename T, int D>
 __global__ void __launch_bounds__(PCG_TPB)
-pcg_update_kernel(int n_cam, int n_part_pq, int it, const double* __restrict__ part_pq, const T* __restrict__ Minv,
-                  const T* __restrict__ p, const T* __restrict__ q, T* __restrict__ x, T* __restrict__ r,
-                  T* __restrict__ z, double* __restrict__ part_rz, double* __restrict__ part_rr,
-                  const PcgState* __restrict__ st) {
+pcg_update_kernel(int n_cam, int it, const T* __restrict__ Minv, const T* __restrict__ p, const T* __restrict__ q,
+                  T* __restrict__ x, T* __restrict__ r, T* __restrict__ z, double* __restrict__ part_rz,
+                  double* __restrict__ part_rr, const PcgState* __restrict__ st) {
   if (st->done) return;
-  const double pq = st->pq;
-  const double alpha_d = st->rho[it & 1] / pq;
-  const T alpha = (T)alpha_d;
-  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int CPB = PCG_TPB / D;
+  const T alpha = (T)(st->rho[it & 1] / st->pq);
+  const int cam = blockIdx.x * CPB + threadIdx.x / D, k = threadIdx.x % D;
+  const bool on = threadIdx.x < CPB * D && cam < n_cam;
+  T rv[D];
+  if (on) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) { const size_t o = (size_t)cam * D + c; rv[c] = r[o] - alpha * q[o]; }
+  }
+  __syncthreads();   // every thread of a camera has read the old r before anyone overwrites it
   double rz = 0.0, rr = 0.0;
-  if (row < n_cam) {
-    const T* m = Minv + (size_t)row * (D * D);
-    T rv[D];
+  if (on) {
+    const size_t o = (size_t)cam * D + k;
+    x[o] += alpha * p[o];
+    r[o] = rv[k];
+    const T* __restrict__ m = Minv + (size_t)cam * (D * D) + k * D;
+    T zz = T(0);
 #pragma unroll
-    for (int c = 0; c < D; ++c) {
-      size_t o = (size_t)row * D + c;
-      x[o] += alpha * p[o];
-      rv[c] = r[o] - alpha * q[o];
-      r[o] = rv[c];
-      rr += (double)rv[c] * (double)rv[c];
-    }
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      T zz = T(0);
-#pragma unroll
-      for (int c = 0; c < D; ++c) zz += m[k * D + c] * rv[c];
-      z[(size_t)row * D + k] = zz;
-      rz += (double)zz * (double)rv[k];
-    }
+    for (int c = 0; c < D; ++c) zz += m[c] * rv[c];
+    z[o] = zz;
+    rz = (double)zz * (double)rv[k];
+    rr = (double)rv[k] * (double)rv[k];
   }
   rz = block_sum(rz);
   rr = block_sum(rr);
   if (threadIdx.x == 0) { part_rz[blockIdx.x] = rz; part_rr[blockIdx.x] = rr; }
 }
 
-// beta = rho_new / rho; p = z + beta p; block 0 publishes the new state
+// beta = rho_new / rho; p = z + beta p (one thread per vector entry); block 0 publishes the new state
 template <typename T, int D>
 __global__ void __launch_bounds__(PCG_TPB)
-pcg_direction_kernel(int n_cam, int n_part, int n_part_pq, int it, double tol2, const double* __restrict__ part_rz,
-                     const double* __restrict__ part_rr, const double* __restrict__ part_pq,
-                     const T* __restrict__ z, T* __restrict__ p, PcgState* st) {
+pcg_direction_kernel(int n_cam, int n_part, int it, double tol2, const double* __restrict__ part_rz,
+                     const double* __restrict__ part_rr, const T* __restrict__ z, T* __restrict__ p, PcgState* st) {
   if (st->done) return;
   const double rho_new = reduce_partials(part_rz, n_part);
   const double rr = reduce_partials(part_rr, n_part);
   const double rho = st->rho[it & 1];
   const T beta = (T)(rho_new / rho);
-  int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row < n_cam) {
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-      size_t o = (size_t)row * D + c;
-      p[o] = z[o] + beta * p[o];
-    }
-  }
-  if (blockIdx.x == 0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_cam * D) p[i] = z[i] + beta * p[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double pq = st->pq;
-    if (threadIdx.x == 0) {
-      st->rho[(it + 1) & 1] = rho_new;
-      st->rr = rr;
-      st->iters = it + 1;
-      // `done` is read at kernel entry by every block of the NEXT launch only
-      if (!(isfinite(rho_new) && isfinite(rr)) || !(pq > 0.0)) st->done = 2;
-      else if (rr < tol2 * st->bb) st->done = 1;
-    }
+    st->rho[(it + 1) & 1] = rho_new;
+    st->rr = rr;
+    st->iters = it + 1;
+    // `done` is read at kernel entry by every block of the NEXT launch only
+    if (!(isfinite(rho_new) && isfinite(rr)) || !(pq > 0.0)) st->done = 2;
+    else if (rr < tol2 * st->bb) st->done = 1;
   }
 }
 
@@ -364,6 +354,7 @@ struct BlockPCG {
             const T* Hd, const T* Minv, const T* b, double tol, int max_iter, isfm_comm* comm, cudaStream_t s,
             KernelTimers& kt, int* status_out) {
     const int nb = div_up(n_cam, PCG_TPB);
+    const int nb_upd = div_up(n_cam, PCG_TPB / D), nb_dir = div_up((int64_t)n_cam * D, PCG_TPB);
     const bool multi = comm_world(comm) > 1;
     { TimerScope ts(kt, T_PCG_VEC);
       pcg_init_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, b, Minv, x.get(), r.get(), p.get(), part_a.get(), part_b.get()); }
@@ -392,11 +383,11 @@ struct BlockPCG {
             pcg_apply_diag_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, Hd, p.get(), y.get(), q.get(), part_pq.get(), state.get()); }
         }
         { TimerScope ts(kt, T_PCG_VEC);
-          pcg_update_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, n_cam, it, part_pq.get(), Minv, p.get(), q.get(), x.get(),
-                                                        r.get(), z.get(), part_a.get(), part_b.get(), state.get()); }
+          pcg_update_kernel<T, D><<<nb_upd, PCG_TPB, 0, s>>>(n_cam, it, Minv, p.get(), q.get(), x.get(), r.get(), z.get(),
+                                                            part_a.get(), part_b.get(), state.get()); }
         { TimerScope ts(kt, T_PCG_VEC);
-          pcg_direction_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, nb, n_cam, it, tol2, part_a.get(), part_b.get(),
-                                                           part_pq.get(), z.get(), p.get(), state.get()); }
+          pcg_direction_kernel<T, D><<<nb_dir, PCG_TPB, 0, s>>>(n_cam, nb_upd, it, tol2, part_a.get(), part_b.get(), z.get(),
+                                                               p.get(), state.get()); }
       }
       ISFM_CUDA(cudaMemcpyAsync(h_state, state.get(), sizeof(PcgState), cudaMemcpyDeviceToHost, s));
       ISFM_CUDA(cudaStreamSynchronize(s));
