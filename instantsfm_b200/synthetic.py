@@ -162,7 +162,7 @@ def _orbit_cameras(rng, n_cam, radius=30.0):
     return matrices_to_pose7(M), C
 
 
-def _visibility(rng, n_cam, n_pt, n_obs, window, kmin=2):
+def _visibility(rng, n_cam, n_pt, n_obs, window, kmin=2, anchor_range=None):
     """Sorted-by-point observation lists: camera_indices, point_indices (int32).
 
     Slots inside the window are visited with a per-point stride modulo a prime W, so the
@@ -170,7 +170,12 @@ def _visibility(rng, n_cam, n_pt, n_obs, window, kmin=2):
     W = _prev_prime(min(window, n_cam))
     k = _track_lengths(rng, n_pt, n_obs, min(200, W), kmin)
     stride = rng.integers(1, W, size=n_pt) if W > 2 else np.ones(n_pt, dtype=np.int64)
-    anchor = rng.integers(0, n_cam, size=n_pt)
+    if anchor_range is None:
+        anchor = rng.integers(0, n_cam, size=n_pt)
+    else:
+        # banded problems: points follow the street (sorted anchors), optionally restricted to
+        # one rank's arc, so that contiguous point ranges touch contiguous camera ranges
+        anchor = np.sort(rng.integers(anchor_range[0], anchor_range[1], size=n_pt))
     start = rng.integers(0, W, size=n_pt)
     pt = np.repeat(np.arange(n_pt, dtype=np.int64), k)
     offs = np.cumsum(k) - k
@@ -204,7 +209,7 @@ def _street_cameras(rng, n_cam, window):
 
 
 def make_ba_problem(n_cam, n_pt, n_obs, window=None, seed=0, model_id=3, noise_px=0.5,
-                    outlier_frac=0.01, perturb=1.0, point_seed=None):
+                    outlier_frac=0.01, perturb=1.0, point_seed=None, anchor_range=None):
     """Build a BAL-shaped problem; ``perturb`` scales the initial-state perturbation.
 
     ``window >= n_cam``: object-centric orbit, every camera may see every point (dense reduced
@@ -235,7 +240,9 @@ def make_ba_problem(n_cam, n_pt, n_obs, window=None, seed=0, model_id=3, noise_p
     cam0[:, 7:7 + nf] *= 1 + rng.normal(scale=perturb * 0.01, size=(n_cam, nf))
     if point_seed is not None:
         rng = np.random.default_rng(point_seed)
-    ci, pi = _visibility(rng, n_cam, n_pt, n_obs, window)
+    if street and anchor_range is None:
+        anchor_range = (0, n_cam)
+    ci, pi = _visibility(rng, n_cam, n_pt, n_obs, window, anchor_range=anchor_range if street else None)
     if street:
         # a point sits on the facade opposite the middle of its camera window, 15..40 deep
         first = np.searchsorted(pi, np.arange(n_pt))
@@ -271,12 +278,14 @@ def make_config(name, scale=1.0, model_id=3, shard=None):
     if scale != 1.0:
         n_pt = max(int(n_pt * scale), 16)
         n_obs = max(int(n_obs * scale), 2 * n_pt)
-    point_seed = None
+    point_seed = anchor_range = None
     if shard is not None:
         rank, world = shard
         n_pt, n_obs = n_pt // world, n_obs // world
         point_seed = seed * 7919 + 1 + rank
-    return make_ba_problem(n_cam, n_pt, n_obs, window, seed, model_id, point_seed=point_seed)
+        if window < n_cam:      # street: this rank's points sit along its own arc of the street
+            anchor_range = (rank * n_cam // world, (rank + 1) * n_cam // world)
+    return make_ba_problem(n_cam, n_pt, n_obs, window, seed, model_id, point_seed=point_seed, anchor_range=anchor_range)
 
 
 @dataclass
