@@ -169,7 +169,8 @@ def _visibility(rng, n_cam, n_pt, n_obs, window, kmin=2, anchor_range=None):
     k_p cameras of a point are distinct."""
     W = _prev_prime(min(window, n_cam))
     k = _track_lengths(rng, n_pt, n_obs, min(200, W), kmin)
-    stride = rng.integers(1, W, size=n_pt) if W > 2 else np.ones(n_pt, dtype=np.int64)
+    # strides >= W / 8 keep even two-view tracks at a useful baseline
+    stride = rng.integers(max(1, W // 8), W, size=n_pt) if W > 2 else np.ones(n_pt, dtype=np.int64)
     if anchor_range is None:
         anchor = rng.integers(0, n_cam, size=n_pt)
     else:

@@ -43,6 +43,24 @@ def main():
         ref = t.clone()
         dist.broadcast(ref, src=0)
         assert torch.equal(t, ref), "camera parameters diverged across ranks"
+    # banded (street) problem: most cameras have NO observation on a given rank
+    a = make_ba_problem(400, 6000, 30000, window=24, seed=95)
+    local_t, (p0, p1) = shard_ba(a.camera_params, a.camera_pps, a.points_3d, a.points_2d, a.camera_indices,
+                                 a.point_indices, rank, world)
+    multi = BAEngine(a.model_id, dtype=np.float64, comm=comm, pcg_tol=1e-10, pcg_max_iter=20000)
+    multi.set_problem(*local_t)
+    single = BAEngine(a.model_id, dtype=np.float64, pcg_tol=1e-10, pcg_max_iter=20000)
+    single.set_problem(a.camera_params, a.camera_pps, a.points_3d, a.points_2d, a.camera_indices, a.point_indices)
+    for it in range(6):
+        lm, sm = multi.step()
+        ls, ss = single.step()
+        assert abs(lm - ls) <= 1e-7 * ls, ("street", it, lm, ls, sm, ss)
+    cm, _ = multi.get_params()
+    cs, _ = single.get_params()
+    assert np.abs(cm - cs).max() <= 1e-6 * np.abs(cs).max()
+    rm, qm = multi.cost()
+    rs, qs = single.cost()
+    assert abs(qm - qs) <= 1e-7 * qs, (qm, qs)
     # global positioning
     g = make_gp_problem(16, 500, 2400, seed=93)
     begin = partition_points(point_offsets(g.point_indices, g.points_3d.shape[0]), world)
