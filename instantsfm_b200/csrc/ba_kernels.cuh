@@ -357,7 +357,10 @@ schur_offdiag_kernel(int64_t n_lists, const int32_t* __restrict__ list_order, co
   constexpr int DEPTH = sizeof(T) == 4 ? 4 : 3;   // pairs in flight per list (ring in shared memory)
   constexpr int VE = 16 / sizeof(T);              // elements per 16-byte vector
   constexpr int NVEC = REC / VE;                  // vectors per record
-  __shared__ __align__(16) T ring_all[SCHUR_TPB / 32][GPW][DEPTH][2][REC];
+  // per-list ring [DEPTH][2][REC]; consecutive lists are offset by 4 extra words so that the
+  // broadcast reads of the GPW lists of a warp fall into different banks
+  constexpr int GS = DEPTH * 2 * REC + 4;
+  __shared__ __align__(16) T ring_all[(SCHUR_TPB / 32) * GPW * GS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int grp = lane / LPL, gl = lane % LPL;
   const int c0 = 2 * gl, c1 = min(2 * gl + 1, D - 1);      // the last lane of an odd D repeats column D-1
@@ -372,15 +375,15 @@ schur_offdiag_kernel(int64_t n_lists, const int32_t* __restrict__ list_order, co
   int maxlen = len;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-  T (*ring)[2][REC] = ring_all[w][grp < GPW ? grp : 0];
+  T* ring = ring_all + (size_t)(w * GPW + (grp < GPW ? grp : 0)) * GS;
 
   auto issue = [&](int t) {
     if (t < len) {
       const uint64_t ab = __ldg(pairs + beg + t);
       const T* ra = OBS + (size_t)(uint32_t)(ab >> 32) * REC;
       const T* rb = OBS + (size_t)(uint32_t)ab * REC;
-      T* da = ring[t % DEPTH][0];
-      T* db = ring[t % DEPTH][1];
+      T* da = ring + (t % DEPTH) * 2 * REC;
+      T* db = da + REC;
       for (int v = gl; v < NVEC; v += LPL) { cp_async16(da + v * VE, ra + v * VE); cp_async16(db + v * VE, rb + v * VE); }
     }
     cp_async_commit();   // committed even when empty: every lane keeps the same group count
@@ -396,8 +399,8 @@ schur_offdiag_kernel(int64_t n_lists, const int32_t* __restrict__ list_order, co
     cp_async_wait<DEPTH - 1>();
     __syncwarp();
     if (t < len) {
-      const T* ra = ring[t % DEPTH][0];
-      const T* rb = ring[t % DEPTH][1];
+      const T* ra = ring + (t % DEPTH) * 2 * REC;
+      const T* rb = ra + REC;
       const T* v = ra + OV;
       const T* j = rb + OJP;
       const T m00 = v[0] * j[0] + v[1] * j[1] + v[2] * j[2], m01 = v[0] * j[3] + v[1] * j[4] + v[2] * j[5];
