@@ -93,9 +93,21 @@ pcg_spmv_upper_kernel(int n_units, const int32_t* __restrict__ unit_row, const i
 #pragma unroll
   for (int c = 0; c < D; ++c) pi[c] = p[(size_t)row * D + c];
 
+  // column / deposit indices of stage k for this lane's blocks (-1 where the lane has no block)
+  auto load_idx = [&](int k, int* jj, int* tp) {
+    const int base = beg + k * WB;
+    const int nb = min(WB, end - base);
+#pragma unroll
+    for (int pass = 0; pass < Cfg::PASSES; ++pass) {
+      const int b = pass * GPW + bl;
+      const bool on = k < ns && bl < GPW && b < nb;
+      jj[pass] = on ? __ldg(ucol + base + b) : -1;
+      tp[pass] = on ? __ldg(tpos + base + b) : -1;
+    }
+  };
   // stage k: the blocks (16-byte cp.async, L2 only) and, per block, its p_j (element-wise
   // cp.async) so that the multiply phase reads everything from shared memory
-  auto issue = [&](int k, int* jj, int* tp) {
+  auto issue = [&](int k, const int* jj) {
     const int base = beg + k * WB;
     const int nb = min(WB, end - base);
     const int last = nb * DD / VE - 1;   // indices past the end re-copy the last vector
@@ -104,37 +116,36 @@ pcg_spmv_upper_kernel(int n_units, const int32_t* __restrict__ unit_row, const i
 #pragma unroll
     for (int q = 0; q < NLD; ++q) cp_async16(dst + (size_t)(lane + 32 * q) * VE, src + (size_t)min(lane + 32 * q, last) * VE);
 #pragma unroll
-    for (int pass = 0; pass < Cfg::PASSES; ++pass) {
-      const int b = pass * GPW + bl;
-      const bool on = bl < GPW && b < nb;
-      jj[pass] = on ? ucol[base + b] : -1;
-      tp[pass] = on ? tpos[base + b] : -1;
-      if (on) cp_async_small<sizeof(T)>(dst + Cfg::POFF + b * D + r, p + (size_t)jj[pass] * D + r);
-    }
+    for (int pass = 0; pass < Cfg::PASSES; ++pass)
+      if (jj[pass] >= 0) cp_async_small<sizeof(T)>(dst + Cfg::POFF + (pass * GPW + bl) * D + r, p + (size_t)jj[pass] * D + r);
     cp_async_commit();
   };
 
-  int jj[Cfg::PASSES], tp[Cfg::PASSES], jn[Cfg::PASSES], tn[Cfg::PASSES];
-  issue(0, jj, tp);
+  // software pipeline: indices two stages ahead, data one stage ahead of the multiply
+  int j0[Cfg::PASSES], t0[Cfg::PASSES], j1[Cfg::PASSES], t1[Cfg::PASSES], j2[Cfg::PASSES], t2[Cfg::PASSES];
+  load_idx(0, j0, t0);
+  load_idx(1, j1, t1);
+  issue(0, j0);
   T acc = T(0);
   for (int k = 0; k < ns; ++k) {
-    if (k + 1 < ns) { issue(k + 1, jn, tn); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    load_idx(k + 2, j2, t2);
+    if (k + 1 < ns) { issue(k + 1, j1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncwarp();
     const T* S = buf + (size_t)(k & 1) * STG;
 #pragma unroll
     for (int pass = 0; pass < Cfg::PASSES; ++pass) {
-      if (jj[pass] >= 0) {
+      if (j0[pass] >= 0) {
         const T* B = S + (pass * GPW + bl) * DD;
         const T* pj = S + Cfg::POFF + (pass * GPW + bl) * D;
         T t = T(0);
 #pragma unroll
         for (int c = 0; c < D; ++c) { acc += B[r * D + c] * pj[c]; t += B[c * D + r] * pi[c]; }
-        if (tp[pass] >= 0) C[(size_t)tp[pass] * D + r] = t;
+        if (t0[pass] >= 0) C[(size_t)t0[pass] * D + r] = t;
       }
     }
     __syncwarp();
 #pragma unroll
-    for (int pass = 0; pass < Cfg::PASSES; ++pass) { jj[pass] = jn[pass]; tp[pass] = tn[pass]; }
+    for (int pass = 0; pass < Cfg::PASSES; ++pass) { j0[pass] = j1[pass]; t0[pass] = t1[pass]; j1[pass] = j2[pass]; t1[pass] = t2[pass]; }
   }
   // fold the GPW block lanes onto lanes 0..D-1
 #pragma unroll
