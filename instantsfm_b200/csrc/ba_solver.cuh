@@ -56,6 +56,7 @@ struct BASolver : BASolverBase {
 
   isfm_ba_desc desc;
   cudaStream_t s;
+  cudaStream_t own_stream = nullptr;
   isfm_comm* comm;
   TrustRegionState tr;
   int64_t n_cam = 0, n_pt = 0, n_obs = 0;
@@ -80,6 +81,12 @@ struct BASolver : BASolverBase {
 
   explicit BASolver(const isfm_ba_desc& d) : desc(d) {
     s = static_cast<cudaStream_t>(d.stream);
+    if (s == nullptr) {
+      // the legacy default stream cannot be captured into a CUDA graph: work on an own BLOCKING
+      // stream, which stays implicitly ordered with the caller's legacy-stream work
+      ISFM_CUDA(cudaStreamCreate(&own_stream));
+      s = own_stream;
+    }
     comm = d.comm;
     timers.stream = s;
     tr.init(d.tr_radius, d.tr_max, d.tr_up, d.tr_down);
@@ -88,6 +95,7 @@ struct BASolver : BASolverBase {
   }
   ~BASolver() override {
     cudaStreamSynchronize(s);   // buffers go back to the stream-ordered pool after all work has finished
+    if (own_stream) cudaStreamDestroy(own_stream);
     if (h_scalars) cudaFreeHost(h_scalars);
   }
 
@@ -288,7 +296,7 @@ struct BASolver : BASolverBase {
           ISFM_CUDA(cudaMemcpyAsync(&h_fail, fail.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
           ISFM_CUDA(cudaStreamSynchronize(s));
           fprintf(stderr, "[isfm] pcg status %d (1 converged, 0 max_iter, 2 breakdown) precond_fail_cam %d bb %.6e rho0 %.6e\n",
-                  pcg_status, h_fail - 1, pcg.h_state->bb, pcg.h_state->rho[0]);
+                  pcg_status, h_fail - 1, pcg.h_state->bb, pcg.h_state->rho);
           if (h_fail) {
             const int c = h_fail - 1;
             std::vector<T> hh((size_t)D * D), ee((size_t)D * D + D);

@@ -16,7 +16,9 @@
 namespace isfm {
 
 struct PcgState {
-  double rho[2];   // r.z, double-buffered by iteration parity
+  double rho;      // r.z of the current iteration
+  double rho_next; // r.z computed by the direction kernel, promoted by the next mat-vec tail
+  int has_next;
   double bb;       // ||b||^2
   double rr;       // ||r||^2 after the last completed iteration
   int done;        // 1: converged, 2: breakdown (non-finite / non-positive curvature)
@@ -28,19 +30,24 @@ struct PcgState {
 // The CTA that finishes last sums the per-CTA partials in index order (deterministic) and
 // publishes the scalar: the next kernel reads one double instead of re-reducing n partials in
 // every CTA.  Integer ticket only; no floating-point atomics.
-__device__ __forceinline__ void publish_sum_last_cta(double cta_value, double* partial, unsigned int* ticket, double* out) {
+__device__ __forceinline__ void publish_pq_last_cta(double cta_value, double* partial, PcgState* st) {
   __shared__ bool is_last__;
   if (threadIdx.x == 0) {
     partial[blockIdx.x] = cta_value;
     __threadfence();
-    is_last__ = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    is_last__ = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (is_last__) {
     double v = 0.0;
     for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) v += __ldcg(partial + i);
     v = block_sum(v);
-    if (threadIdx.x == 0) { *out = v; *ticket = 0u; }
+    if (threadIdx.x == 0) {
+      st->pq = v;
+      st->ticket = 0u;
+      // nobody reads rho inside this kernel: promote the value the previous direction kernel left
+      if (st->has_next) { st->rho = st->rho_next; st->has_next = 0; }
+    }
   }
 }
 
@@ -210,7 +217,7 @@ pcg_combine_kernel(const int32_t* __restrict__ lrow_ptr, const int32_t* __restri
 #pragma unroll
       for (int k = 0; k < D; ++k) s += (double)qs[k];
     }
-    publish_sum_last_cta(s, partial, &st->ticket, &st->pq);
+    publish_pq_last_cta(s, partial, st);
   }
 }
 
@@ -236,7 +243,7 @@ pcg_apply_diag_kernel(int n_cam, const T* __restrict__ Hd, const T* __restrict__
     }
   }
   s = block_sum(s);
-  publish_sum_last_cta(s, partial, &st->ticket, &st->pq);
+  publish_pq_last_cta(s, partial, st);
 }
 
 // r0 = b, x0 = 0, z0 = Minv r0, p0 = z0; partials of (r.z, b.b) per camera
@@ -271,7 +278,7 @@ __global__ void pcg_init_state_kernel(int n, const double* __restrict__ part_rz,
   double rz = reduce_partials(part_rz, n);
   double bb = reduce_partials(part_bb, n);
   if (threadIdx.x == 0) {
-    st->rho[0] = rz; st->rho[1] = 0.0; st->bb = bb; st->rr = bb; st->iters = 0; st->pq = 0.0; st->ticket = 0u;
+    st->rho = rz; st->rho_next = 0.0; st->has_next = 0; st->bb = bb; st->rr = bb; st->iters = 0; st->pq = 0.0; st->ticket = 0u;
     st->done = (bb == 0.0) ? 1 : ((isfinite(rz) && isfinite(bb)) ? 0 : 2);
   }
 }
@@ -281,12 +288,12 @@ __global__ void pcg_init_state_kernel(int n, const double* __restrict__ part_rz,
 // D = 9 instead of one thread per camera, which left a 1.8 k-camera system on 14 CTAs.
 template <typename T, int D>
 __global__ void __launch_bounds__(PCG_TPB)
-pcg_update_kernel(int n_cam, int it, const T* __restrict__ Minv, const T* __restrict__ p, const T* __restrict__ q,
+pcg_update_kernel(int n_cam, const T* __restrict__ Minv, const T* __restrict__ p, const T* __restrict__ q,
                   T* __restrict__ x, T* __restrict__ r, T* __restrict__ z, double* __restrict__ part_rz,
                   double* __restrict__ part_rr, const PcgState* __restrict__ st) {
   if (st->done) return;
   constexpr int CPB = PCG_TPB / D;
-  const T alpha = (T)(st->rho[it & 1] / st->pq);
+  const T alpha = (T)(st->rho / st->pq);
   const int cam = blockIdx.x * CPB + threadIdx.x / D, k = threadIdx.x % D;
   const bool on = threadIdx.x < CPB * D && cam < n_cam;
   T rv[D];
@@ -316,20 +323,21 @@ pcg_update_kernel(int n_cam, int it, const T* __restrict__ Minv, const T* __rest
 // beta = rho_new / rho; p = z + beta p (one thread per vector entry); block 0 publishes the new state
 template <typename T, int D>
 __global__ void __launch_bounds__(PCG_TPB)
-pcg_direction_kernel(int n_cam, int n_part, int it, double tol2, const double* __restrict__ part_rz,
+pcg_direction_kernel(int n_cam, int n_part, double tol2, const double* __restrict__ part_rz,
                      const double* __restrict__ part_rr, const T* __restrict__ z, T* __restrict__ p, PcgState* st) {
   if (st->done) return;
   const double rho_new = reduce_partials(part_rz, n_part);
   const double rr = reduce_partials(part_rr, n_part);
-  const double rho = st->rho[it & 1];
+  const double rho = st->rho;
   const T beta = (T)(rho_new / rho);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_cam * D) p[i] = z[i] + beta * p[i];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double pq = st->pq;
-    st->rho[(it + 1) & 1] = rho_new;
+    st->rho_next = rho_new;   // promoted to rho by the next mat-vec tail (other CTAs still read rho here)
+    st->has_next = 1;
     st->rr = rr;
-    st->iters = it + 1;
+    st->iters += 1;
     // `done` is read at kernel entry by every block of the NEXT launch only
     if (!(isfinite(rho_new) && isfinite(rr)) || !(pq > 0.0)) st->done = 2;
     else if (rr < tol2 * st->bb) st->done = 1;
@@ -343,8 +351,14 @@ struct BlockPCG {
   DeviceBuffer<double> part_pq, part_a, part_b;
   DeviceBuffer<PcgState> state;
   PcgState* h_state = nullptr;  // pinned
+  cudaGraphExec_t graph_exec = nullptr;   // captured chunk of PCG iterations (single rank)
+  bool graph_disabled = false;
+  const T* g_E = nullptr; const T* g_Hd = nullptr; const T* g_Minv = nullptr; double g_tol2 = 0.0; int64_t g_units = -1;
 
-  ~BlockPCG() { if (h_state) cudaFreeHost(h_state); }
+  ~BlockPCG() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (h_state) cudaFreeHost(h_state);
+  }
 
   void resize(int n, int64_t n_off, int64_t n_chunks) {
     n_cam = n;
@@ -373,33 +387,65 @@ struct BlockPCG {
       pcg_init_state_kernel<D><<<1, 256, 0, s>>>(n_cam, part_a.get(), part_b.get(), state.get()); }
     const int check_every = 8;
     const double tol2 = tol * tol;
+    auto launch_iteration = [&]() {
+      { TimerScope ts(kt, T_PCG_SPMV);
+        pcg_spmv_upper_kernel<T, D><<<div_up(sp.n_chunks, SpmvCfg<T, D>::NW), PCG_TPB, SpmvCfg<T, D>::SMEM, s>>>(
+            (int)sp.n_chunks, sp.chunk_row.get(), sp.chunk_beg.get(), sp.urow_ptr.get(), sp.ucol.get(), sp.tpos.get(), E,
+            p.get(), yup.get(), C.get(), state.get()); }
+      if (!multi) {
+        TimerScope ts(kt, T_PCG_VEC);
+        pcg_combine_kernel<T, D, true><<<n_cam, PCG_TPB, 0, s>>>(sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(), C.get(), Hd,
+                                                                 p.get(), q.get(), part_pq.get(), state.get());
+      } else {
+        { TimerScope ts(kt, T_PCG_VEC);
+          pcg_combine_kernel<T, D, false><<<n_cam, PCG_TPB, 0, s>>>(sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(), C.get(), Hd,
+                                                                    p.get(), y.get(), part_pq.get(), state.get()); }
+        { TimerScope ts(kt, T_COMM);
+          comm_allreduce_sum(comm, y.get(), (size_t)n_cam * D, sizeof(T) == 8, s); }
+        { TimerScope ts(kt, T_PCG_VEC);
+          pcg_apply_diag_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, Hd, p.get(), y.get(), q.get(), part_pq.get(), state.get()); }
+      }
+      { TimerScope ts(kt, T_PCG_VEC);
+        pcg_update_kernel<T, D><<<nb_upd, PCG_TPB, 0, s>>>(n_cam, Minv, p.get(), q.get(), x.get(), r.get(), z.get(), part_a.get(),
+                                                          part_b.get(), state.get()); }
+      { TimerScope ts(kt, T_PCG_VEC);
+        pcg_direction_kernel<T, D><<<nb_dir, PCG_TPB, 0, s>>>(n_cam, nb_upd, tol2, part_a.get(), part_b.get(), z.get(), p.get(),
+                                                             state.get()); }
+    };
+    // Single rank, no per-kernel timing: a chunk of `check_every` iterations (identical launches --
+    // the iteration state lives on the device) is captured once in a CUDA graph and replayed.
+    bool use_graph = !multi && !kt.enabled && !graph_disabled && !getenv("ISFM_NO_GRAPH");
+    if (use_graph && !(graph_exec && g_E == E && g_Hd == Hd && g_Minv == Minv && g_tol2 == tol2 && g_units == sp.n_chunks)) {
+      if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      const int64_t lc = g_launch_count;
+      int64_t saved[ISFM_N_TIMERS];
+      for (int i = 0; i < ISFM_N_TIMERS; ++i) saved[i] = kt.launches[i];
+      bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        for (int k = 0; k < check_every; ++k) launch_iteration();
+        ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && graph != nullptr;
+      }
+      if (ok) ok = cudaGraphInstantiate(&graph_exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      if (!ok) { graph_exec = nullptr; graph_disabled = true; cudaGetLastError(); }   // e.g. legacy default stream: plain launches
+      g_launch_count = lc;                       // captured, not executed
+      for (int i = 0; i < ISFM_N_TIMERS; ++i) kt.launches[i] = saved[i];
+      g_E = E; g_Hd = Hd; g_Minv = Minv; g_tol2 = tol2; g_units = sp.n_chunks;
+      use_graph = graph_exec != nullptr;
+    }
     int it = 0;
     h_state->done = 0; h_state->iters = 0;
     while (it < max_iter) {
-      int chunk = std::min(check_every, max_iter - it);
-      for (int k = 0; k < chunk; ++k, ++it) {
-        { TimerScope ts(kt, T_PCG_SPMV);
-          pcg_spmv_upper_kernel<T, D><<<div_up(sp.n_chunks, SpmvCfg<T, D>::NW), PCG_TPB, SpmvCfg<T, D>::SMEM, s>>>(
-              (int)sp.n_chunks, sp.chunk_row.get(), sp.chunk_beg.get(), sp.urow_ptr.get(), sp.ucol.get(),
-                                                                           sp.tpos.get(), E, p.get(), yup.get(), C.get(), state.get()); }
-        if (!multi) {
-          TimerScope ts(kt, T_PCG_VEC);
-          pcg_combine_kernel<T, D, true><<<n_cam, PCG_TPB, 0, s>>>(sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(), C.get(), Hd, p.get(), q.get(), part_pq.get(), state.get());
-        } else {
-          { TimerScope ts(kt, T_PCG_VEC);
-            pcg_combine_kernel<T, D, false><<<n_cam, PCG_TPB, 0, s>>>(sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(), C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get()); }
-          { TimerScope ts(kt, T_COMM);
-            comm_allreduce_sum(comm, y.get(), (size_t)n_cam * D, sizeof(T) == 8, s); }
-          { TimerScope ts(kt, T_PCG_VEC);
-            pcg_apply_diag_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, Hd, p.get(), y.get(), q.get(), part_pq.get(), state.get()); }
-        }
-        { TimerScope ts(kt, T_PCG_VEC);
-          pcg_update_kernel<T, D><<<nb_upd, PCG_TPB, 0, s>>>(n_cam, it, Minv, p.get(), q.get(), x.get(), r.get(), z.get(),
-                                                            part_a.get(), part_b.get(), state.get()); }
-        { TimerScope ts(kt, T_PCG_VEC);
-          pcg_direction_kernel<T, D><<<nb_dir, PCG_TPB, 0, s>>>(n_cam, nb_upd, it, tol2, part_a.get(), part_b.get(), z.get(),
-                                                               p.get(), state.get()); }
+      const int chunk = std::min(check_every, max_iter - it);
+      if (use_graph && chunk == check_every) {
+        ISFM_CUDA(cudaGraphLaunch(graph_exec, s));
+        g_launch_count += 4 * check_every;
+        kt.launches[T_PCG_SPMV] += check_every; kt.launches[T_PCG_VEC] += 3 * check_every;
+      } else {
+        for (int k = 0; k < chunk; ++k) launch_iteration();
       }
+      it += chunk;
       ISFM_CUDA(cudaMemcpyAsync(h_state, state.get(), sizeof(PcgState), cudaMemcpyDeviceToHost, s));
       ISFM_CUDA(cudaStreamSynchronize(s));
       if (h_state->done) break;
