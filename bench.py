@@ -42,6 +42,10 @@ def emit(line):
 METRIC = "ba_lm_observations_per_sec"
 UNIT = "obs/s"
 CPU_SAMPLE_SCALE = 0.02   # cpu_baseline: config with points/observations scaled by this factor
+# dram__bytes_read.sum + dram__bytes_write.sum per launch on config C3 (1 GPU, full size), from the
+# `ncu --set full` captures summarised in profiles/r1_ncu_full_summary.txt (ncu cannot run inside the bench)
+NCU_TRAFFIC_C3 = {"pcg_spmv": 578.9e6, "schur_offdiag": 2888.7e6, "linearize": 798.6e6, "camera_blocks": 783.9e6,
+                  "backsub": 801.9e6}
 
 
 def _peaks():
@@ -249,7 +253,9 @@ def main_ours(args):
                          "achieved_gbs": (ab / (per_launch_ms * 1e-3) / 1e9) if ab and per_launch_ms > 0 else None}
     top = max((k for k in kernels if kernels[k]["achieved_gbs"] is not None), key=lambda k: kernels[k]["ms_per_step"])
     roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[top]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": kernels[top]["achieved_gbs"] / peak,
+                "traffic": NCU_TRAFFIC_C3.get(top) if (args.config == "C3" and world == 1 and args.scale == 1.0) else None,
+                "traffic_source": "profiles/r1_ncu_full_summary.txt (bytes per launch)", "peak_source": peak_src,
                 "share_of_step": kernels[top]["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values())}
     # ---- end to end through the C ABI from pinned host buffers ---------------------------
     # three complete solves (create, set_problem = H2D of every tensor + sort + Schur pattern,
