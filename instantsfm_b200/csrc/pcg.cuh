@@ -65,7 +65,7 @@ template <typename T, int D> struct SpmvCfg {
   static constexpr int NW = PCG_TPB / 32;                            // warps = work units per CTA
   static constexpr int GPW = 32 / D;                                 // blocks per warp pass
   // blocks per stage: a multiple of 4 (16-byte alignment of every stage source)
-  static constexpr int WB = sizeof(T) == 4 ? GPW * 4 : (GPW * 2 + 3) / 4 * 4;
+  static constexpr int WB = sizeof(T) == 4 ? GPW * 4 : (GPW * 2 + 3) / 4 * 4;   // (8-block stages measured slower)
   static constexpr int PASSES = (WB + GPW - 1) / GPW;
   static constexpr int VE = 16 / sizeof(T);                          // elements per 16-byte vector
   static constexpr int NV = WB * D * D / VE;                         // vectors per stage
