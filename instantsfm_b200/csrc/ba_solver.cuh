@@ -153,7 +153,7 @@ struct BASolver : BASolverBase {
       TimerScope ts(timers, T_COMM);
       comm_allreduce_sum(comm, scalars.get(), 3, true, s);
     }
-    ISFM_CUDA(cudaMemcpyAsync(h_scalars, scalars.get(), 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ISFM_CUDA(cudaMemcpyAsync(h_scalars, scalars.get(), 4 * sizeof(double), cudaMemcpyDeviceToHost, s));   // [3]: ||D_c||^2
     ISFM_CUDA(cudaStreamSynchronize(s));
   }
 
@@ -315,6 +315,9 @@ struct BASolver : BASolverBase {
         { TimerScope ts(timers, T_UPDATE);
           camera_update_kernel<T, NI><<<div_up(n_cam, 128), 128, 0, s>>>((int)n_cam, cam[cur].get(), pcg.x.get(),
                                                                         cam[trial].get(), pcg.part_a.get()); }
+        // ||D_c||^2 of this trial (identical on every rank: not all-reduced), fetched with the trial scalars
+        { TimerScope ts(timers, T_REDUCE);
+          reduce_scalars_kernel<<<1, 256, 0, s>>>(pcg.part_a.get(), nullptr, nullptr, div_up(n_cam, 128), 0, 0, scalars.get() + 3); }
       } else {
         TimerScope ts(timers, T_BACKSUB);
         mterm_parts = red_grid(n_pt);
@@ -353,14 +356,7 @@ struct BASolver : BASolverBase {
     stats.rejects = rejects;
     stats.loss = loss;
     stats.damping = tr.damping;
-    if (desc.optimize_poses) {
-      // ||D_c|| of the last trial, from the per-block partials of camera_update_kernel
-      { TimerScope ts(timers, T_REDUCE);
-        reduce_scalars_kernel<<<1, 256, 0, s>>>(pcg.part_a.get(), nullptr, nullptr, div_up(n_cam, 128), 0, 0, scalars.get() + 3); }
-      ISFM_CUDA(cudaMemcpyAsync(h_scalars + 3, scalars.get() + 3, sizeof(double), cudaMemcpyDeviceToHost, s));
-      ISFM_CUDA(cudaStreamSynchronize(s));
-      stats.step_norm_cam = std::sqrt(h_scalars[3]);
-    }
+    if (desc.optimize_poses) stats.step_norm_cam = std::sqrt(h_scalars[3]);   // last trial
     ISFM_CUDA(cudaGetLastError());
     if (loss_out) *loss_out = loss;
     if (st) *st = stats;

@@ -25,6 +25,8 @@ struct PcgState {
   int iters;
   double pq;       // p.q of the current iteration (published by the last CTA of the mat-vec tail)
   unsigned int ticket;
+  unsigned int ticket2;   // last-CTA election of the merged update / direction kernel
+  int max_iter;
 };
 
 // The CTA that finishes last sums the per-CTA partials in index order (deterministic) and
@@ -99,6 +101,9 @@ pcg_spmv_upper_kernel(int n_units, const int32_t* __restrict__ unit_row, const i
   T pi[D];
 #pragma unroll
   for (int c = 0; c < D; ++c) pi[c] = p[(size_t)row * D + c];
+  // E is streamed once per mat-vec (evict_first); the deposits are read back by the combine
+  // kernel right after and fit the L2 (evict_last): they need not travel to HBM and back
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
 
   // column / deposit indices of stage k for this lane's blocks (-1 where the lane has no block)
   auto load_idx = [&](int k, int* jj, int* tp) {
@@ -121,7 +126,7 @@ pcg_spmv_upper_kernel(int n_units, const int32_t* __restrict__ unit_row, const i
     const T* src = EU + (size_t)base * DD;
     T* dst = buf + (size_t)(k & 1) * STG;
 #pragma unroll
-    for (int q = 0; q < NLD; ++q) cp_async16(dst + (size_t)(lane + 32 * q) * VE, src + (size_t)min(lane + 32 * q, last) * VE);
+    for (int q = 0; q < NLD; ++q) cp_async16_hint(dst + (size_t)(lane + 32 * q) * VE, src + (size_t)min(lane + 32 * q, last) * VE, pol_stream);
 #pragma unroll
     for (int pass = 0; pass < Cfg::PASSES; ++pass)
       if (jj[pass] >= 0) cp_async_small<sizeof(T)>(dst + Cfg::POFF + (pass * GPW + bl) * D + r, p + (size_t)jj[pass] * D + r);
@@ -147,7 +152,7 @@ pcg_spmv_upper_kernel(int n_units, const int32_t* __restrict__ unit_row, const i
         T t = T(0);
 #pragma unroll
         for (int c = 0; c < D; ++c) { acc += B[r * D + c] * pj[c]; t += B[c * D + r] * pi[c]; }
-        if (t0[pass] >= 0) C[(size_t)t0[pass] * D + r] = t;
+        if (t0[pass] >= 0) st_global_hint(C + (size_t)t0[pass] * D + r, t, pol_keep);
       }
     }
     __syncwarp();
@@ -160,62 +165,75 @@ pcg_spmv_upper_kernel(int n_units, const int32_t* __restrict__ unit_row, const i
     T o = __shfl_sync(0xffffffffu, acc, (lane + k * D) & 31);
     if (lane < D) acc += o;
   }
-  if (lane < D) yup_part[(size_t)unit * D + lane] = acc;
+  if (lane < D) st_global_hint(yup_part + (size_t)unit * D + lane, acc, pol_keep);
 }
 
 // y_i = sum of row i's chunk partials + sum of the deposits of row i (contiguous in C).
-// FUSED (single rank): q_i = Hd_i p_i - y_i and the per-row partial of p.q; otherwise y is
-// written for the all-reduce.
+// FUSED (single rank): q_i = Hd_i p_i - y_i and the per-CTA partial of p.q; otherwise y is
+// written for the all-reduce.  Row i of the lower triangle holds up to i deposits, so a CTA takes
+// the two rows b and n-1-b: every CTA of a dense system sums the same number of deposits (no
+// tail of long rows), with eight independent loads in flight per thread.
+constexpr int COMB_TPB = 256;
+
 template <typename T, int D, bool FUSED>
-__global__ void __launch_bounds__(PCG_TPB)
-pcg_combine_kernel(const int32_t* __restrict__ lrow_ptr, const int32_t* __restrict__ chunk_ptr,
+__global__ void __launch_bounds__(COMB_TPB)
+pcg_combine_kernel(int n_cam, const int32_t* __restrict__ lrow_ptr, const int32_t* __restrict__ chunk_ptr,
                    const T* __restrict__ yup_part, const T* __restrict__ C, const T* __restrict__ Hd,
                    const T* __restrict__ p, T* __restrict__ out, double* __restrict__ partial,
                    PcgState* __restrict__ st) {
   if (st->done) return;
-  constexpr int G = PCG_TPB / D;   // entry groups per CTA; threads >= G * D idle
+  constexpr int G = COMB_TPB / D;   // entry groups per CTA; threads >= G * D idle
+  constexpr int MLP = 8;
   __shared__ T sh[G][D];
-  __shared__ T qs[D];
-  const int row = blockIdx.x;
+  __shared__ T qs[2][D];
   const int g = threadIdx.x / D, c = threadIdx.x % D;
-  T acc = T(0);
-  if (g < G) {
-    for (int k = chunk_ptr[row] + g; k < chunk_ptr[row + 1]; k += G) acc += yup_part[(size_t)k * D + c];
-    const int beg = lrow_ptr[row], end = lrow_ptr[row + 1];
-    int k = beg + g;
-    // four independent loads in flight per thread (rows of a dense system hold ~n_cam deposits)
-    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
-    for (; k + 3 * G < end; k += 4 * G) {
-      a0 += C[(size_t)k * D + c]; a1 += C[(size_t)(k + G) * D + c];
-      a2 += C[(size_t)(k + 2 * G) * D + c]; a3 += C[(size_t)(k + 3 * G) * D + c];
-    }
-    for (; k < end; k += G) a0 += C[(size_t)k * D + c];
-    acc += (a0 + a1) + (a2 + a3);
-    sh[g][c] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x < D) {
-    T y = T(0);
-    for (int k = 0; k < G; ++k) y += sh[k][threadIdx.x];
-    if (FUSED) {
-      const T* __restrict__ h = Hd + (size_t)row * (D * D) + threadIdx.x * D;
-      const T* __restrict__ pi = p + (size_t)row * D;
-      T q = T(0);
+  int halves = 1;
+  for (int half = 0; half < 2; ++half) {
+    const int row = half == 0 ? (int)blockIdx.x : n_cam - 1 - (int)blockIdx.x;
+    if (half == 1 && row <= (int)blockIdx.x) break;   // middle row of an odd system: once
+    halves = half + 1;
+    if (g < G) {
+      T acc = T(0);
+      for (int k = chunk_ptr[row] + g; k < chunk_ptr[row + 1]; k += G) acc += yup_part[(size_t)k * D + c];
+      const int end = lrow_ptr[row + 1];
+      int k = lrow_ptr[row] + g;
+      T a[MLP];
 #pragma unroll
-      for (int k = 0; k < D; ++k) q += h[k] * pi[k];
-      q -= y;
-      out[(size_t)row * D + threadIdx.x] = q;
-      qs[threadIdx.x] = q * pi[threadIdx.x];
-    } else {
-      out[(size_t)row * D + threadIdx.x] = y;
+      for (int u = 0; u < MLP; ++u) a[u] = T(0);
+      for (; k + (MLP - 1) * G < end; k += MLP * G) {
+#pragma unroll
+        for (int u = 0; u < MLP; ++u) a[u] += __ldcs(C + (size_t)(k + u * G) * D + c);
+      }
+      for (; k < end; k += G) a[0] += __ldcs(C + (size_t)k * D + c);
+#pragma unroll
+      for (int u = 1; u < MLP; ++u) a[0] += a[u];
+      sh[g][c] = acc + a[0];
     }
+    __syncthreads();
+    if (threadIdx.x < D) {
+      T y = T(0);
+      for (int k = 0; k < G; ++k) y += sh[k][threadIdx.x];
+      if (FUSED) {
+        const T* __restrict__ h = Hd + (size_t)row * (D * D) + threadIdx.x * D;
+        const T* __restrict__ pi = p + (size_t)row * D;
+        T q = T(0);
+#pragma unroll
+        for (int k = 0; k < D; ++k) q += h[k] * pi[k];
+        q -= y;
+        out[(size_t)row * D + threadIdx.x] = q;
+        qs[half][threadIdx.x] = q * pi[threadIdx.x];
+      } else {
+        out[(size_t)row * D + threadIdx.x] = y;
+      }
+    }
+    __syncthreads();   // sh is reused by the second row; qs complete
   }
   if (FUSED) {
-    __syncthreads();
     double s = 0.0;
     if (threadIdx.x == 0) {
+      for (int h = 0; h < halves; ++h)
 #pragma unroll
-      for (int k = 0; k < D; ++k) s += (double)qs[k];
+        for (int k = 0; k < D; ++k) s += (double)qs[h][k];
     }
     publish_pq_last_cta(s, partial, st);
   }
@@ -273,27 +291,54 @@ __global__ void pcg_init_kernel(int n_cam, const T* __restrict__ b, const T* __r
 }
 
 template <int D>
-__global__ void pcg_init_state_kernel(int n, const double* __restrict__ part_rz, const double* __restrict__ part_bb,
-                                      PcgState* st) {
+__global__ void pcg_init_state_kernel(int n, int max_iter, const double* __restrict__ part_rz,
+                                      const double* __restrict__ part_bb, PcgState* st) {
   double rz = reduce_partials(part_rz, n);
   double bb = reduce_partials(part_bb, n);
   if (threadIdx.x == 0) {
-    st->rho = rz; st->rho_next = 0.0; st->has_next = 0; st->bb = bb; st->rr = bb; st->iters = 0; st->pq = 0.0; st->ticket = 0u;
+    st->rho = rz; st->rho_next = 0.0; st->has_next = 0; st->bb = bb; st->rr = bb; st->iters = 0; st->pq = 0.0;
+    st->ticket = 0u; st->ticket2 = 0u; st->max_iter = max_iter;
     st->done = (bb == 0.0) ? 1 : ((isfinite(rz) && isfinite(bb)) ? 0 : 2);
   }
 }
 
+// End-of-iteration bookkeeping (one thread): new state, convergence test, and -- inside the
+// device-side WHILE graph -- the loop condition of the conditional node.
+__device__ __forceinline__ void pcg_finish_iteration(PcgState* st, double rho_new, double rr, double tol2, bool promote_now,
+                                                     cudaGraphConditionalHandle cond, int use_cond) {
+  const double pq = st->pq;
+  if (promote_now) { st->rho = rho_new; st->has_next = 0; }
+  else { st->rho_next = rho_new; st->has_next = 1; }   // promoted by the next mat-vec tail (other CTAs still read rho)
+  st->rr = rr;
+  const int it = st->iters + 1;
+  st->iters = it;
+  int done = 0;
+  // `done` is read at kernel entry by every block of the NEXT launch only
+  if (!(isfinite(rho_new) && isfinite(rr)) || !(pq > 0.0)) done = 2;
+  else if (rr < tol2 * st->bb) done = 1;
+  if (done) st->done = done;
+  if (use_cond) cudaGraphSetConditional(cond, (!done && it < st->max_iter) ? 1u : 0u);
+}
+
 // alpha = rho / (p.q); x += alpha p; r -= alpha q; z = Minv r; partials of r.z and r.r.
-// D threads per camera (thread k owns component k and row k of Minv): 14 cameras per CTA at
-// D = 9 instead of one thread per camera, which left a 1.8 k-camera system on 14 CTAs.
-template <typename T, int D>
-__global__ void __launch_bounds__(PCG_TPB)
-pcg_update_kernel(int n_cam, const T* __restrict__ Minv, const T* __restrict__ p, const T* __restrict__ q,
+// D threads per camera (thread k owns component k and row k of Minv).
+// MERGED (small systems, where launches dominate): the CTA that finishes last also computes
+// beta = rho_new / rho, the new direction p = z + beta p for the whole vector and the iteration
+// state -- one launch less per iteration.  Otherwise pcg_direction_kernel follows.
+constexpr int UPD_TPB = 128;
+
+template <typename T, int D, bool MERGED>
+__global__ void __launch_bounds__(UPD_TPB)
+pcg_update_kernel(int n_cam, double tol2, const T* __restrict__ Minv, T* __restrict__ p, const T* __restrict__ q,
                   T* __restrict__ x, T* __restrict__ r, T* __restrict__ z, double* __restrict__ part_rz,
-                  double* __restrict__ part_rr, const PcgState* __restrict__ st) {
-  if (st->done) return;
-  constexpr int CPB = PCG_TPB / D;
-  const T alpha = (T)(st->rho / st->pq);
+                  double* __restrict__ part_rr, PcgState* __restrict__ st, cudaGraphConditionalHandle cond, int use_cond) {
+  if (st->done) {
+    if (MERGED && use_cond && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(cond, 0u);
+    return;
+  }
+  constexpr int CPB = UPD_TPB / D;
+  const double rho = st->rho;
+  const T alpha = (T)(rho / st->pq);
   const int cam = blockIdx.x * CPB + threadIdx.x / D, k = threadIdx.x % D;
   const bool on = threadIdx.x < CPB * D && cam < n_cam;
   T rv[D];
@@ -317,31 +362,52 @@ pcg_update_kernel(int n_cam, const T* __restrict__ Minv, const T* __restrict__ p
   }
   rz = block_sum(rz);
   rr = block_sum(rr);
-  if (threadIdx.x == 0) { part_rz[blockIdx.x] = rz; part_rr[blockIdx.x] = rr; }
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    part_rz[blockIdx.x] = rz; part_rr[blockIdx.x] = rr;
+    if (MERGED) {
+      __threadfence();
+      is_last = atomicAdd(&st->ticket2, 1u) == gridDim.x - 1;
+    }
+  }
+  if (!MERGED) return;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += UPD_TPB) { a += __ldcg(part_rz + i); b += __ldcg(part_rr + i); }
+  a = block_sum(a);
+  b = block_sum(b);
+  __shared__ double rho_new_sh;
+  if (threadIdx.x == 0) rho_new_sh = a;
+  __syncthreads();
+  const T beta = (T)(rho_new_sh / rho);
+  const int n = n_cam * D;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n; i += UPD_TPB) p[i] = __ldcg(z + i) + beta * p[i];
+  if (threadIdx.x == 0) {
+    st->ticket2 = 0u;
+    pcg_finish_iteration(st, a, b, tol2, true, cond, use_cond);
+  }
 }
 
 // beta = rho_new / rho; p = z + beta p (one thread per vector entry); block 0 publishes the new state
 template <typename T, int D>
 __global__ void __launch_bounds__(PCG_TPB)
 pcg_direction_kernel(int n_cam, int n_part, double tol2, const double* __restrict__ part_rz,
-                     const double* __restrict__ part_rr, const T* __restrict__ z, T* __restrict__ p, PcgState* st) {
-  if (st->done) return;
+                     const double* __restrict__ part_rr, const T* __restrict__ z, T* __restrict__ p, PcgState* st,
+                     cudaGraphConditionalHandle cond, int use_cond) {
+  if (st->done) {
+    if (use_cond && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(cond, 0u);
+    return;
+  }
   const double rho_new = reduce_partials(part_rz, n_part);
   const double rr = reduce_partials(part_rr, n_part);
   const double rho = st->rho;
   const T beta = (T)(rho_new / rho);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_cam * D) p[i] = z[i] + beta * p[i];
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const double pq = st->pq;
-    st->rho_next = rho_new;   // promoted to rho by the next mat-vec tail (other CTAs still read rho here)
-    st->has_next = 1;
-    st->rr = rr;
-    st->iters += 1;
-    // `done` is read at kernel entry by every block of the NEXT launch only
-    if (!(isfinite(rho_new) && isfinite(rr)) || !(pq > 0.0)) st->done = 2;
-    else if (rr < tol2 * st->bb) st->done = 1;
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) pcg_finish_iteration(st, rho_new, rr, tol2, false, cond, use_cond);
 }
 
 template <typename T, int D>
@@ -351,7 +417,10 @@ struct BlockPCG {
   DeviceBuffer<double> part_pq, part_a, part_b;
   DeviceBuffer<PcgState> state;
   PcgState* h_state = nullptr;  // pinned
-  cudaGraphExec_t graph_exec = nullptr;   // captured chunk of PCG iterations (single rank)
+  // The whole iteration loop of a single-rank solve is ONE graph launch: a conditional WHILE node
+  // whose body holds the kernels of one iteration; the last kernel sets the loop condition on the
+  // device (converged / breakdown / max_iter), so the host neither polls nor re-launches.
+  cudaGraphExec_t graph_exec = nullptr;
   bool graph_disabled = false;
   const T* g_E = nullptr; const T* g_Hd = nullptr; const T* g_Minv = nullptr; double g_tol2 = 0.0; int64_t g_units = -1;
 
@@ -371,6 +440,7 @@ struct BlockPCG {
     ISFM_CUDA(cudaFuncSetAttribute(pcg_spmv_upper_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)SpmvCfg<T, D>::SMEM));
     if (!h_state) ISFM_CUDA(cudaMallocHost(&h_state, sizeof(PcgState)));
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
   }
 
   // Solves S x = b.  Returns iterations; result in x.  status: 1 converged, 0 hit max_iter,
@@ -379,76 +449,101 @@ struct BlockPCG {
             const T* Hd, const T* Minv, const T* b, double tol, int max_iter, isfm_comm* comm, cudaStream_t s,
             KernelTimers& kt, int* status_out) {
     const int nb = div_up(n_cam, PCG_TPB);
-    const int nb_upd = div_up(n_cam, PCG_TPB / D), nb_dir = div_up((int64_t)n_cam * D, PCG_TPB);
+    const int nb_upd = div_up(n_cam, UPD_TPB / D), nb_dir = div_up((int64_t)n_cam * D, PCG_TPB);
+    const int nb_comb = (n_cam + 1) / 2;
     const bool multi = comm_world(comm) > 1;
+    const bool merged = (int64_t)n_cam * D <= 4096;   // the last CTA of the update kernel also builds p
     { TimerScope ts(kt, T_PCG_VEC);
       pcg_init_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, b, Minv, x.get(), r.get(), p.get(), part_a.get(), part_b.get()); }
     { TimerScope ts(kt, T_PCG_VEC);
-      pcg_init_state_kernel<D><<<1, 256, 0, s>>>(n_cam, part_a.get(), part_b.get(), state.get()); }
-    const int check_every = 8;
+      pcg_init_state_kernel<D><<<1, 256, 0, s>>>(n_cam, max_iter, part_a.get(), part_b.get(), state.get()); }
     const double tol2 = tol * tol;
-    auto launch_iteration = [&]() {
+    auto launch_iteration = [&](cudaGraphConditionalHandle cond, int use_cond) {
       { TimerScope ts(kt, T_PCG_SPMV);
         pcg_spmv_upper_kernel<T, D><<<div_up(sp.n_chunks, SpmvCfg<T, D>::NW), PCG_TPB, SpmvCfg<T, D>::SMEM, s>>>(
             (int)sp.n_chunks, sp.chunk_row.get(), sp.chunk_beg.get(), sp.urow_ptr.get(), sp.ucol.get(), sp.tpos.get(), E,
             p.get(), yup.get(), C.get(), state.get()); }
       if (!multi) {
         TimerScope ts(kt, T_PCG_VEC);
-        pcg_combine_kernel<T, D, true><<<n_cam, PCG_TPB, 0, s>>>(sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(), C.get(), Hd,
-                                                                 p.get(), q.get(), part_pq.get(), state.get());
+        pcg_combine_kernel<T, D, true><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(),
+                                                                   C.get(), Hd, p.get(), q.get(), part_pq.get(), state.get());
       } else {
         { TimerScope ts(kt, T_PCG_VEC);
-          pcg_combine_kernel<T, D, false><<<n_cam, PCG_TPB, 0, s>>>(sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(), C.get(), Hd,
-                                                                    p.get(), y.get(), part_pq.get(), state.get()); }
+          pcg_combine_kernel<T, D, false><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(),
+                                                                      C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get()); }
         { TimerScope ts(kt, T_COMM);
           comm_allreduce_sum(comm, y.get(), (size_t)n_cam * D, sizeof(T) == 8, s); }
         { TimerScope ts(kt, T_PCG_VEC);
           pcg_apply_diag_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, Hd, p.get(), y.get(), q.get(), part_pq.get(), state.get()); }
       }
-      { TimerScope ts(kt, T_PCG_VEC);
-        pcg_update_kernel<T, D><<<nb_upd, PCG_TPB, 0, s>>>(n_cam, Minv, p.get(), q.get(), x.get(), r.get(), z.get(), part_a.get(),
-                                                          part_b.get(), state.get()); }
-      { TimerScope ts(kt, T_PCG_VEC);
-        pcg_direction_kernel<T, D><<<nb_dir, PCG_TPB, 0, s>>>(n_cam, nb_upd, tol2, part_a.get(), part_b.get(), z.get(), p.get(),
-                                                             state.get()); }
+      if (merged) {
+        TimerScope ts(kt, T_PCG_VEC);
+        pcg_update_kernel<T, D, true><<<nb_upd, UPD_TPB, 0, s>>>(n_cam, tol2, Minv, p.get(), q.get(), x.get(), r.get(), z.get(),
+                                                                part_a.get(), part_b.get(), state.get(), cond, use_cond);
+      } else {
+        { TimerScope ts(kt, T_PCG_VEC);
+          pcg_update_kernel<T, D, false><<<nb_upd, UPD_TPB, 0, s>>>(n_cam, tol2, Minv, p.get(), q.get(), x.get(), r.get(), z.get(),
+                                                                   part_a.get(), part_b.get(), state.get(), cond, 0); }
+        { TimerScope ts(kt, T_PCG_VEC);
+          pcg_direction_kernel<T, D><<<nb_dir, PCG_TPB, 0, s>>>(n_cam, nb_upd, tol2, part_a.get(), part_b.get(), z.get(), p.get(),
+                                                               state.get(), cond, use_cond); }
+      }
     };
-    // Single rank, no per-kernel timing: a chunk of `check_every` iterations (identical launches --
-    // the iteration state lives on the device) is captured once in a CUDA graph and replayed.
+    const int vec_per_iter = merged ? 2 : 3;
+    // Single rank, no per-kernel timing: device-side WHILE graph.
     bool use_graph = !multi && !kt.enabled && !graph_disabled && !getenv("ISFM_NO_GRAPH");
     if (use_graph && !(graph_exec && g_E == E && g_Hd == Hd && g_Minv == Minv && g_tol2 == tol2 && g_units == sp.n_chunks)) {
       if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
-      cudaGraph_t graph = nullptr;
       const int64_t lc = g_launch_count;
       int64_t saved[ISFM_N_TIMERS];
       for (int i = 0; i < ISFM_N_TIMERS; ++i) saved[i] = kt.launches[i];
-      bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      cudaGraph_t graph = nullptr;
+      cudaGraphConditionalHandle cond = 0;
+      bool ok = cudaGraphCreate(&graph, 0) == cudaSuccess;
+      if (ok) ok = cudaGraphConditionalHandleCreate(&cond, graph, 1u, cudaGraphCondAssignDefault) == cudaSuccess;
+      cudaGraphNode_t node = nullptr;
+      cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+      np.type = cudaGraphNodeTypeConditional;
+      np.conditional.handle = cond;
+      np.conditional.type = cudaGraphCondTypeWhile;
+      np.conditional.size = 1;
+      if (ok) ok = cudaGraphAddNode(&node, graph, nullptr, 0, &np) == cudaSuccess;
       if (ok) {
-        for (int k = 0; k < check_every; ++k) launch_iteration();
-        ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && graph != nullptr;
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        ok = cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          launch_iteration(cond, 1);
+          cudaGraph_t same = nullptr;
+          ok = cudaStreamEndCapture(s, &same) == cudaSuccess;
+        }
       }
       if (ok) ok = cudaGraphInstantiate(&graph_exec, graph, 0) == cudaSuccess;
       if (graph) cudaGraphDestroy(graph);
-      if (!ok) { graph_exec = nullptr; graph_disabled = true; cudaGetLastError(); }   // e.g. legacy default stream: plain launches
+      if (!ok) { graph_exec = nullptr; graph_disabled = true; cudaGetLastError(); }   // plain launches + host polling instead
       g_launch_count = lc;                       // captured, not executed
       for (int i = 0; i < ISFM_N_TIMERS; ++i) kt.launches[i] = saved[i];
       g_E = E; g_Hd = Hd; g_Minv = Minv; g_tol2 = tol2; g_units = sp.n_chunks;
       use_graph = graph_exec != nullptr;
     }
-    int it = 0;
     h_state->done = 0; h_state->iters = 0;
-    while (it < max_iter) {
-      const int chunk = std::min(check_every, max_iter - it);
-      if (use_graph && chunk == check_every) {
-        ISFM_CUDA(cudaGraphLaunch(graph_exec, s));
-        g_launch_count += 4 * check_every;
-        kt.launches[T_PCG_SPMV] += check_every; kt.launches[T_PCG_VEC] += 3 * check_every;
-      } else {
-        for (int k = 0; k < chunk; ++k) launch_iteration();
-      }
-      it += chunk;
+    if (use_graph) {
+      ISFM_CUDA(cudaGraphLaunch(graph_exec, s));
       ISFM_CUDA(cudaMemcpyAsync(h_state, state.get(), sizeof(PcgState), cudaMemcpyDeviceToHost, s));
       ISFM_CUDA(cudaStreamSynchronize(s));
-      if (h_state->done) break;
+      const int it = h_state->iters;
+      g_launch_count += (int64_t)(1 + vec_per_iter) * it;
+      kt.launches[T_PCG_SPMV] += it; kt.launches[T_PCG_VEC] += (int64_t)vec_per_iter * it;
+    } else {
+      const int check_every = 8;
+      int it = 0;
+      while (it < max_iter) {
+        const int chunk = std::min(check_every, max_iter - it);
+        for (int k = 0; k < chunk; ++k) launch_iteration(0, 0);
+        it += chunk;
+        ISFM_CUDA(cudaMemcpyAsync(h_state, state.get(), sizeof(PcgState), cudaMemcpyDeviceToHost, s));
+        ISFM_CUDA(cudaStreamSynchronize(s));
+        if (h_state->done) break;
+      }
     }
     ISFM_CUDA(cudaGetLastError());
     if (status_out) *status_out = h_state->done;
