@@ -70,12 +70,37 @@ __device__ __forceinline__ void load_quads(const T* __restrict__ rec, T* dst) {
   }
 }
 
+// Packed camera table read by the per-observation kernels: row = [t, q, intrinsics | pp | pad],
+// a multiple of four elements, so that a camera is gathered with ceil((CW + 2) / 4) 128-bit loads
+// instead of CW + 2 scalar ones (the gathers are random over all cameras on wide-baseline scenes).
+template <int CW> struct CamPack { static constexpr int CWP = (CW + 2 + 3) / 4 * 4; };
+
+template <typename T, int CW>
+__device__ __forceinline__ void load_camera(const T* __restrict__ camq, int c, T* cr, T* ppv) {
+  constexpr int CWP = CamPack<CW>::CWP;
+  T q[CWP];
+#pragma unroll
+  for (int i = 0; i < CWP / 4; ++i) QuadIO<T>::ldg(camq + (size_t)c * CWP + 4 * i, q + 4 * i);
+#pragma unroll
+  for (int i = 0; i < CW; ++i) cr[i] = q[i];
+  ppv[0] = q[CW]; ppv[1] = q[CW + 1];
+}
+
+template <typename T, int CW>
+__global__ void pack_cameras_kernel(int n_cam, const T* __restrict__ cam, const T* __restrict__ pp, T* __restrict__ camq) {
+  constexpr int CWP = CamPack<CW>::CWP;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cam * CWP) return;
+  const int c = i / CWP, k = i % CWP;
+  camq[i] = k < CW ? cam[(size_t)c * CW + k] : (k < CW + 2 ? pp[2 * (size_t)c + (k - CW)] : T(0));
+}
+
 // ---------------------------------------------------------------------------------------
 // K1: residual + Huber weight + Jacobian blocks per observation; cost partials per block.
 // ---------------------------------------------------------------------------------------
 template <typename T, int MODEL>
 __global__ void __launch_bounds__(BA_TPB)
-linearize_kernel(int64_t n_obs, const T* __restrict__ cam, const T* __restrict__ pp, const T* __restrict__ pts,
+linearize_kernel(int64_t n_obs, const T* __restrict__ camq, const T* __restrict__ pts,
                  const T* __restrict__ obs, const int32_t* __restrict__ cam_of, const int32_t* __restrict__ pt_of,
                  T delta, T* __restrict__ R, T* __restrict__ OBS,
                  double* __restrict__ part_rho, double* __restrict__ part_sq) {
@@ -88,9 +113,7 @@ linearize_kernel(int64_t n_obs, const T* __restrict__ cam, const T* __restrict__
   for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < n_obs; a += (int64_t)gridDim.x * blockDim.x) {
     const int c = cam_of[a], p = pt_of[a];
     T cr[CW], ppv[2], X[3], o[2], r[2], rec[4 * NQ];
-#pragma unroll
-    for (int i = 0; i < CW; ++i) cr[i] = __ldg(cam + (size_t)c * CW + i);
-    ppv[0] = __ldg(pp + 2 * (size_t)c); ppv[1] = __ldg(pp + 2 * (size_t)c + 1);
+    load_camera<T, CW>(camq, c, cr, ppv);
 #pragma unroll
     for (int i = 0; i < 3; ++i) X[i] = __ldg(pts + 3 * (size_t)p + i);
     o[0] = obs[2 * a]; o[1] = obs[2 * a + 1];
@@ -115,7 +138,7 @@ linearize_kernel(int64_t n_obs, const T* __restrict__ cam, const T* __restrict__
 // trial cost: residual only
 template <typename T, int MODEL>
 __global__ void __launch_bounds__(BA_TPB)
-cost_kernel(int64_t n_obs, const T* __restrict__ cam, const T* __restrict__ pp, const T* __restrict__ pts,
+cost_kernel(int64_t n_obs, const T* __restrict__ camq, const T* __restrict__ pts,
             const T* __restrict__ obs, const int32_t* __restrict__ cam_of, const int32_t* __restrict__ pt_of,
             T delta, double* __restrict__ part_rho, double* __restrict__ part_sq) {
   constexpr int NI = ModelTraits<MODEL>::NI;
@@ -124,9 +147,7 @@ cost_kernel(int64_t n_obs, const T* __restrict__ cam, const T* __restrict__ pp, 
   for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < n_obs; a += (int64_t)gridDim.x * blockDim.x) {
     const int c = cam_of[a], p = pt_of[a];
     T cr[CW], ppv[2], X[3], o[2], r[2];
-#pragma unroll
-    for (int i = 0; i < CW; ++i) cr[i] = __ldg(cam + (size_t)c * CW + i);
-    ppv[0] = __ldg(pp + 2 * (size_t)c); ppv[1] = __ldg(pp + 2 * (size_t)c + 1);
+    load_camera<T, CW>(camq, c, cr, ppv);
 #pragma unroll
     for (int i = 0; i < 3; ++i) X[i] = __ldg(pts + 3 * (size_t)p + i);
     o[0] = obs[2 * a]; o[1] = obs[2 * a + 1];
@@ -142,15 +163,16 @@ cost_kernel(int64_t n_obs, const T* __restrict__ cam, const T* __restrict__ pp, 
 
 // unweighted residuals (debug / parity)
 template <typename T, int MODEL>
-__global__ void residual_kernel(int64_t n_obs, const T* __restrict__ cam, const T* __restrict__ pp,
+__global__ void residual_kernel(int64_t n_obs, const T* __restrict__ camq,
                                 const T* __restrict__ pts, const T* __restrict__ obs,
                                 const int32_t* __restrict__ cam_of, const int32_t* __restrict__ pt_of, T* __restrict__ out) {
   constexpr int NI = ModelTraits<MODEL>::NI;
   constexpr int CW = 7 + NI;
   int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (a >= n_obs) return;
-  ba_residual<MODEL, T>(cam + (size_t)cam_of[a] * CW, pp + 2 * (size_t)cam_of[a], pts + 3 * (size_t)pt_of[a], obs + 2 * a,
-                        out + 2 * a);
+  T cr[CW], ppv[2];
+  load_camera<T, CW>(camq, cam_of[a], cr, ppv);
+  ba_residual<MODEL, T>(cr, ppv, pts + 3 * (size_t)pt_of[a], obs + 2 * a, out + 2 * a);
 }
 
 // out[k] = sum of partials k (one block per output scalar)
@@ -517,9 +539,9 @@ backsub_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const int32_t* 
 
 // x <- x (+) D for cameras: Exp(D[:6]) * pose, intrinsics += D[6:]   (bae update_parameter)
 template <typename T, int NI>
-__global__ void camera_update_kernel(int n_cam, const T* __restrict__ cam, const T* __restrict__ DC, T* __restrict__ cam_trial,
-                                     double* __restrict__ part_norm) {
-  constexpr int D = 6 + NI, CW = 7 + NI;
+__global__ void camera_update_kernel(int n_cam, const T* __restrict__ cam, const T* __restrict__ pp, const T* __restrict__ DC,
+                                     T* __restrict__ cam_trial, T* __restrict__ camq_trial, double* __restrict__ part_norm) {
+  constexpr int D = 6 + NI, CW = 7 + NI, CWP = CamPack<CW>::CWP;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double nrm = 0.0;
   if (i < n_cam) {
@@ -532,7 +554,10 @@ __global__ void camera_update_kernel(int n_cam, const T* __restrict__ cam, const
 #pragma unroll
     for (int k = 0; k < NI; ++k) out[7 + k] = in[7 + k] + d[6 + k];
 #pragma unroll
-    for (int k = 0; k < CW; ++k) cam_trial[(size_t)i * CW + k] = out[k];
+    for (int k = 0; k < CW; ++k) { cam_trial[(size_t)i * CW + k] = out[k]; camq_trial[(size_t)i * CWP + k] = out[k]; }
+    camq_trial[(size_t)i * CWP + CW] = pp[2 * (size_t)i]; camq_trial[(size_t)i * CWP + CW + 1] = pp[2 * (size_t)i + 1];
+#pragma unroll
+    for (int k = CW + 2; k < CWP; ++k) camq_trial[(size_t)i * CWP + k] = T(0);
   }
   nrm = block_sum(nrm);
   if (threadIdx.x == 0) part_norm[blockIdx.x] = nrm;
@@ -552,114 +577,165 @@ __global__ void camera_update_kernel(int n_cam, const T* __restrict__ cam, const
 // Replaces linearize_kernel + point_solve_kernel<BUILD> when no track exceeds FUSED_TPB
 // observations; rejected trials re-damp with point_solve_kernel<false>.
 // ---------------------------------------------------------------------------------------
-constexpr int FUSED_TPB = 256;
+#ifndef ISFM_FUSED_TPB
+#define ISFM_FUSED_TPB 256
+#endif
+constexpr int FUSED_TPB = ISFM_FUSED_TPB;
+// phase-ablation switches of the timing harness (tools/kbench.cu); compiled out of the library
+#ifdef ISFM_KBENCH
+#define ISFM_ABL(bit) ((dbg & (bit)) != 0)
+#else
+#define ISFM_ABL(bit) false
+#endif
 template <typename T, int D> struct FusedCfg {
   static constexpr int REC = ObsRec<D>::REC;
   static constexpr int QR = REC / 4;            // quads per record
-  static constexpr int SQ = QR | 1;             // staged row stride in quads (odd)
-  static constexpr size_t SMEM = (size_t)FUSED_TPB * SQ * 4 * sizeof(T) + (size_t)FUSED_TPB * 6 * sizeof(T);
+  static constexpr int QV = ObsRec<D>::V / 4;   // quads [0, QV): Jc | Jp only (staged); [QV, QR): end of Jp, V, padding
+  // staged row: the record's QR quads + three quads of contributions to Hpp (6) and g_p (3); odd stride
+  static constexpr int QC = QR;                 // first contribution quad
+  static constexpr int SQ = (QR + 3) | 1;
+  static constexpr size_t SMEM = (size_t)FUSED_TPB * SQ * 4 * sizeof(T);
 };
 
 template <typename T, int MODEL>
-__global__ void __launch_bounds__(FUSED_TPB, sizeof(T) == 4 ? 4 : 1)
-fused_linearize_kernel(const int32_t* __restrict__ cta_pt, const int32_t* __restrict__ pt_off,
-                       const T* __restrict__ cam, const T* __restrict__ pp, const T* __restrict__ pts,
+__global__ void __launch_bounds__(FUSED_TPB, sizeof(T) == 4 ? 4 * (256 / FUSED_TPB) : 1)
+fused_linearize_kernel(const int4* __restrict__ tiles, const int32_t* __restrict__ pt_off,
+                       const T* __restrict__ camq, const T* __restrict__ pts,
                        const T* __restrict__ obs, const int32_t* __restrict__ cam_of, const int32_t* __restrict__ pt_of,
                        T delta, T mu, T* __restrict__ R, T* __restrict__ OBS, T* __restrict__ HPP, T* __restrict__ GPT,
                        T* __restrict__ HPPINV, T* __restrict__ TP, double* __restrict__ part_rho,
-                       double* __restrict__ part_sq) {
+                       double* __restrict__ part_sq, int want_cost, int dbg) {
   constexpr int NI = ModelTraits<MODEL>::NI;
   constexpr int D = 6 + NI;
   constexpr int CW = 7 + NI;
   typedef FusedCfg<T, D> Cfg;
   constexpr int REC = Cfg::REC, QR = Cfg::QR, SQ = Cfg::SQ, OJP = ObsRec<D>::JP, OV = ObsRec<D>::V;
+  constexpr int QV = Cfg::QV, QC = Cfg::QC;
   extern __shared__ __align__(16) unsigned char fused_smem[];
-  T* stage = reinterpret_cast<T*>(fused_smem);                 // [FUSED_TPB][SQ * 4]; first used as contrib[FUSED_TPB][9]
-  T* hinv = stage + (size_t)FUSED_TPB * SQ * 4;                // [FUSED_TPB][6]
+  T* stage = reinterpret_cast<T*>(fused_smem);                 // [FUSED_TPB][SQ * 4]
   const int t = threadIdx.x;
-  const int p0 = cta_pt[blockIdx.x], p1 = cta_pt[blockIdx.x + 1];
-  const int o0 = pt_off[p0], n = pt_off[p1] - o0;
-  const int64_t a = (int64_t)o0 + t;
-  T rec[REC];
-  T rw0 = T(0), rw1 = T(0);
-  int lp = 0;
   double rho_d = 0.0, sq_d = 0.0;
+  const int4 tile = __ldg(tiles + blockIdx.x);   // {first point, end point, first observation, observations}
+  const int o0 = tile.z, n = tile.w;
+  const int64_t a = (int64_t)o0 + t;
+  T* srow = stage + (size_t)t * SQ * 4;
+  // a point without observations (possible in caller data) has no thread below: write its blocks here
+  if (t < tile.y - tile.x) {
+    const int pz = tile.x + t;
+    if (pt_off[pz + 1] == pt_off[pz]) {
+      const T dinv = T(1) / damp_diag(T(0), mu);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { HPP[(size_t)pz * 6 + i] = T(0); HPPINV[(size_t)pz * 6 + i] = (i == 0 || i == 3 || i == 5) ? dinv : T(0); }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { GPT[(size_t)pz * 3 + i] = T(0); TP[(size_t)pz * 3 + i] = T(0); }
+    }
+  }
+  T tail[REC - 4 * QV];          // record elements [4 QV, REC): the end of Jp, V, padding
+  int p = 0, kb = 0, ke = 0;
   if (t < n) {
-    const int c = cam_of[a], p = pt_of[a];
-    lp = p - p0;
-    T cr[CW], ppv[2], X[3], o[2], r[2];
+    int c = cam_of[a];
+    p = pt_of[a];
+    kb = pt_off[p] - o0; ke = pt_off[p + 1] - o0;
+    if (ISFM_ABL(8)) { c = t & 7; }
+    const int pg = ISFM_ABL(8) ? (t & 15) : p;
+    T cr[CW], ppv[2], X[3], o[2], r[2], rec[REC];
+    load_camera<T, CW>(camq, c, cr, ppv);
 #pragma unroll
-    for (int i = 0; i < CW; ++i) cr[i] = __ldg(cam + (size_t)c * CW + i);
-    ppv[0] = __ldg(pp + 2 * (size_t)c); ppv[1] = __ldg(pp + 2 * (size_t)c + 1);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) X[i] = __ldg(pts + 3 * (size_t)p + i);
+    for (int i = 0; i < 3; ++i) X[i] = __ldg(pts + 3 * (size_t)pg + i);
     o[0] = obs[2 * a]; o[1] = obs[2 * a + 1];
+    if (ISFM_ABL(4)) {
+#pragma unroll
+      for (int i = 0; i < REC; ++i) rec[i] = cr[i % CW] + X[i % 3] + o[i & 1] + ppv[i & 1];
+      r[0] = rec[0]; r[1] = rec[1];
+    } else
     ba_linearize<MODEL, T>(cr, ppv, X, o, r, rec, rec + OJP);
     T s = r[0] * r[0] + r[1] * r[1], rho, w;
     huber(s, delta, rho, w);
-    rho_d = (double)rho; sq_d = (double)s;
-    rw0 = w * r[0]; rw1 = w * r[1];
+    rho_d += (double)rho; sq_d += (double)s;
+    const T rw0 = w * r[0], rw1 = w * r[1];
 #pragma unroll
     for (int i = 0; i < 2 * D + 6; ++i) rec[i] *= w;
 #pragma unroll
-    for (int i = OV + 6; i < REC; ++i) rec[i] = T(0);
+    for (int i = OV; i < REC; ++i) rec[i] = T(0);
     const T* j = rec + OJP;
-    T* cb = stage + (size_t)t * 9;
+    T cb[12];
     cb[0] = j[0] * j[0] + j[3] * j[3]; cb[1] = j[0] * j[1] + j[3] * j[4]; cb[2] = j[0] * j[2] + j[3] * j[5];
     cb[3] = j[1] * j[1] + j[4] * j[4]; cb[4] = j[1] * j[2] + j[4] * j[5]; cb[5] = j[2] * j[2] + j[5] * j[5];
     cb[6] = j[0] * rw0 + j[3] * rw1; cb[7] = j[1] * rw0 + j[4] * rw1; cb[8] = j[2] * rw0 + j[5] * rw1;
-    R[2 * a] = rw0; R[2 * a + 1] = rw1;
+    cb[9] = cb[10] = cb[11] = T(0);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) QuadIO<T>::st(srow + 4 * (QC + q), cb + 4 * q);
+    if (!ISFM_ABL(32)) { R[2 * a] = rw0; R[2 * a + 1] = rw1; }
+    // Jc and the quads fully covered by Jp leave the registers now; only the tail stays live
+#pragma unroll
+    for (int q = 0; q < QV; ++q) QuadIO<T>::st(srow + 4 * q, rec + 4 * q);
+#pragma unroll
+    for (int i = 0; i < REC - 4 * QV; ++i) tail[i] = rec[4 * QV + i];
   }
-  __syncthreads();
-  // one thread per point (measured faster than letting each point's first observation thread do
-  // it: the point threads then fill two warps densely instead of diverging all eight)
-  if (t < p1 - p0) {
-    const int p = p0 + t;
-    const int kb = pt_off[p] - o0, ke = pt_off[p + 1] - o0;
+  __syncthreads();   // staged Jc | Jp quads and contributions are complete
+  // Every observation thread sums the contributions of its own point (same order in every thread:
+  // bit-identical, and no serial phase on a quarter of the warps), inverts the damped 3x3 block and
+  // forms V = Jp Hpp^-1; the thread of the point's first observation stores the point arrays.
+  if (t < n && !ISFM_ABL(2)) {
     T h[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
     for (int k = kb; k < ke; ++k) {
-      const T* cb = stage + (size_t)k * 9;
+      T cb[12];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) QuadIO<T>::ld(stage + ((size_t)k * SQ + QC + q) * 4, cb + 4 * q);
 #pragma unroll
       for (int i = 0; i < 6; ++i) h[i] += cb[i];
       g[0] += cb[6]; g[1] += cb[7]; g[2] += cb[8];
     }
+    const bool head = t == kb && !ISFM_ABL(32);
+    if (head) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) HPP[(size_t)p * 6 + i] = h[i];
+      for (int i = 0; i < 6; ++i) HPP[(size_t)p * 6 + i] = h[i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) GPT[(size_t)p * 3 + i] = g[i];
+      for (int i = 0; i < 3; ++i) GPT[(size_t)p * 3 + i] = g[i];
+    }
     h[0] = damp_diag(h[0], mu); h[3] = damp_diag(h[3], mu); h[5] = damp_diag(h[5], mu);
     T iv[6];
     sym3_inverse(h, iv);
+    if (head) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { HPPINV[(size_t)p * 6 + i] = iv[i]; hinv[t * 6 + i] = iv[i]; }
-    TP[(size_t)p * 3 + 0] = iv[0] * g[0] + iv[1] * g[1] + iv[2] * g[2];
-    TP[(size_t)p * 3 + 1] = iv[1] * g[0] + iv[3] * g[1] + iv[4] * g[2];
-    TP[(size_t)p * 3 + 2] = iv[2] * g[0] + iv[4] * g[1] + iv[5] * g[2];
-  }
-  __syncthreads();   // contributions consumed: the stage area is reused for the records
-  if (t < n) {
-    const T* iv = hinv + lp * 6;
-    const T* j = rec + OJP;
-    T* v = rec + OV;
+      for (int i = 0; i < 6; ++i) HPPINV[(size_t)p * 6 + i] = iv[i];
+      TP[(size_t)p * 3 + 0] = iv[0] * g[0] + iv[1] * g[1] + iv[2] * g[2];
+      TP[(size_t)p * 3 + 1] = iv[1] * g[0] + iv[3] * g[1] + iv[4] * g[2];
+      TP[(size_t)p * 3 + 2] = iv[2] * g[0] + iv[4] * g[1] + iv[5] * g[2];
+    }
+    // Jp: elements [OJP, OJP + 6) of the record; those below 4 QV were staged, re-read them
+    T jp[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) jp[i] = (OJP + i >= 4 * QV) ? tail[OJP + i - 4 * QV] : srow[OJP + i];
 #pragma unroll
     for (int row = 0; row < 2; ++row) {
-      T a0 = j[3 * row], a1 = j[3 * row + 1], a2 = j[3 * row + 2];
-      v[3 * row + 0] = a0 * iv[0] + a1 * iv[1] + a2 * iv[2];
-      v[3 * row + 1] = a0 * iv[1] + a1 * iv[3] + a2 * iv[4];
-      v[3 * row + 2] = a0 * iv[2] + a1 * iv[4] + a2 * iv[5];
+      T a0 = jp[3 * row], a1 = jp[3 * row + 1], a2 = jp[3 * row + 2];
+      tail[OV - 4 * QV + 3 * row + 0] = a0 * iv[0] + a1 * iv[1] + a2 * iv[2];
+      tail[OV - 4 * QV + 3 * row + 1] = a0 * iv[1] + a1 * iv[3] + a2 * iv[4];
+      tail[OV - 4 * QV + 3 * row + 2] = a0 * iv[2] + a1 * iv[4] + a2 * iv[5];
     }
-    T* srow = stage + (size_t)t * SQ * 4;
 #pragma unroll
-    for (int q = 0; q < QR; ++q) QuadIO<T>::st(srow + 4 * q, rec + 4 * q);
+    for (int q = QV; q < QR; ++q) QuadIO<T>::st(srow + 4 * q, tail + 4 * (q - QV));
   }
   __syncthreads();
-  // coalesced write of the CTA's slab: quad i of the slab = record i / QR, quad i % QR
-  T* dst = OBS + (size_t)o0 * REC;
-  for (int i = t; i < n * QR; i += FUSED_TPB) {
-    T q4[4];
-    QuadIO<T>::ld(stage + ((size_t)(i / QR) * SQ + (i % QR)) * 4, q4);
-    QuadIO<T>::st(dst + (size_t)i * 4, q4);
+  // coalesced write of the CTA's slab: slab quad i = record i / QR, quad i % QR (n <= FUSED_TPB
+  // records = at most QR rounds; a thread's shared-memory loads all precede its stores)
+  if (!ISFM_ABL(1)) {
+    T* dst = OBS + (size_t)o0 * REC;
+    T q4[QR][4];
+#pragma unroll
+    for (int u = 0; u < QR; ++u) {
+      const int i = t + u * FUSED_TPB;
+      if (i < n * QR) QuadIO<T>::ld(stage + ((size_t)(i / QR) * SQ + (i % QR)) * 4, q4[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < QR; ++u) {
+      const int i = t + u * FUSED_TPB;
+      if (i < n * QR) QuadIO<T>::st(dst + (size_t)i * 4, q4[u]);
+    }
   }
+  // cost partials: wanted on the first LM step only (later steps carry the accepted trial cost)
+  if (!want_cost || ISFM_ABL(16)) return;
   rho_d = block_sum(rho_d);
   sq_d = block_sum(sq_d);
   if (t == 0) { part_rho[blockIdx.x] = rho_d; part_sq[blockIdx.x] = sq_d; }

@@ -62,7 +62,8 @@ struct BASolver : BASolverBase {
   int64_t n_cam = 0, n_pt = 0, n_obs = 0;
   ObsIndex ix;
   SchurPattern sp;
-  DeviceBuffer<T> cam[2], pts[2], pp, obs;
+  DeviceBuffer<T> cam[2], camq[2], pts[2], pp, obs;   // camq: packed [cam row | pp | pad] rows read by the kernels
+  static constexpr int CWP = CamPack<CW>::CWP;
   static constexpr int REC = ObsRec<D>::REC;
   DeviceBuffer<T> R, OBS, HPP, GPT, HPPINV, TP, DP;
   DeviceBuffer<T> HCC_GC, HD, E, EG, RED, MINV, bvec;  // HCC_GC = [HCC | GC | cost] packed for one all-reduce
@@ -75,8 +76,8 @@ struct BASolver : BASolverBase {
   double loss = 0.0;
   double mu_last = 1.0;
   bool fused_ok = false;      // every track fits one CTA of the fused K1 (<= FUSED_TPB observations)
-  int n_fused_cta = 0;
-  DeviceBuffer<int32_t> fused_cta_pt;
+  int n_fused_cta = 0;        // tiles of whole points with <= FUSED_TPB observations
+  DeviceBuffer<int4> fused_tiles;   // {first point, end point, first observation, observations} per CTA
   double min_damping = 0.0;   // floor on the LM damping used to build the systems (see DESIGN.md, fp32 conditioning)
 
   explicit BASolver(const isfm_ba_desc& d) : desc(d) {
@@ -115,6 +116,8 @@ struct BASolver : BASolverBase {
     upload(cam[0], cam_in, (size_t)nc * CW); cam[1].alloc((size_t)nc * CW);
     upload(pts[0], pts_in, (size_t)np * 3); pts[1].alloc((size_t)np * 3);
     upload(pp, pp_in, (size_t)nc * 2);
+    camq[0].alloc((size_t)nc * CWP); camq[1].alloc((size_t)nc * CWP);
+    pack_cameras(0);
     DeviceBuffer<T> obs_raw; DeviceBuffer<int32_t> ci, pi;
     upload(obs_raw, obs_in, (size_t)no * 2);
     upload(ci, cam_idx, (size_t)no); upload(pi, pt_idx, (size_t)no);
@@ -143,6 +146,11 @@ struct BASolver : BASolverBase {
     tr.init(desc.tr_radius, desc.tr_max, desc.tr_up, desc.tr_down);
   }
 
+  void pack_cameras(int which) {
+    TimerScope ts(timers, T_MISC);
+    pack_cameras_kernel<T, CW><<<div_up(n_cam * CWP, 256), 256, 0, s>>>((int)n_cam, cam[which].get(), pp.get(), camq[which].get());
+  }
+
   int red_grid(int64_t n) const { return (int)std::min<int64_t>(RED_BLOCKS, div_up(n, BA_TPB)); }
 
   // reduce up to three partial arrays to scalars, all-reduce them, copy to the host
@@ -160,18 +168,18 @@ struct BASolver : BASolverBase {
   void run_linearize() {
     const int g = red_grid(n_obs);
     TimerScope ts(timers, T_LINEARIZE);
-    linearize_kernel<T, MODEL><<<g, BA_TPB, 0, s>>>(n_obs, cam[cur].get(), pp.get(), pts[cur].get(), obs.get(),
+    linearize_kernel<T, MODEL><<<g, BA_TPB, 0, s>>>(n_obs, camq[cur].get(), pts[cur].get(), obs.get(),
                                                     ix.cam_of.get(), ix.pt_of.get(), (T)desc.huber_delta, R.get(), OBS.get(),
                                                     part_a.get(), part_b.get());
   }
 
   // fused K1 + point solve of the first trial; returns the number of cost partials
-  int run_fused_linearize(T mu) {
+  int run_fused_linearize(T mu, bool want_cost) {
     TimerScope ts(timers, T_LINEARIZE);
     fused_linearize_kernel<T, MODEL><<<n_fused_cta, FUSED_TPB, FusedCfg<T, D>::SMEM, s>>>(
-        fused_cta_pt.get(), ix.pt_off.get(), cam[cur].get(), pp.get(), pts[cur].get(), obs.get(), ix.cam_of.get(),
+        fused_tiles.get(), ix.pt_off.get(), camq[cur].get(), pts[cur].get(), obs.get(), ix.cam_of.get(),
         ix.pt_of.get(), (T)desc.huber_delta, mu, R.get(), OBS.get(), HPP.get(), GPT.get(), HPPINV.get(), TP.get(),
-        part_a.get(), part_b.get());
+        part_a.get(), part_b.get(), want_cost ? 1 : 0, 0);
     return n_fused_cta;
   }
 
@@ -190,8 +198,10 @@ struct BASolver : BASolverBase {
     cta.push_back((int32_t)n_pt);
     if (!fused_ok) return;
     n_fused_cta = (int)cta.size() - 1;
-    fused_cta_pt.alloc(cta.size());
-    ISFM_CUDA(cudaMemcpyAsync(fused_cta_pt.get(), cta.data(), cta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    std::vector<int4> tiles((size_t)n_fused_cta);
+    for (int i = 0; i < n_fused_cta; ++i) tiles[i] = make_int4(cta[i], cta[i + 1], off[cta[i]], off[cta[i + 1]] - off[cta[i]]);
+    fused_tiles.alloc(tiles.size());
+    ISFM_CUDA(cudaMemcpyAsync(fused_tiles.get(), tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
     ISFM_CUDA(cudaStreamSynchronize(s));
     ISFM_CUDA(cudaFuncSetAttribute(fused_linearize_kernel<T, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)FusedCfg<T, D>::SMEM));
@@ -200,7 +210,7 @@ struct BASolver : BASolverBase {
   void run_cost(int which, double* robust, double* sq) {
     const int g = red_grid(n_obs);
     { TimerScope ts(timers, T_COST);
-      cost_kernel<T, MODEL><<<g, BA_TPB, 0, s>>>(n_obs, cam[which].get(), pp.get(), pts[which].get(), obs.get(),
+      cost_kernel<T, MODEL><<<g, BA_TPB, 0, s>>>(n_obs, camq[which].get(), pts[which].get(), obs.get(),
                                                  ix.cam_of.get(), ix.pt_of.get(), (T)desc.huber_delta, part_a.get(),
                                                  part_b.get()); }
     fetch_scalars(part_a.get(), g, part_b.get(), g, nullptr, 0, true);
@@ -264,7 +274,7 @@ struct BASolver : BASolverBase {
     const double mu_cap = sizeof(T) == 4 ? 1e24 : 1e100;
     const double mu_first = std::min(1.0 + std::max(tr.damping, min_damping), mu_cap);
     int lin_parts;
-    if (fused_ok) lin_parts = run_fused_linearize((T)mu_first);
+    if (fused_ok) lin_parts = run_fused_linearize((T)mu_first, !have_loss);
     else { run_linearize(); lin_parts = red_grid(n_obs); }
     if (!have_loss) {
       const int g = lin_parts;
@@ -313,8 +323,8 @@ struct BASolver : BASolverBase {
                                                              GPT.get(), HPP.get(), HPPINV.get(), pcg.x.get(), pts[cur].get(),
                                                              pts[trial].get(), DP.get(), part_c.get()); }
         { TimerScope ts(timers, T_UPDATE);
-          camera_update_kernel<T, NI><<<div_up(n_cam, 128), 128, 0, s>>>((int)n_cam, cam[cur].get(), pcg.x.get(),
-                                                                        cam[trial].get(), pcg.part_a.get()); }
+          camera_update_kernel<T, NI><<<div_up(n_cam, 128), 128, 0, s>>>((int)n_cam, cam[cur].get(), pp.get(), pcg.x.get(),
+                                                                        cam[trial].get(), camq[trial].get(), pcg.part_a.get()); }
         // ||D_c||^2 of this trial (identical on every rank: not all-reduced), fetched with the trial scalars
         { TimerScope ts(timers, T_REDUCE);
           reduce_scalars_kernel<<<1, 256, 0, s>>>(pcg.part_a.get(), nullptr, nullptr, div_up(n_cam, 128), 0, 0, scalars.get() + 3); }
@@ -324,10 +334,11 @@ struct BASolver : BASolverBase {
         point_only_step_kernel<T, D><<<mterm_parts, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), OBS.get(), R.get(), TP.get(),
                                                                  pts[cur].get(), pts[trial].get(), DP.get(), part_c.get());
         ISFM_CUDA(cudaMemcpyAsync(cam[trial].get(), cam[cur].get(), (size_t)n_cam * CW * sizeof(T), cudaMemcpyDeviceToDevice, s));
+        ISFM_CUDA(cudaMemcpyAsync(camq[trial].get(), camq[cur].get(), (size_t)n_cam * CWP * sizeof(T), cudaMemcpyDeviceToDevice, s));
       }
       const int g = red_grid(n_obs);
       { TimerScope ts(timers, T_COST);
-        cost_kernel<T, MODEL><<<g, BA_TPB, 0, s>>>(n_obs, cam[trial].get(), pp.get(), pts[trial].get(), obs.get(),
+        cost_kernel<T, MODEL><<<g, BA_TPB, 0, s>>>(n_obs, camq[trial].get(), pts[trial].get(), obs.get(),
                                                    ix.cam_of.get(), ix.pt_of.get(), (T)desc.huber_delta, part_a.get(),
                                                    part_b.get()); }
       // scalars: [0] new robust cost, [1] plain squared cost, [2] model term (summed over ranks)
@@ -371,7 +382,10 @@ struct BASolver : BASolverBase {
 
   void set_params(const void* cam_in, const void* pts_in) override {
     ISFM_REQUIRE(has_problem, ISFM_ESTATE, "no problem set");
-    if (cam_in) ISFM_CUDA(cudaMemcpyAsync(cam[cur].get(), cam_in, (size_t)n_cam * CW * sizeof(T), cudaMemcpyDefault, s));
+    if (cam_in) {
+      ISFM_CUDA(cudaMemcpyAsync(cam[cur].get(), cam_in, (size_t)n_cam * CW * sizeof(T), cudaMemcpyDefault, s));
+      pack_cameras(cur);
+    }
     if (pts_in) ISFM_CUDA(cudaMemcpyAsync(pts[cur].get(), pts_in, (size_t)n_pt * 3 * sizeof(T), cudaMemcpyDefault, s));
     ISFM_CUDA(cudaStreamSynchronize(s));
     have_loss = false;
@@ -450,7 +464,7 @@ struct BASolver : BASolverBase {
     }
     if (what == ISFM_BA_RESIDUALS) {
       DeviceBuffer<T> tmp; tmp.alloc((size_t)n_obs * 2);
-      residual_kernel<T, MODEL><<<div_up(n_obs, BA_TPB), BA_TPB, 0, s>>>(n_obs, cam[cur].get(), pp.get(), pts[cur].get(),
+      residual_kernel<T, MODEL><<<div_up(n_obs, BA_TPB), BA_TPB, 0, s>>>(n_obs, camq[cur].get(), pts[cur].get(),
                                                                        obs.get(), ix.cam_of.get(), ix.pt_of.get(), tmp.get());
       unsort_rows(tmp.get(), 2, 0, 2, dst);
       return;

@@ -292,10 +292,13 @@ template <typename T> ISFM_HD T damp_diag(T d, T mu) {
 // inverse of a symmetric 3x3 given as (xx xy xz yy yz zz); computed in double on the matrix
 // scaled by its largest diagonal entry (no overflow of the determinant under heavy damping).
 template <typename T> ISFM_HD void sym3_inverse(const T h[6], T inv[6]) {
-  double s = (double)h[0];
-  if ((double)h[3] > s) s = (double)h[3];
-  if ((double)h[5] > s) s = (double)h[5];
-  const double is = s > 0.0 ? 1.0 / s : 1.0;
+  double is = 1.0;
+  if (sizeof(T) == 8) {   // float entries (<= 1e32 * 1e24) cannot overflow a double determinant: no scaling needed
+    double s = (double)h[0];
+    if ((double)h[3] > s) s = (double)h[3];
+    if ((double)h[5] > s) s = (double)h[5];
+    is = s > 0.0 ? 1.0 / s : 1.0;
+  }
   double a = h[0] * is, b = h[1] * is, c = h[2] * is, d = h[3] * is, e = h[4] * is, f = h[5] * is;
   double A = d * f - e * e, Bc = c * e - b * f, Cc = b * e - c * d;
   double det = a * A + b * Bc + c * Cc;
