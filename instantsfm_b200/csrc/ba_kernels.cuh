@@ -59,6 +59,11 @@ template <> struct QuadIO<double> {
     *reinterpret_cast<double2*>(p + 2) = make_double2(d[2], d[3]);
   }
 };
+// asynchronous global -> shared copy of one quad (L2 only)
+template <typename T> __device__ __forceinline__ void cp_async_quad(T* smem_dst, const T* gmem_src) {
+  cp_async16(smem_dst, gmem_src);
+  if (sizeof(T) == 8) cp_async16(smem_dst + 2, gmem_src + 2);
+}
 // loads quads [Q0, Q1) of a record into dst[0 .. 4 (Q1 - Q0)); element e of the record is
 // dst[e - 4 Q0].  READONLY selects the non-coherent path.
 template <typename T, int Q0, int Q1, bool READONLY>
@@ -739,6 +744,109 @@ fused_linearize_kernel(const int4* __restrict__ tiles, const int32_t* __restrict
   rho_d = block_sum(rho_d);
   sq_d = block_sum(sq_d);
   if (t == 0) { part_rho[blockIdx.x] = rho_d; part_sq[blockIdx.x] = sq_d; }
+}
+
+// ---------------------------------------------------------------------------------------
+// K5 on the tiles of the fused K1 (whole points, <= FUSED_TPB observations per CTA), one thread
+// per observation.  The thread-per-point sweep of backsub_kernel reads every record through 32
+// different cache lines per warp instruction; here the Jc | Jp quads of the tile's contiguous
+// record slab are copied to shared memory with coalesced 16-byte cp.async, the per-observation
+// products Jp^T (Jc D_c) and w.(2R + w) go back to shared memory as one quad, and one thread
+// per point sums its (contiguous) quads, solves for D_p and accumulates the model term.
+// DCQ: the camera step padded to rows of DQ = 4 ceil(D / 4) elements (128-bit gathers).
+// ---------------------------------------------------------------------------------------
+template <typename T, int D> struct BacksubCfg {
+  static constexpr int REC = ObsRec<D>::REC;
+  static constexpr int QJ = (2 * D + 6 + 3) / 4;   // quads covering Jc | Jp
+  static constexpr int SQ = (QJ + 1) | 1;          // + one quad of products; odd stride
+  static constexpr int DQ = (D + 3) / 4 * 4;
+  static constexpr size_t SMEM = (size_t)FUSED_TPB * SQ * 4 * sizeof(T);
+};
+
+template <typename T>
+__global__ void pad_rows_kernel(int n, int W, int WP, const T* __restrict__ src, T* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * WP) return;
+  const int r = i / WP, k = i % WP;
+  dst[i] = k < W ? src[(size_t)r * W + k] : T(0);
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(FUSED_TPB)
+backsub_tiles_kernel(const int4* __restrict__ tiles, const int32_t* __restrict__ pt_off, const int32_t* __restrict__ cam_of,
+                     const T* __restrict__ OBS, const T* __restrict__ R, const T* __restrict__ GPT, const T* __restrict__ HPP,
+                     const T* __restrict__ HPPINV, const T* __restrict__ DCQ, const T* __restrict__ pts,
+                     T* __restrict__ pts_trial, T* __restrict__ DP, double* __restrict__ part_m) {
+  typedef BacksubCfg<T, D> Cfg;
+  constexpr int REC = Cfg::REC, QJ = Cfg::QJ, SQ = Cfg::SQ, DQ = Cfg::DQ, OJP = ObsRec<D>::JP;
+  extern __shared__ __align__(16) unsigned char backsub_smem[];
+  T* stage = reinterpret_cast<T*>(backsub_smem);   // [FUSED_TPB][SQ * 4]
+  const int t = threadIdx.x;
+  const int4 tile = __ldg(tiles + blockIdx.x);
+  const int o0 = tile.z, n = tile.w, npts = tile.y - tile.x;
+  {
+    const T* src = OBS + (size_t)o0 * REC;
+#pragma unroll
+    for (int u = 0; u < QJ; ++u) {
+      const int i = t + u * FUSED_TPB;
+      if (i < n * QJ) cp_async_quad<T>(stage + ((size_t)(i / QJ) * SQ + (i % QJ)) * 4, src + (size_t)(i / QJ) * REC + (i % QJ) * 4);
+    }
+    cp_async_commit();
+  }
+  T dc[DQ], r0 = T(0), r1 = T(0);
+  if (t < n) {
+    const int64_t a = (int64_t)o0 + t;
+    const int c = cam_of[a];
+#pragma unroll
+    for (int q = 0; q < DQ / 4; ++q) QuadIO<T>::ldg(DCQ + (size_t)c * DQ + 4 * q, dc + 4 * q);
+    r0 = R[2 * a]; r1 = R[2 * a + 1];
+  }
+  int kb = 0, ke = 0;
+  T u0 = T(0), u1 = T(0), u2 = T(0);
+  const int p = tile.x + t;
+  if (t < npts) {
+    kb = pt_off[p] - o0; ke = pt_off[p + 1] - o0;
+    u0 = GPT[3 * (size_t)p]; u1 = GPT[3 * (size_t)p + 1]; u2 = GPT[3 * (size_t)p + 2];
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  T* srow = stage + (size_t)t * SQ * 4;
+  if (t < n) {
+    T rec[4 * QJ];
+#pragma unroll
+    for (int q = 0; q < QJ; ++q) QuadIO<T>::ld(srow + 4 * q, rec + 4 * q);
+    T w0 = T(0), w1 = T(0);
+#pragma unroll
+    for (int c = 0; c < D; ++c) { w0 += rec[c] * dc[c]; w1 += rec[D + c] * dc[c]; }
+    const T* j = rec + OJP;
+    T prod[4];
+    prod[0] = j[0] * w0 + j[3] * w1; prod[1] = j[1] * w0 + j[4] * w1; prod[2] = j[2] * w0 + j[5] * w1;
+    prod[3] = w0 * (2 * r0 + w0) + w1 * (2 * r1 + w1);
+    QuadIO<T>::st(srow + 4 * QJ, prod);
+  }
+  __syncthreads();
+  double msum = 0.0;
+  if (t < npts) {
+    T A = T(0);   // sum_a w_a . (2 R_a + w_a),  w_a = Jc_a D_c
+    for (int k = kb; k < ke; ++k) {
+      T prod[4];
+      QuadIO<T>::ld(stage + ((size_t)k * SQ + QJ) * 4, prod);
+      u0 += prod[0]; u1 += prod[1]; u2 += prod[2]; A += prod[3];
+    }
+    const T* iv = HPPINV + (size_t)p * 6;
+    T d0 = -(iv[0] * u0 + iv[1] * u1 + iv[2] * u2);
+    T d1 = -(iv[1] * u0 + iv[3] * u1 + iv[4] * u2);
+    T d2 = -(iv[2] * u0 + iv[4] * u1 + iv[5] * u2);
+    DP[3 * (size_t)p] = d0; DP[3 * (size_t)p + 1] = d1; DP[3 * (size_t)p + 2] = d2;
+    pts_trial[3 * (size_t)p] = pts[3 * (size_t)p] + d0; pts_trial[3 * (size_t)p + 1] = pts[3 * (size_t)p + 1] + d1;
+    pts_trial[3 * (size_t)p + 2] = pts[3 * (size_t)p + 2] + d2;
+    // model term, closed form (see backsub_kernel): A + 2 D_p . u + D_p^T Hpp D_p
+    const T* h = HPP + (size_t)p * 6;
+    T hd0 = h[0] * d0 + h[1] * d1 + h[2] * d2, hd1 = h[1] * d0 + h[3] * d1 + h[4] * d2, hd2 = h[2] * d0 + h[4] * d1 + h[5] * d2;
+    msum = (double)A + 2.0 * ((double)d0 * u0 + (double)d1 * u1 + (double)d2 * u2) + ((double)d0 * hd0 + (double)d1 * hd1 + (double)d2 * hd2);
+  }
+  msum = block_sum(msum);
+  if (t == 0) part_m[blockIdx.x] = msum;
 }
 
 // gather rows: dst[i] = src[idx[i]] with row width W (set-up only)

@@ -65,7 +65,7 @@ struct BASolver : BASolverBase {
   DeviceBuffer<T> cam[2], camq[2], pts[2], pp, obs;   // camq: packed [cam row | pp | pad] rows read by the kernels
   static constexpr int CWP = CamPack<CW>::CWP;
   static constexpr int REC = ObsRec<D>::REC;
-  DeviceBuffer<T> R, OBS, HPP, GPT, HPPINV, TP, DP;
+  DeviceBuffer<T> R, OBS, HPP, GPT, HPPINV, TP, DP, DCQ;
   DeviceBuffer<T> HCC_GC, HD, E, EG, RED, MINV, bvec;  // HCC_GC = [HCC | GC | cost] packed for one all-reduce
   DeviceBuffer<double> part_a, part_b, part_c, scalars;
   DeviceBuffer<int> fail;
@@ -138,7 +138,7 @@ struct BASolver : BASolverBase {
       HCC_GC.alloc((size_t)nc * (D * D + D)); HD.alloc((size_t)nc * D * D);
       E.alloc((size_t)sp.nnzu * D * D); E.zero(s);   // padding slots stay zero
       EG.alloc((size_t)nc * D); RED.alloc((size_t)nc * (D * D + D));
-      MINV.alloc((size_t)nc * D * D); bvec.alloc((size_t)nc * D);
+      MINV.alloc((size_t)nc * D * D); bvec.alloc((size_t)nc * D); DCQ.alloc((size_t)nc * BacksubCfg<T, D>::DQ);
       pcg.resize((int)nc, sp.n_off, sp.n_chunks);
     }
     ISFM_CUDA(cudaStreamSynchronize(s));
@@ -205,6 +205,8 @@ struct BASolver : BASolverBase {
     ISFM_CUDA(cudaStreamSynchronize(s));
     ISFM_CUDA(cudaFuncSetAttribute(fused_linearize_kernel<T, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)FusedCfg<T, D>::SMEM));
+    ISFM_CUDA(cudaFuncSetAttribute(backsub_tiles_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)BacksubCfg<T, D>::SMEM));
   }
 
   void run_cost(int which, double* robust, double* sq) {
@@ -317,7 +319,17 @@ struct BASolver : BASolverBase {
             ISFM_CUDA(cudaMemsetAsync(fail.get(), 0, sizeof(int), s));
           }
         }
-        { TimerScope ts(timers, T_BACKSUB);
+        if (fused_ok && !getenv("ISFM_NO_TILE_BACKSUB")) {
+          constexpr int DQ = BacksubCfg<T, D>::DQ;
+          { TimerScope ts(timers, T_MISC);
+            pad_rows_kernel<T><<<div_up(n_cam * DQ, 256), 256, 0, s>>>((int)n_cam, D, DQ, pcg.x.get(), DCQ.get()); }
+          TimerScope ts(timers, T_BACKSUB);
+          mterm_parts = n_fused_cta;
+          backsub_tiles_kernel<T, D><<<n_fused_cta, FUSED_TPB, BacksubCfg<T, D>::SMEM, s>>>(
+              fused_tiles.get(), ix.pt_off.get(), ix.cam_of.get(), OBS.get(), R.get(), GPT.get(), HPP.get(), HPPINV.get(),
+              DCQ.get(), pts[cur].get(), pts[trial].get(), DP.get(), part_c.get());
+        } else {
+          TimerScope ts(timers, T_BACKSUB);
           mterm_parts = red_grid(n_pt);
           backsub_kernel<T, D><<<mterm_parts, BA_TPB, 0, s>>>(n_pt, ix.pt_off.get(), ix.cam_of.get(), OBS.get(), R.get(),
                                                              GPT.get(), HPP.get(), HPPINV.get(), pcg.x.get(), pts[cur].get(),
