@@ -109,13 +109,13 @@ def algorithmic_bytes(name, n_obs, n_pt, n_cam, d, n_pairs, n_lists, nnzb, fsize
     """Algorithmic HBM bytes of ONE launch of a kernel family."""
     dd = d * d
     table = {
-        # fused K1 + point solve: obs + indices read; R and the full record (Jc | Jp | V, padded) written;
+        # fused K1 + point solve: obs + indices read; R and the full record (Jc | Jp | V | rho, padded) written;
         # per point X read, Hpp | g_p | Hpp^-1 | t_p written; camera table read
-        "linearize": n_obs * (8 + 8 + fsize * (2 + (2 * d + 12 + 3) // 4 * 4)) + n_pt * (8 + fsize * (3 + 18)) + n_cam * (9 + d) * fsize,
+        "linearize": n_obs * (8 + 8 + fsize * (2 + (2 * d + 14 + 3) // 4 * 4)) + n_pt * (8 + fsize * (3 + 18)) + n_cam * (9 + d) * fsize,
         "point_blocks": n_obs * fsize * (6 + 2 + 6) + n_pt * (4 + fsize * (6 + 3 + 6 + 3)),
         "point_solve": n_obs * fsize * (6 + 6) + n_pt * (4 + fsize * (6 + 3 + 6 + 3)),
-        # average of the H pass (idx 4, Jc, R) and the E pass (idx 8, Jc, V, Jp, t_p): reported per pass below
-        "camera_blocks": n_obs * (6 + fsize * (2 * d + 1 + 6 + 1.5)) + n_cam * fsize * (dd + d),
+        # one sweep per trial: camera-major index + Jc | Jp | V | rho of every record; Hcc - E_ii, diag Hcc, g_c - e written
+        "camera_blocks": n_obs * (4 + fsize * (2 * d + 14)) + n_cam * fsize * (2 * dd + 2 * d),
         "schur_offdiag": n_pairs * (8 + fsize * (4 * d + 12)) + n_lists * (16 + dd * fsize),
         # upper triangle only: blocks + col/tpos indices, B^T p_i deposits written, p gathered
         "pcg_spmv": ((nnzb + n_cam) // 2) * (dd * fsize + 8) + ((nnzb - n_cam) // 2) * d * fsize + n_cam * d * fsize,

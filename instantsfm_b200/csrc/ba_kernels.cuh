@@ -9,6 +9,7 @@
 //                           [0, 2D)        Jc  weighted camera block, row-major 2 x D (D = 6 + NI)
 //                           [2D, 2D+6)     Jp  weighted point block, 2 x 3
 //                           [2D+6, 2D+12)  V = Jp * Hpp^-1 (2 x 3), rewritten per trial
+//                           [2D+12, 2D+14) rho = R - Jp t_p (t_p = Hpp^-1 g_p), rewritten per trial
 //                         so that every gather of an observation is one or two full lines
 //                         fetched with 128-bit loads
 //   HPP   [n_pt][6]  GPT [n_pt][3]  HPPINV [n_pt][6]  TP [n_pt][3] = Hpp^-1 g_p
@@ -29,7 +30,8 @@ constexpr int RED_BLOCKS = 148 * 4;  // grid of the grid-stride reduction kernel
 template <int D> struct ObsRec {
   static constexpr int JP = 2 * D;                       // offset of Jp
   static constexpr int V = 2 * D + 6;                    // offset of V
-  static constexpr int REC = (2 * D + 12 + 3) / 4 * 4;   // stride in elements, multiple of 4
+  static constexpr int RHO = 2 * D + 12;                 // offset of rho = R - Jp t_p
+  static constexpr int REC = (2 * D + 14 + 3) / 4 * 4;   // stride in elements, multiple of 4
 };
 
 // 128-bit loads / stores of "quads" (4 consecutive elements; two double2 for T = double)
@@ -232,14 +234,17 @@ point_solve_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, T* __restri
   sym3_inverse(h, iv);
 #pragma unroll
   for (int i = 0; i < 6; ++i) HPPINV[(size_t)p * 6 + i] = iv[i];
-  TP[(size_t)p * 3 + 0] = iv[0] * g[0] + iv[1] * g[1] + iv[2] * g[2];
-  TP[(size_t)p * 3 + 1] = iv[1] * g[0] + iv[3] * g[1] + iv[4] * g[2];
-  TP[(size_t)p * 3 + 2] = iv[2] * g[0] + iv[4] * g[1] + iv[5] * g[2];
+  const T t0 = iv[0] * g[0] + iv[1] * g[1] + iv[2] * g[2];
+  const T t1 = iv[1] * g[0] + iv[3] * g[1] + iv[4] * g[2];
+  const T t2 = iv[2] * g[0] + iv[4] * g[1] + iv[5] * g[2];
+  TP[(size_t)p * 3 + 0] = t0; TP[(size_t)p * 3 + 1] = t1; TP[(size_t)p * 3 + 2] = t2;
   if (WRITE_V) {
     for (int a = beg; a < end; ++a) {
       T* rec = OBS + (size_t)a * REC;
       const T* j = rec + OJP;
       T* v = rec + OV;
+      rec[ObsRec<D>::RHO] = R[2 * (size_t)a] - (j[0] * t0 + j[1] * t1 + j[2] * t2);
+      rec[ObsRec<D>::RHO + 1] = R[2 * (size_t)a + 1] - (j[3] * t0 + j[4] * t1 + j[5] * t2);
 #pragma unroll
       for (int row = 0; row < 2; ++row) {
         T a0 = j[3 * row], a1 = j[3 * row + 1], a2 = j[3 * row + 2];
@@ -274,21 +279,18 @@ point_only_step_kernel(int64_t n_pt, const int32_t* __restrict__ pt_off, const T
 }
 
 // ---------------------------------------------------------------------------------------
-// K2 (camera side): one CTA per camera over its observation records (camera-major list).
-// PASS_E = false: Hcc_i = sum Jc^T Jc, g_c = sum Jc^T R            (once per LM step)
-// PASS_E = true : E_ii  = sum Jc^T (V Jp^T) Jc, e_i = sum Jc^T (Jp t_p)   (once per trial)
-// Each record is fetched with 128-bit loads; warp-shuffle + shared-memory reduction, no atomics.
+// Undamped camera blocks Hcc_i = sum Jc^T Jc and g_c = sum Jc^T R, one CTA per camera over its
+// camera-major record list.  Not on the step path any more (camera_schur_kernel forms
+// Hcc - E_ii directly); kept for the parity / debug buffers ISFM_BA_HCC and ISFM_BA_GC.
 // ---------------------------------------------------------------------------------------
 constexpr int CAM_TPB = 128;
 
-template <typename T, int D, bool PASS_E>
+template <typename T, int D>
 __global__ void __launch_bounds__(CAM_TPB)
-camera_blocks_kernel(const int32_t* __restrict__ cam_off, const int32_t* __restrict__ cam_perm,
-                     const int32_t* __restrict__ pt_of, const T* __restrict__ OBS, const T* __restrict__ R,
-                     const T* __restrict__ TP, T* __restrict__ out_blocks, const int32_t* __restrict__ out_slot,
-                     T* __restrict__ out_vec) {
-  constexpr int REC = ObsRec<D>::REC, OJP = ObsRec<D>::JP, OV = ObsRec<D>::V;
-  constexpr int NQ = PASS_E ? REC / 4 : (2 * D + 3) / 4;
+camera_hessian_kernel(const int32_t* __restrict__ cam_off, const int32_t* __restrict__ cam_perm,
+                      const T* __restrict__ OBS, const T* __restrict__ R, T* __restrict__ out_blocks, T* __restrict__ out_vec) {
+  constexpr int REC = ObsRec<D>::REC;
+  constexpr int NQ = (2 * D + 3) / 4;
   constexpr int NU = D * (D + 1) / 2;
   constexpr int NACC = NU + D;
   constexpr int NW = CAM_TPB / 32;
@@ -303,25 +305,12 @@ camera_blocks_kernel(const int32_t* __restrict__ cam_off, const int32_t* __restr
     T rec[4 * NQ];
     load_quads<T, 0, NQ, true>(OBS + (size_t)a * REC, rec);
     const T* jc = rec;
-    T m00, m01, m10, m11, s0, s1;
-    if constexpr (PASS_E) {
-      const T* v = rec + OV;
-      const T* j = rec + OJP;
-      const T* t = TP + 3 * (size_t)pt_of[a];
-      m00 = v[0] * j[0] + v[1] * j[1] + v[2] * j[2]; m01 = v[0] * j[3] + v[1] * j[4] + v[2] * j[5];
-      m10 = v[3] * j[0] + v[4] * j[1] + v[5] * j[2]; m11 = v[3] * j[3] + v[4] * j[4] + v[5] * j[5];
-      s0 = j[0] * t[0] + j[1] * t[1] + j[2] * t[2]; s1 = j[3] * t[0] + j[4] * t[1] + j[5] * t[2];
-    } else {
-      m00 = T(1); m01 = T(0); m10 = T(0); m11 = T(1);
-      s0 = R[2 * (size_t)a]; s1 = R[2 * (size_t)a + 1];
-    }
+    const T s0 = R[2 * (size_t)a], s1 = R[2 * (size_t)a + 1];
     int u = 0;
 #pragma unroll
     for (int r = 0; r < D; ++r) {
-      // row r of Jc^T M : (jc[r], jc[D + r]) * M
-      T l0 = jc[r] * m00 + jc[D + r] * m10, l1 = jc[r] * m01 + jc[D + r] * m11;
 #pragma unroll
-      for (int c = r; c < D; ++c) acc[u++] += l0 * jc[c] + l1 * jc[D + c];
+      for (int c = r; c < D; ++c) acc[u++] += jc[r] * jc[c] + jc[D + r] * jc[D + c];
       acc[NU + r] += jc[r] * s0 + jc[D + r] * s1;
     }
   }
@@ -337,7 +326,6 @@ camera_blocks_kernel(const int32_t* __restrict__ cam_off, const int32_t* __restr
     for (int i = 0; i < NACC; ++i) sh[w][i] = acc[i];
   }
   __syncthreads();
-  // thread t < NACC sums the NW warp partials of accumulator t and scatters it
   for (int t = threadIdx.x; t < NACC; t += CAM_TPB) {
     T v = T(0);
 #pragma unroll
@@ -345,11 +333,10 @@ camera_blocks_kernel(const int32_t* __restrict__ cam_off, const int32_t* __restr
     if (t >= NU) {
       out_vec[(size_t)cam * D + (t - NU)] = v;
     } else {
-      // invert the packed upper-triangle index
-      int r = 0, rem = t;
+      int r = 0, rem = t;   // invert the packed upper-triangle index
       while (rem >= D - r) { rem -= D - r; ++r; }
-      int c = r + rem;
-      T* blk = out_blocks + (size_t)(out_slot ? out_slot[cam] : cam) * (D * D);
+      const int c = r + rem;
+      T* blk = out_blocks + (size_t)cam * (D * D);
       blk[r * D + c] = v;
       blk[c * D + r] = v;
     }
@@ -381,7 +368,7 @@ schur_offdiag_kernel(int64_t n_lists, const int32_t* __restrict__ list_order, co
                      const uint8_t* __restrict__ list_diag, const T* __restrict__ OBS, T* __restrict__ E) {
   constexpr int REC = ObsRec<D>::REC, OJP = ObsRec<D>::JP, OV = ObsRec<D>::V;
   constexpr int LPL = SchurGroup<D>::LPL, GPW = SchurGroup<D>::PER_WARP;
-  constexpr int DEPTH = sizeof(T) == 4 ? 4 : 3;   // pairs in flight per list (ring in shared memory)
+  constexpr int DEPTH = sizeof(T) == 4 ? 4 : 2;   // pairs in flight per list (ring in shared memory; 48 KB static limit)
   constexpr int VE = 16 / sizeof(T);              // elements per 16-byte vector
   constexpr int NVEC = REC / VE;                  // vectors per record
   // per-list ring [DEPTH][2][REC]; consecutive lists are offset by 4 extra words so that the
@@ -456,45 +443,119 @@ schur_offdiag_kernel(int64_t n_lists, const int32_t* __restrict__ list_order, co
   }
 }
 
-// gather diag(E) blocks and e into the reduction buffer [n_cam][D*D + D]
+// ---------------------------------------------------------------------------------------
+// K2 (camera side, per trial): one CTA per camera over its observation records, one sweep for
+// everything the reduced system needs from the diagonal:
+//   HME_i = [ sum Jc^T (I - V Jp^T) Jc  |  diag(sum Jc^T Jc)  |  sum Jc^T rho ]
+//         = [ Hcc_i - E_ii              |  diag(Hcc_i)        |  (g_c - e)_i  ]
+// The difference Hcc - E_ii is formed per observation on the 2x2 factor I - M (M = Jp Hpp^-1 Jp^T
+// has its eigenvalues in [0, 1)), not as the difference of two large sums: the cancellation
+// that costs fp32 its digits on weakly observed cameras never happens.  diag(Hcc) is kept apart
+// because the LM damping scales the clamped diagonal of Hcc only.  The record carries everything
+// (Jc, Jp, V, rho): no gathers besides the record itself.  Also zeroes the diagonal slot of E
+// (only duplicate-camera pair lists add to it).  No atomics.
+// ---------------------------------------------------------------------------------------
 template <typename T, int D>
-__global__ void gather_diag_kernel(int n_cam, const int32_t* __restrict__ diag_slot, const T* __restrict__ E,
-                                   const T* __restrict__ EG, T* __restrict__ red) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_cam * (D * D + D)) return;
-  int cam = i / (D * D + D), k = i % (D * D + D);
-  red[i] = k < D * D ? E[(size_t)diag_slot[cam] * (D * D) + k] : EG[(size_t)cam * D + (k - D * D)];
+__global__ void __launch_bounds__(CAM_TPB)
+camera_schur_kernel(const int32_t* __restrict__ cam_off, const int32_t* __restrict__ cam_perm, const T* __restrict__ OBS,
+                    T* __restrict__ HME, T* __restrict__ E, const int32_t* __restrict__ diag_slot) {
+  constexpr int REC = ObsRec<D>::REC, OJP = ObsRec<D>::JP, OV = ObsRec<D>::V, ORHO = ObsRec<D>::RHO;
+  constexpr int NQ = REC / 4;
+  constexpr int NU = D * (D + 1) / 2;
+  constexpr int NACC = NU + 2 * D;
+  constexpr int NW = CAM_TPB / 32;
+  constexpr int W = D * D + 2 * D;
+  __shared__ T sh[NW][NACC];
+  const int cam = blockIdx.x;
+  const int beg = cam_off[cam], end = cam_off[cam + 1];
+  T acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = T(0);
+  for (int k = beg + threadIdx.x; k < end; k += CAM_TPB) {
+    const int a = cam_perm[k];
+    T rec[4 * NQ];
+    load_quads<T, 0, NQ, true>(OBS + (size_t)a * REC, rec);
+    const T* jc = rec;
+    const T* v = rec + OV;
+    const T* j = rec + OJP;
+    const T x00 = T(1) - (v[0] * j[0] + v[1] * j[1] + v[2] * j[2]), x01 = -(v[0] * j[3] + v[1] * j[4] + v[2] * j[5]);
+    const T x10 = -(v[3] * j[0] + v[4] * j[1] + v[5] * j[2]), x11 = T(1) - (v[3] * j[3] + v[4] * j[4] + v[5] * j[5]);
+    const T s0 = rec[ORHO], s1 = rec[ORHO + 1];
+    int u = 0;
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      const T l0 = jc[r] * x00 + jc[D + r] * x10, l1 = jc[r] * x01 + jc[D + r] * x11;
+#pragma unroll
+      for (int c = r; c < D; ++c) acc[u++] += l0 * jc[c] + l1 * jc[D + c];
+      acc[NU + r] += jc[r] * jc[r] + jc[D + r] * jc[D + r];
+      acc[NU + D + r] += jc[r] * s0 + jc[D + r] * s1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) {
+    T v = acc[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    acc[i] = v;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) sh[w][i] = acc[i];
+  }
+  __syncthreads();
+  T* out = HME + (size_t)cam * W;
+  for (int t = threadIdx.x; t < NACC; t += CAM_TPB) {
+    T v = T(0);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) v += sh[k][t];
+    if (t >= NU) {
+      out[D * D + (t - NU)] = v;
+    } else {
+      int r = 0, rem = t;
+      while (rem >= D - r) { rem -= D - r; ++r; }
+      const int c = r + rem;
+      out[r * D + c] = v;
+      out[c * D + r] = v;
+    }
+  }
+  if (E) {
+    T* blk = E + (size_t)diag_slot[cam] * (D * D);
+    for (int t = threadIdx.x; t < D * D; t += CAM_TPB) blk[t] = T(0);
+  }
 }
 
-// K3: Hd = damp(Hcc); Minv = (Hd - sum_ranks E_ii)^-1 ; b = -(g_c - sum_ranks e)
+// K3: S_ii = (Hcc - E_ii) + diag(clamp(diag Hcc) mu - diag Hcc); Minv = S_ii^-1; b = -(g_c - e).
+// HD receives S_ii: the PCG operator is q = HD p - E p with the diagonal slot of E holding only
+// the duplicate-camera contributions.
 template <typename T, int D>
-__global__ void precond_kernel(int n_cam, const T* __restrict__ HCC, const T* __restrict__ GC, const T* __restrict__ red,
-                               T mu, T* __restrict__ HD, T* __restrict__ MINV, T* __restrict__ bvec, int* __restrict__ fail) {
+__global__ void precond_kernel(int n_cam, const T* __restrict__ HME, T mu, T* __restrict__ HD, T* __restrict__ MINV,
+                               T* __restrict__ bvec, int* __restrict__ fail) {
   int cam = blockIdx.x * blockDim.x + threadIdx.x;
   if (cam >= n_cam) return;
+  constexpr int W = D * D + 2 * D;
   double M[D * D];
-  const T* h = HCC + (size_t)cam * (D * D);
-  const T* e = red + (size_t)cam * (D * D + D);
+  const T* h = HME + (size_t)cam * W;
 #pragma unroll 1
   for (int r = 0; r < D; ++r)
     for (int c = 0; c < D; ++c) {
-      T v = h[r * D + c];
-      if (r == c) v = damp_diag(v, mu);
-      HD[(size_t)cam * (D * D) + r * D + c] = v;
-      M[r * D + c] = (double)v - (double)e[r * D + c];
+      double v = (double)h[r * D + c];
+      if (r == c) { const T d = h[D * D + r]; v += (double)damp_diag(d, mu) - (double)d; }
+      HD[(size_t)cam * (D * D) + r * D + c] = (T)v;
+      M[r * D + c] = v;
     }
   if (!spd_inverse<D>(M)) {
-    // Hd - E_ii lost positive definiteness to cancellation (degenerate points in fp32): fall back
-    // to the always-SPD damped Hcc block -- a weaker preconditioner, the system itself is unchanged
+    // rounding made S_ii indefinite (degenerate geometry): fall back to the damped diagonal of Hcc,
+    // always positive -- a weaker preconditioner, the system itself is unchanged
     *fail = cam + 1;
 #pragma unroll 1
-    for (int k = 0; k < D * D; ++k) M[k] = (double)HD[(size_t)cam * (D * D) + k];
-    spd_inverse<D>(M);
+    for (int k = 0; k < D * D; ++k) M[k] = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < D; ++r) M[r * D + r] = 1.0 / (double)damp_diag(h[D * D + r], mu);
   }
 #pragma unroll 1
   for (int k = 0; k < D * D; ++k) MINV[(size_t)cam * (D * D) + k] = (T)M[k];
 #pragma unroll 1
-  for (int k = 0; k < D; ++k) bvec[(size_t)cam * D + k] = -(GC[(size_t)cam * D + k] - e[D * D + k]);
+  for (int k = 0; k < D; ++k) bvec[(size_t)cam * D + k] = -h[D * D + D + k];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -635,7 +696,8 @@ fused_linearize_kernel(const int4* __restrict__ tiles, const int32_t* __restrict
       for (int i = 0; i < 3; ++i) { GPT[(size_t)pz * 3 + i] = T(0); TP[(size_t)pz * 3 + i] = T(0); }
     }
   }
-  T tail[REC - 4 * QV];          // record elements [4 QV, REC): the end of Jp, V, padding
+  T tail[REC - 4 * QV];          // record elements [4 QV, REC): the end of Jp, V, rho, padding
+  T rw0 = T(0), rw1 = T(0);
   int p = 0, kb = 0, ke = 0;
   if (t < n) {
     int c = cam_of[a];
@@ -657,7 +719,7 @@ fused_linearize_kernel(const int4* __restrict__ tiles, const int32_t* __restrict
     T s = r[0] * r[0] + r[1] * r[1], rho, w;
     huber(s, delta, rho, w);
     rho_d += (double)rho; sq_d += (double)s;
-    const T rw0 = w * r[0], rw1 = w * r[1];
+    rw0 = w * r[0]; rw1 = w * r[1];
 #pragma unroll
     for (int i = 0; i < 2 * D + 6; ++i) rec[i] *= w;
 #pragma unroll
@@ -701,12 +763,13 @@ fused_linearize_kernel(const int4* __restrict__ tiles, const int32_t* __restrict
     h[0] = damp_diag(h[0], mu); h[3] = damp_diag(h[3], mu); h[5] = damp_diag(h[5], mu);
     T iv[6];
     sym3_inverse(h, iv);
+    const T t0 = iv[0] * g[0] + iv[1] * g[1] + iv[2] * g[2];
+    const T t1 = iv[1] * g[0] + iv[3] * g[1] + iv[4] * g[2];
+    const T t2 = iv[2] * g[0] + iv[4] * g[1] + iv[5] * g[2];
     if (head) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) HPPINV[(size_t)p * 6 + i] = iv[i];
-      TP[(size_t)p * 3 + 0] = iv[0] * g[0] + iv[1] * g[1] + iv[2] * g[2];
-      TP[(size_t)p * 3 + 1] = iv[1] * g[0] + iv[3] * g[1] + iv[4] * g[2];
-      TP[(size_t)p * 3 + 2] = iv[2] * g[0] + iv[4] * g[1] + iv[5] * g[2];
+      TP[(size_t)p * 3 + 0] = t0; TP[(size_t)p * 3 + 1] = t1; TP[(size_t)p * 3 + 2] = t2;
     }
     // Jp: elements [OJP, OJP + 6) of the record; those below 4 QV were staged, re-read them
     T jp[6];
@@ -719,6 +782,8 @@ fused_linearize_kernel(const int4* __restrict__ tiles, const int32_t* __restrict
       tail[OV - 4 * QV + 3 * row + 1] = a0 * iv[1] + a1 * iv[3] + a2 * iv[4];
       tail[OV - 4 * QV + 3 * row + 2] = a0 * iv[2] + a1 * iv[4] + a2 * iv[5];
     }
+    tail[ObsRec<D>::RHO - 4 * QV] = rw0 - (jp[0] * t0 + jp[1] * t1 + jp[2] * t2);
+    tail[ObsRec<D>::RHO - 4 * QV + 1] = rw1 - (jp[3] * t0 + jp[4] * t1 + jp[5] * t2);
 #pragma unroll
     for (int q = QV; q < QR; ++q) QuadIO<T>::st(srow + 4 * q, tail + 4 * (q - QV));
   }

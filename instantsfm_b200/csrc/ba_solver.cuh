@@ -66,7 +66,7 @@ struct BASolver : BASolverBase {
   static constexpr int CWP = CamPack<CW>::CWP;
   static constexpr int REC = ObsRec<D>::REC;
   DeviceBuffer<T> R, OBS, HPP, GPT, HPPINV, TP, DP, DCQ;
-  DeviceBuffer<T> HCC_GC, HD, E, EG, RED, MINV, bvec;  // HCC_GC = [HCC | GC | cost] packed for one all-reduce
+  DeviceBuffer<T> HCC_GC, HME, HD, E, MINV, bvec;  // HME = [Hcc - E_ii | diag Hcc | g_c - e] per camera: one all-reduce per trial
   DeviceBuffer<double> part_a, part_b, part_c, scalars;
   DeviceBuffer<int> fail;
   double* h_scalars = nullptr;  // pinned [4]
@@ -137,7 +137,7 @@ struct BASolver : BASolverBase {
       build_schur_pattern(sp, ix, s, timers);
       HCC_GC.alloc((size_t)nc * (D * D + D)); HD.alloc((size_t)nc * D * D);
       E.alloc((size_t)sp.nnzu * D * D); E.zero(s);   // padding slots stay zero
-      EG.alloc((size_t)nc * D); RED.alloc((size_t)nc * (D * D + D));
+      HME.alloc((size_t)nc * (D * D + 2 * D));
       MINV.alloc((size_t)nc * D * D); bvec.alloc((size_t)nc * D); DCQ.alloc((size_t)nc * BacksubCfg<T, D>::DQ);
       pcg.resize((int)nc, sp.n_off, sp.n_chunks);
     }
@@ -233,8 +233,8 @@ struct BASolver : BASolverBase {
 
   void run_camera_hessian() {
     { TimerScope ts(timers, T_CAMERA_BLOCKS);
-      camera_blocks_kernel<T, D, false><<<(int)n_cam, CAM_TPB, 0, s>>>(ix.cam_off.get(), ix.cam_perm.get(), ix.pt_of.get(),
-                                                                      OBS.get(), R.get(), nullptr, HCC(), nullptr, GC()); }
+      camera_hessian_kernel<T, D><<<(int)n_cam, CAM_TPB, 0, s>>>(ix.cam_off.get(), ix.cam_perm.get(), OBS.get(), R.get(), HCC(),
+                                                                GC()); }
     if (comm_world(comm) > 1) {
       TimerScope ts(timers, T_COMM);
       comm_allreduce_sum(comm, HCC_GC.get(), (size_t)n_cam * (D * D + D), sizeof(T) == 8, s);
@@ -244,9 +244,8 @@ struct BASolver : BASolverBase {
   // builds E, the preconditioner and the right-hand side for damping mu; solves for D_c
   int run_schur_and_pcg(T mu, int* pcg_status) {
     { TimerScope ts(timers, T_CAMERA_BLOCKS);
-      camera_blocks_kernel<T, D, true><<<(int)n_cam, CAM_TPB, 0, s>>>(ix.cam_off.get(), ix.cam_perm.get(), ix.pt_of.get(),
-                                                                     OBS.get(), R.get(), TP.get(), E.get(), sp.diag_slot.get(),
-                                                                     EG.get()); }
+      camera_schur_kernel<T, D><<<(int)n_cam, CAM_TPB, 0, s>>>(ix.cam_off.get(), ix.cam_perm.get(), OBS.get(), HME.get(), E.get(),
+                                                              sp.diag_slot.get()); }
     if (sp.n_lists > 0) {
       TimerScope ts(timers, T_SCHUR_OFFDIAG);
       const int lists_per_cta = SchurGroup<D>::PER_WARP * (SCHUR_TPB / 32);
@@ -254,16 +253,13 @@ struct BASolver : BASolverBase {
           sp.n_lists, sp.list_order.get(), sp.list_off.get(), sp.pairs.get(), sp.list_slot.get(), sp.list_diag.get(), OBS.get(),
           E.get());
     }
-    { TimerScope ts(timers, T_PRECOND);
-      gather_diag_kernel<T, D><<<div_up(n_cam * (D * D + D), BA_TPB), BA_TPB, 0, s>>>((int)n_cam, sp.diag_slot.get(), E.get(),
-                                                                                      EG.get(), RED.get()); }
     if (comm_world(comm) > 1) {
       TimerScope ts(timers, T_COMM);
-      comm_allreduce_sum(comm, RED.get(), (size_t)n_cam * (D * D + D), sizeof(T) == 8, s);
+      comm_allreduce_sum(comm, HME.get(), (size_t)n_cam * (D * D + 2 * D), sizeof(T) == 8, s);
     }
     { TimerScope ts(timers, T_PRECOND);
-      precond_kernel<T, D><<<div_up(n_cam, 64), 64, 0, s>>>((int)n_cam, HCC(), GC(), RED.get(), mu, HD.get(), MINV.get(),
-                                                            bvec.get(), fail.get()); }
+      precond_kernel<T, D><<<div_up(n_cam, 64), 64, 0, s>>>((int)n_cam, HME.get(), mu, HD.get(), MINV.get(), bvec.get(),
+                                                            fail.get()); }
     int max_iter = desc.pcg_max_iter > 0 ? desc.pcg_max_iter : (int)std::min<int64_t>(10 * n_cam * D, 5000);
     return pcg.solve(sp, E.get(), HD.get(), MINV.get(),
                      bvec.get(), desc.pcg_tol, max_iter, comm, s, timers, pcg_status);
@@ -291,7 +287,6 @@ struct BASolver : BASolverBase {
     stats.loss_before = last;
     double mu = 1.0;
     bool built = false;
-    if (desc.optimize_poses) run_camera_hessian();
     int rejects = 0;
     const int trial = cur ^ 1;
     while (last <= loss) {
@@ -313,9 +308,9 @@ struct BASolver : BASolverBase {
             const int c = h_fail - 1;
             std::vector<T> hh((size_t)D * D), ee((size_t)D * D + D);
             ISFM_CUDA(cudaMemcpy(hh.data(), HD.get() + (size_t)c * D * D, hh.size() * sizeof(T), cudaMemcpyDeviceToHost));
-            ISFM_CUDA(cudaMemcpy(ee.data(), RED.get() + (size_t)c * (D * D + D), ee.size() * sizeof(T), cudaMemcpyDeviceToHost));
-            for (int r = 0; r < D; ++r) fprintf(stderr, "[isfm]   cam %d diag %d: Hd %.9e  E %.9e  S %.9e\n", c, r, (double)hh[r * D + r],
-                                               (double)ee[r * D + r], (double)hh[r * D + r] - (double)ee[r * D + r]);
+            ISFM_CUDA(cudaMemcpy(ee.data(), HME.get() + (size_t)c * (D * D + 2 * D), ee.size() * sizeof(T), cudaMemcpyDeviceToHost));
+            for (int r = 0; r < D; ++r) fprintf(stderr, "[isfm]   cam %d diag %d: S_ii %.9e  Hcc - E_ii %.9e\n", c, r, (double)hh[r * D + r],
+                                               (double)ee[r * D + r]);
             ISFM_CUDA(cudaMemsetAsync(fail.get(), 0, sizeof(int), s));
           }
         }
