@@ -302,6 +302,8 @@ def main_ours(args):
                 "lm_iters_per_sec": args.steps / (ms_total * 1e-3), "final_rmse_px": rmse, "final_robust_cost": rob,
                 "pcg_iters_per_step": float(np.mean([s["pcg_iters"] for s in stats])),
                 "rejects": int(sum(s["rejects"] for s in stats)),
+                "pcg_exchange": (None if world == 1 else ("peer-memory push over NVLink fused into the PCG kernels (device-side WHILE graph)"
+                                                          if comm.peer_enabled else "ncclAllReduce per iteration")),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
                 "profile_pass": {"pcg_iters_per_step": pcg_iters_prof / prof_steps, "wall_ms_per_step": prof_wall_ms,
                                  "kernel_ms_per_step": sum(k["ms_per_step"] for k in kernels.values())},

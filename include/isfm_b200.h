@@ -77,6 +77,10 @@ int64_t isfm_launch_count(void);
 int isfm_comm_unique_id(uint8_t id_out[128]);
 int isfm_comm_create(const uint8_t id[128], int rank, int world, isfm_comm** out);
 void isfm_comm_destroy(isfm_comm* comm);
+/* Transport of the per-PCG-iteration sum: 1 = peer-memory exchange over NVLink (CUDA IPC,   */
+/* fused into the producing / consuming kernels), 0 = ncclAllReduce (not set up yet, or IPC  */
+/* unavailable, or ISFM_NO_PEER set).  Valid after the first isfm_*_set_problem on the comm. */
+int isfm_comm_peer_enabled(const isfm_comm* comm);
 
 /* ------------------------------------------------------------------------------------ */
 /* integer prep on host arrays (bit-exact contract)                          */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "isfm_comm_unique_id": (c_int, [POINTER(c_uint8)]),
     "isfm_comm_create": (c_int, [POINTER(c_uint8), c_int, c_int, POINTER(c_void_p)]),
     "isfm_comm_destroy": (None, [c_void_p]),
+    "isfm_comm_peer_enabled": (c_int, [c_void_p]),
     "isfm_partition_points": (c_int, [POINTER(c_int64), c_int64, c_int, POINTER(c_int64)]),
     "isfm_ba_default_desc": (None, [POINTER(BADesc)]),
     "isfm_ba_create": (c_int, [POINTER(BADesc), POINTER(c_void_p)]),

@@ -139,7 +139,7 @@ struct BASolver : BASolverBase {
       E.alloc((size_t)sp.nnzu * D * D); E.zero(s);   // padding slots stay zero
       HME.alloc((size_t)nc * (D * D + 2 * D));
       MINV.alloc((size_t)nc * D * D); bvec.alloc((size_t)nc * D); DCQ.alloc((size_t)nc * BacksubCfg<T, D>::DQ);
-      pcg.resize((int)nc, sp.n_off, sp.n_chunks);
+      pcg.resize((int)nc, sp.n_off, sp.n_chunks, comm, s);
     }
     ISFM_CUDA(cudaStreamSynchronize(s));
     cur = 0; have_loss = false; has_problem = true;

@@ -389,7 +389,7 @@ struct GPSolver : GPSolverBase {
     part_a.alloc(std::max<int64_t>(RED_BLOCKS, nc)); part_b.alloc(std::max<int64_t>(RED_BLOCKS, nc));
     part_c.alloc(std::max<int64_t>(RED_BLOCKS, nc));
     scalars.alloc(4); fail.alloc(1); fail.zero(s);
-    pcg.resize((int)nc, sp.n_off, sp.n_chunks);
+    pcg.resize((int)nc, sp.n_off, sp.n_chunks, comm, s);
     ISFM_CUDA(cudaStreamSynchronize(s));
     cur = 0; have_loss = false; has_problem = true;
     tr.init(desc.tr_radius, desc.tr_max, desc.tr_up, desc.tr_down);

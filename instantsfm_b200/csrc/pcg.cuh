@@ -169,19 +169,30 @@ pcg_spmv_upper_kernel(int n_units, const int32_t* __restrict__ unit_row, const i
 }
 
 // y_i = sum of row i's chunk partials + sum of the deposits of row i (contiguous in C).
-// FUSED (single rank): q_i = Hd_i p_i - y_i and the per-CTA partial of p.q; otherwise y is
-// written for the all-reduce.  Row i of the lower triangle holds up to i deposits, so a CTA takes
+// COMB_FUSED (single rank): q_i = Hd_i p_i - y_i and the per-CTA partial of p.q.
+// COMB_PLAIN: y is written for an NCCL all-reduce.
+// COMB_PUSH: this rank's y rows are stored straight into the exchange slot of EVERY rank
+// (remote stores over NVLink); the CTA that finishes last publishes the sequence number in all
+// peers' flags behind a system-scope fence -- the first half of the all-reduce is this
+// kernel's epilogue (see comm.cuh), pcg_apply_diag_kernel<.., true> is the second half.  Row i of the lower triangle holds up to i deposits, so a CTA takes
 // the two rows b and n-1-b: every CTA of a dense system sums the same number of deposits (no
 // tail of long rows), with eight independent loads in flight per thread.
 constexpr int COMB_TPB = 256;
+constexpr int COMB_PLAIN = 0, COMB_FUSED = 1, COMB_PUSH = 2;
 
-template <typename T, int D, bool FUSED>
+template <typename T, int D, int MODE>
 __global__ void __launch_bounds__(COMB_TPB)
 pcg_combine_kernel(int n_cam, const int32_t* __restrict__ lrow_ptr, const int32_t* __restrict__ chunk_ptr,
                    const T* __restrict__ yup_part, const T* __restrict__ C, const T* __restrict__ Hd,
                    const T* __restrict__ p, T* __restrict__ out, double* __restrict__ partial,
-                   PcgState* __restrict__ st) {
+                   PcgState* __restrict__ st, const PeerExchange px) {
   if (st->done) return;
+  constexpr bool FUSED = MODE == COMB_FUSED;
+  // sequence number of THIS exchange; the counter is advanced by the last CTA only, after every
+  // CTA has read it (each CTA reads before it takes its ticket)
+  uint32_t seq = 0;
+  if (MODE == COMB_PUSH) seq = *reinterpret_cast<volatile uint32_t*>(peer_seq(px)) + 1u;
+  const int parity = (int)(seq & 1u);
   constexpr int G = COMB_TPB / D;   // entry groups per CTA; threads >= G * D idle
   constexpr int MLP = 8;
   __shared__ T sh[G][D];
@@ -222,11 +233,27 @@ pcg_combine_kernel(int n_cam, const int32_t* __restrict__ lrow_ptr, const int32_
         q -= y;
         out[(size_t)row * D + threadIdx.x] = q;
         qs[half][threadIdx.x] = q * pi[threadIdx.x];
+      } else if (MODE == COMB_PUSH) {
+        for (int dst = 0; dst < px.world; ++dst) peer_slot<T>(px, dst, parity, px.rank)[(size_t)row * D + threadIdx.x] = y;
       } else {
         out[(size_t)row * D + threadIdx.x] = y;
       }
     }
     __syncthreads();   // sh is reused by the second row; qs complete
+  }
+  if (MODE == COMB_PUSH) {
+    // the stores of threads 0..D-1 are ordered before thread 0's fence by the barrier above
+    __shared__ bool last_push__;
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      last_push__ = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last_push__) {
+      __threadfence_system();
+      if ((int)threadIdx.x < px.world) st_release_sys(peer_flags(px, threadIdx.x, parity) + px.rank, seq);
+      if (threadIdx.x == 0) { *peer_seq(px) = seq; st->ticket = 0u; }
+    }
   }
   if (FUSED) {
     double s = 0.0;
@@ -239,26 +266,45 @@ pcg_combine_kernel(int n_cam, const int32_t* __restrict__ lrow_ptr, const int32_
   }
 }
 
-// multi-rank second half: q = Hd p - y (y all-reduced), per-row partial of p.q
-template <typename T, int D>
+// multi-rank second half: q = Hd p - y, per-row partial of p.q.  y is either the NCCL
+// all-reduced vector or (PEER) the sum, in rank order, of the `world` partial vectors the ranks
+// pushed into this rank's exchange slots: every rank adds the same numbers in the same order, so
+// q, and with it the whole PCG state, stays bit-identical across ranks.
+template <typename T, int D, bool PEER>
 __global__ void __launch_bounds__(PCG_TPB)
 pcg_apply_diag_kernel(int n_cam, const T* __restrict__ Hd, const T* __restrict__ p, const T* __restrict__ y,
-                      T* __restrict__ q, double* __restrict__ partial, PcgState* __restrict__ st) {
+                      T* __restrict__ q, double* __restrict__ partial, PcgState* __restrict__ st, const PeerExchange px) {
   if (st->done) return;
-  int row = blockIdx.x * blockDim.x + threadIdx.x;
-  double s = 0.0;
-  if (row < n_cam) {
-    const T* h = Hd + (size_t)row * (D * D);
-    const T* pi = p + (size_t)row * D;
-#pragma unroll
-    for (int r = 0; r < D; ++r) {
-      T v = T(0);
-#pragma unroll
-      for (int c = 0; c < D; ++c) v += h[r * D + c] * pi[c];
-      v -= y[(size_t)row * D + r];
-      q[(size_t)row * D + r] = v;
-      s += (double)v * (double)pi[r];
+  int parity = 0;
+  if (PEER) {
+    const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(peer_seq(px));   // advanced by the push kernel before us
+    parity = (int)(seq & 1u);
+    if (!peer_wait_all(px, parity, seq)) {   // a peer never arrived: stop the solve, the host reports it
+      if (threadIdx.x == 0) st->done = 3;
+      return;
     }
+  }
+  // D threads per camera: thread (cam, k) owns component k -- row k of Hd_cam and entry k of
+  // every partial vector (consecutive threads read consecutive words of the exchange slots)
+  constexpr int CPB = PCG_TPB / D;
+  const int cam = blockIdx.x * CPB + threadIdx.x / D, k = threadIdx.x % D;
+  double s = 0.0;
+  if (threadIdx.x < CPB * D && cam < n_cam) {
+    const T* __restrict__ h = Hd + (size_t)cam * (D * D) + k * D;
+    const T* __restrict__ pi = p + (size_t)cam * D;
+    const size_t o = (size_t)cam * D + k;
+    T v = T(0);
+#pragma unroll
+    for (int c = 0; c < D; ++c) v += h[c] * pi[c];
+    if (PEER) {
+      T ysum = T(0);
+      for (int src = 0; src < px.world; ++src) ysum += __ldcg(peer_slot<T>(px, px.rank, parity, src) + o);
+      v -= ysum;
+    } else {
+      v -= y[o];
+    }
+    q[o] = v;
+    s = (double)v * (double)pi[k];
   }
   s = block_sum(s);
   publish_pq_last_cta(s, partial, st);
@@ -423,14 +469,18 @@ struct BlockPCG {
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_disabled = false;
   const T* g_E = nullptr; const T* g_Hd = nullptr; const T* g_Minv = nullptr; double g_tol2 = 0.0; int64_t g_units = -1;
+  const void* g_peer_base = nullptr;   // the graph bakes the exchange pointers in
 
   ~BlockPCG() {
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     if (h_state) cudaFreeHost(h_state);
   }
 
-  void resize(int n, int64_t n_off, int64_t n_chunks) {
+  // `comm` (may be NULL): every rank calls resize with the same n, so the peer exchange can be
+  // (re)sized collectively here
+  void resize(int n, int64_t n_off, int64_t n_chunks, isfm_comm* comm = nullptr, cudaStream_t s = 0) {
     n_cam = n;
+    if (comm_world(comm) > 1) comm_peer_ensure(comm, (size_t)n * D * sizeof(T), s);
     size_t len = (size_t)n * D;
     x.alloc(len); r.alloc(len); z.alloc(len); p.alloc(len); q.alloc(len); y.alloc(len);
     yup.alloc((size_t)std::max<int64_t>(n_chunks, 1) * D);
@@ -450,8 +500,10 @@ struct BlockPCG {
             KernelTimers& kt, int* status_out) {
     const int nb = div_up(n_cam, PCG_TPB);
     const int nb_upd = div_up(n_cam, UPD_TPB / D), nb_dir = div_up((int64_t)n_cam * D, PCG_TPB);
-    const int nb_comb = (n_cam + 1) / 2;
+    const int nb_comb = (n_cam + 1) / 2, nb_diag = div_up(n_cam, PCG_TPB / D);
     const bool multi = comm_world(comm) > 1;
+    const bool peer = multi && comm->peer_ready && (size_t)n_cam * D * sizeof(T) <= comm->px.slot_bytes;
+    const PeerExchange px = peer ? comm->px : PeerExchange{};
     const bool merged = (int64_t)n_cam * D <= 4096;   // the last CTA of the update kernel also builds p
     { TimerScope ts(kt, T_PCG_VEC);
       pcg_init_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, b, Minv, x.get(), r.get(), p.get(), part_a.get(), part_b.get()); }
@@ -465,16 +517,23 @@ struct BlockPCG {
             p.get(), yup.get(), C.get(), state.get()); }
       if (!multi) {
         TimerScope ts(kt, T_PCG_VEC);
-        pcg_combine_kernel<T, D, true><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(),
-                                                                   C.get(), Hd, p.get(), q.get(), part_pq.get(), state.get());
+        pcg_combine_kernel<T, D, COMB_FUSED><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(),
+                                                                         C.get(), Hd, p.get(), q.get(), part_pq.get(), state.get(), px);
+      } else if (peer) {
+        // all-reduce of y over peer memory: pushed by the combine epilogue, summed by the next kernel
+        { TimerScope ts(kt, T_PCG_VEC);
+          pcg_combine_kernel<T, D, COMB_PUSH><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(),
+                                                                          C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get(), px); }
+        { TimerScope ts(kt, T_COMM);
+          pcg_apply_diag_kernel<T, D, true><<<nb_diag, PCG_TPB, 0, s>>>(n_cam, Hd, p.get(), y.get(), q.get(), part_pq.get(), state.get(), px); }
       } else {
         { TimerScope ts(kt, T_PCG_VEC);
-          pcg_combine_kernel<T, D, false><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(),
-                                                                      C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get()); }
+          pcg_combine_kernel<T, D, COMB_PLAIN><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(),
+                                                                           C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get(), px); }
         { TimerScope ts(kt, T_COMM);
           comm_allreduce_sum(comm, y.get(), (size_t)n_cam * D, sizeof(T) == 8, s); }
         { TimerScope ts(kt, T_PCG_VEC);
-          pcg_apply_diag_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, Hd, p.get(), y.get(), q.get(), part_pq.get(), state.get()); }
+          pcg_apply_diag_kernel<T, D, false><<<nb_diag, PCG_TPB, 0, s>>>(n_cam, Hd, p.get(), y.get(), q.get(), part_pq.get(), state.get(), px); }
       }
       if (merged) {
         TimerScope ts(kt, T_PCG_VEC);
@@ -489,10 +548,12 @@ struct BlockPCG {
                                                                state.get(), cond, use_cond); }
       }
     };
-    const int vec_per_iter = merged ? 2 : 3;
-    // Single rank, no per-kernel timing: device-side WHILE graph.
-    bool use_graph = !multi && !kt.enabled && !graph_disabled && !getenv("ISFM_NO_GRAPH");
-    if (use_graph && !(graph_exec && g_E == E && g_Hd == Hd && g_Minv == Minv && g_tol2 == tol2 && g_units == sp.n_chunks)) {
+    const int vec_per_iter = (merged ? 2 : 3) + (multi ? 1 : 0);
+    // No per-kernel timing and no NCCL call inside the loop (single rank, or the peer-memory
+    // exchange): device-side WHILE graph.
+    bool use_graph = (!multi || peer) && !kt.enabled && !graph_disabled && !getenv("ISFM_NO_GRAPH");
+    if (use_graph && !(graph_exec && g_E == E && g_Hd == Hd && g_Minv == Minv && g_tol2 == tol2 && g_units == sp.n_chunks &&
+                       g_peer_base == (peer ? (const void*)comm->px.base[0] : nullptr))) {
       if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
       const int64_t lc = g_launch_count;
       int64_t saved[ISFM_N_TIMERS];
@@ -523,6 +584,7 @@ struct BlockPCG {
       g_launch_count = lc;                       // captured, not executed
       for (int i = 0; i < ISFM_N_TIMERS; ++i) kt.launches[i] = saved[i];
       g_E = E; g_Hd = Hd; g_Minv = Minv; g_tol2 = tol2; g_units = sp.n_chunks;
+      g_peer_base = peer ? (const void*)comm->px.base[0] : nullptr;
       use_graph = graph_exec != nullptr;
     }
     h_state->done = 0; h_state->iters = 0;
@@ -546,6 +608,7 @@ struct BlockPCG {
       }
     }
     ISFM_CUDA(cudaGetLastError());
+    if (h_state->done == 3) throw IsfmError(ISFM_ENCCL, "peer-memory exchange timed out waiting for a rank (PCG)");
     if (status_out) *status_out = h_state->done;
     return h_state->iters;
   }

@@ -71,6 +71,12 @@ class Communicator:
         check(lib.isfm_comm_create(ident, rank, world, byref(self.handle)))
         self.rank, self.world = rank, world
 
+    @property
+    def peer_enabled(self):
+        """True once the per-iteration sums travel over the peer-memory exchange (NVLink, CUDA
+        IPC) instead of ncclAllReduce; decided at the first set_problem on this communicator."""
+        return bool(self.handle) and bool(_lib.load().isfm_comm_peer_enabled(self.handle))
+
     def close(self):
         if self.handle:
             _lib.load().isfm_comm_destroy(self.handle)

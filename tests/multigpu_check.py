@@ -77,8 +77,11 @@ def main():
         ls, _ = single.step()
         assert abs(lm - ls) <= 1e-8 * ls, ("gp", it, lm, ls)
     dist.barrier()
+    want_peer = not os.environ.get("ISFM_NO_PEER")
+    if os.environ.get("ISFM_REQUIRE_PEER"):
+        assert comm.peer_enabled == want_peer, "peer-memory exchange was expected to be %s" % ("on" if want_peer else "off")
     if rank == 0:
-        print("MULTIGPU_OK world", world)
+        print("MULTIGPU_OK world", world, "transport", "peer" if comm.peer_enabled else "nccl")
     dist.destroy_process_group()
 
 

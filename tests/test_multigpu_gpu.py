@@ -8,12 +8,20 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_two_rank_solve_matches_single_rank():
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_two_rank_solve_matches_single_rank(transport):
+    """Both transports of the per-iteration sum (peer-memory exchange fused into the PCG kernels,
+    ncclAllReduce) must reproduce the single-rank solve."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29531", os.path.join(here, "multigpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    env.pop("ISFM_NO_PEER", None)
+    if transport == "nccl":
+        env["ISFM_NO_PEER"] = "1"
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and "MULTIGPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    assert ("transport " + transport) in out.stdout, out.stdout[-2000:]
