@@ -44,8 +44,8 @@ UNIT = "obs/s"
 CPU_SAMPLE_SCALE = 0.02   # cpu_baseline: config with points/observations scaled by this factor
 # dram__bytes_read.sum + dram__bytes_write.sum per launch on config C3 (1 GPU, full size), from the
 # `ncu --set full` captures summarised in profiles/r1_ncu_full_summary.txt (ncu cannot run inside the bench)
-NCU_TRAFFIC_C3 = {"pcg_spmv": 578.9e6, "schur_offdiag": 2888.7e6, "linearize": 798.6e6, "camera_blocks": 783.9e6,
-                  "backsub": 801.9e6}
+NCU_TRAFFIC_C3 = {"pcg_spmv": 535.1e6, "schur_offdiag": 2887.5e6, "linearize": 787.2e6, "camera_blocks": 664.7e6,
+                  "backsub": 800.7e6}
 
 
 def _peaks():
@@ -90,7 +90,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.002)   # the timed region is ~50 ms: sample every ~2 ms
 
     def start(self):
         if self.nv is not None:

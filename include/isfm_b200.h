@@ -227,6 +227,33 @@ int isfm_gp_cost(isfm_gp* h, double* robust_cost_out, double* sq_cost_out);
 int isfm_gp_get_timers(isfm_gp* h, double ms_out[ISFM_N_TIMERS], int64_t launches_out[ISFM_N_TIMERS]);
 int isfm_gp_reset_timers(isfm_gp* h, int32_t enable);
 
+/* ------------------------------------------------------------------------------------ */
+/* inter-BA track filters (instantsfm/processors/track_filter.py).       */
+/* Stateless; every pointer may be host or device memory (host arrays are staged); fp64   */
+/* like the reference's numpy.  image_ids / track_idx are the flattened (image_id, index  */
+/* of the track in dict order) of every observation, in the reference's loop order.       */
+/* ------------------------------------------------------------------------------------ */
+typedef enum isfm_filter_mode {
+  ISFM_FILTER_ANGLE = 0,                   /* FilterTracksByAngle, track_filter.py:5-24:
+                                              threshold = cos(deg2rad(max_angle_error))      */
+  ISFM_FILTER_REPROJECTION_NORMALIZED = 1  /* FilterTracksByReprojectionNormalized :26-66:
+                                              threshold = max_reprojection_error             */
+} isfm_filter_mode;
+/* world2cam [n_img,4,4] row-major, xyz [n_trk,3], features_undist [n_obs,3] (the bearing of
+ * each observation, Image.features_undist[feature_id]); valid_out[n_obs] = 1 keeps it.    */
+int isfm_filter_observations(int32_t mode, int64_t n_obs, int64_t n_img, int64_t n_trk,
+                             const double* world2cam, const double* xyz,
+                             const double* features_undist, const int32_t* image_ids,
+                             const int32_t* track_idx, double threshold, uint8_t* valid_out,
+                             void* stream);
+/* FilterTracksTriangulationAngle, track_filter.py:116-137.  track_off[n_trk+1] is the CSR
+ * of image_ids[n_obs] by track; centers [n_img,3] = Image.center(); cos_threshold =
+ * cos(deg2rad(min_angle)); remove_out[n_trk] = 1 where the reference deletes the track.   */
+int isfm_filter_triangulation_angle(int64_t n_trk, int64_t n_obs, int64_t n_img,
+                                    const int64_t* track_off, const int32_t* image_ids,
+                                    const double* centers, const double* xyz,
+                                    double cos_threshold, uint8_t* remove_out, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

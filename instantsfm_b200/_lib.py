@@ -74,6 +74,10 @@ SIGNATURES = {
     "isfm_gp_cost": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "isfm_gp_get_timers": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64)]),
     "isfm_gp_reset_timers": (c_int, [c_void_p, c_int32]),
+    "isfm_filter_observations": (c_int, [c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_double, c_void_p, c_void_p]),
+    "isfm_filter_triangulation_angle": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                                                c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -7,6 +7,8 @@
 #include <cstdlib>
 
 #include "ba_kernels.cuh"
+#include <chrono>
+
 #include "comm.cuh"
 #include "index_prep.cuh"
 #include "pcg.cuh"
@@ -113,6 +115,16 @@ struct BASolver : BASolverBase {
                    const void* obs_in, const int32_t* cam_idx, const int32_t* pt_idx) override {
     ISFM_REQUIRE(cam_in && pp_in && pts_in && obs_in && cam_idx && pt_idx, ISFM_EINVAL, "null input");
     n_cam = nc; n_pt = np; n_obs = no;
+    // ISFM_DEBUG_SETUP=1: wall-clock per set-up phase (each mark synchronises the stream)
+    const bool dbg_setup = getenv("ISFM_DEBUG_SETUP") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+      if (!dbg_setup) return;
+      cudaStreamSynchronize(s);
+      auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[isfm setup] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+      t_last = now;
+    };
     upload(cam[0], cam_in, (size_t)nc * CW); cam[1].alloc((size_t)nc * CW);
     upload(pts[0], pts_in, (size_t)np * 3); pts[1].alloc((size_t)np * 3);
     upload(pp, pp_in, (size_t)nc * 2);
@@ -121,25 +133,31 @@ struct BASolver : BASolverBase {
     DeviceBuffer<T> obs_raw; DeviceBuffer<int32_t> ci, pi;
     upload(obs_raw, obs_in, (size_t)no * 2);
     upload(ci, cam_idx, (size_t)no); upload(pi, pt_idx, (size_t)no);
+    mark("alloc + H2D");
     build_obs_index(ix, nc, np, no, ci.get(), pi.get(), s, timers);
+    mark("build_obs_index (sorts, CSR)");
     obs.alloc((size_t)no * 2);
     { TimerScope ts(timers, T_INDEX_PREP);
       gather_rows_kernel<T><<<div_up(no * 2, BA_TPB), BA_TPB, 0, s>>>(no, 2, obs_raw.get(), ix.obs_perm.get(), obs.get()); }
     R.alloc((size_t)no * 2); OBS.alloc((size_t)no * REC);
     HPP.alloc((size_t)np * 6); GPT.alloc((size_t)np * 3); HPPINV.alloc((size_t)np * 6); TP.alloc((size_t)np * 3);
     DP.alloc((size_t)np * 3);
+    mark("obs gather + allocs");
     build_fused_partition();
+    mark("fused tile partition");
     if (getenv("ISFM_NO_FUSED")) fused_ok = false;
     const int64_t n_part = std::max<int64_t>(std::max<int64_t>(RED_BLOCKS, nc), n_fused_cta);
     part_a.alloc(n_part); part_b.alloc(n_part); part_c.alloc(n_part);
     scalars.alloc(4); fail.alloc(1); fail.zero(s);
     if (desc.optimize_poses) {
       build_schur_pattern(sp, ix, s, timers);
+      mark("build_schur_pattern");
       HCC_GC.alloc((size_t)nc * (D * D + D)); HD.alloc((size_t)nc * D * D);
       E.alloc((size_t)sp.nnzu * D * D); E.zero(s);   // padding slots stay zero
       HME.alloc((size_t)nc * (D * D + 2 * D));
       MINV.alloc((size_t)nc * D * D); bvec.alloc((size_t)nc * D); DCQ.alloc((size_t)nc * BacksubCfg<T, D>::DQ);
       pcg.resize((int)nc, sp.n_off, sp.n_chunks, comm, s);
+      mark("Schur / PCG allocs + E.zero");
     }
     ISFM_CUDA(cudaStreamSynchronize(s));
     cur = 0; have_loss = false; has_problem = true;

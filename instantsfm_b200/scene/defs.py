@@ -82,6 +82,10 @@ class Image:
         self.depths = [] if depths is None else depths
         self.features_undist = [] if features_undist is None else features_undist
 
+    def center(self):
+        """scene/defs.py:35-36."""
+        return self.world2cam[:3, :3].T @ -self.world2cam[:3, 3]
+
 
 class Track:
     def __init__(self, **kwargs):

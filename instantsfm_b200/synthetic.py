@@ -408,3 +408,51 @@ def gp_arrays_to_scene(g, seed=0):
         tracks[5 + 2 * p] = Track(id=5 + 2 * p, xyz=g.points_3d[p].copy(),
                                   observations=np.stack([g.camera_indices[sl].astype(np.int64), feat_id[sl]], axis=1))
     return cameras, images, tracks
+
+
+def make_filter_scene(n_img=12, n_trk=300, mean_len=4.0, seed=0, outlier_frac=0.15, behind_frac=0.05):
+    """Seeded scene for the track filters (processors/track_filter.py): images with poses and unit
+    bearings (``features_undist``), tracks with points and (image_id, feature_id) observations.
+    Bearings are the exact direction of the point in the camera plus noise; a fraction are gross
+    outliers, a fraction of the points sit behind one of their cameras, some tracks have a single
+    view, one is empty, one sees the same image twice.  Returns (cameras, images, tracks)."""
+    from .scene.defs import Image, Track
+    rng = np.random.default_rng(seed)
+    images = []
+    for i in range(n_img):
+        ang = 2 * np.pi * i / n_img
+        c = np.array([12 * np.cos(ang), 12 * np.sin(ang), rng.normal(0, 0.5)])
+        z = -c / np.linalg.norm(c) + rng.normal(0, 0.05, 3)
+        z /= np.linalg.norm(z)
+        x = np.cross([0, 0, 1.0], z); x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        R = np.stack([x, y, z], 0)
+        w2c = np.eye(4); w2c[:3, :3] = R; w2c[:3, 3] = -R @ c
+        images.append(Image(id=i, cam_id=0, is_registered=True, world2cam=w2c, features_undist=[]))
+    feats = [[] for _ in range(n_img)]
+    tracks = {}
+    for t in range(n_trk):
+        X = rng.normal(0, 2.0, 3)
+        far = rng.random() < 0.2
+        if far:   # far points: small triangulation angles
+            X = X / np.linalg.norm(X) * rng.uniform(300, 3000)
+        k = 0 if t == 7 else (1 if t % 23 == 0 else min(n_img, 2 + rng.geometric(1.0 / max(mean_len - 1.0, 1.0))))
+        ids = rng.choice(n_img, size=k, replace=False) if not far else (rng.integers(0, n_img) + np.arange(k)) % n_img
+        if t == 11 and k >= 2:
+            ids[1] = ids[0]   # the same image twice in one track
+        if k and rng.random() < behind_frac:
+            c = images[ids[0]].center()
+            X = c + (c - X) * 0.5   # behind (or very near) the first camera
+        obs = []
+        for i in ids:
+            p = images[i].world2cam[:3, :3] @ X + images[i].world2cam[:3, 3]
+            b = p / np.linalg.norm(p) + rng.normal(0, 2e-3, 3)
+            if rng.random() < outlier_frac:
+                b = b + rng.normal(0, 0.2, 3)
+            b /= np.linalg.norm(b)
+            obs.append((int(i), len(feats[i])))
+            feats[i].append(b)
+        tracks[1000 + 3 * t] = Track(id=1000 + 3 * t, xyz=X, observations=np.array(obs, dtype=np.int64).reshape(-1, 2))
+    for i, img in enumerate(images):
+        img.features_undist = np.array(feats[i]).reshape(-1, 3)
+    return [], images, tracks

@@ -17,12 +17,16 @@ if [ "$TESTS" = tests ]; then
 fi
 timeout 600 python bench.py --steps 10 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench exit $?"
 cat "$OUT/bench.json" | head -c 600; echo
+timeout 300 python tools/filter_bench.py > "$OUT/filter_bench.json" 2> "$OUT/filter_bench.err"; echo "filter_bench exit $?"; cat "$OUT/filter_bench.json"
+# ncu cannot see kernel nodes inside a graph with conditional nodes: the profiled runs launch the PCG
+# iterations as plain stream launches (ISFM_NO_GRAPH=1, same kernels, host polls every 8 iterations)
+export ISFM_NO_GRAPH=1
 timeout 300 python tools/prof_run.py > "$OUT/prof_run.log" 2>&1; PR=$?; echo "prof_run exit $PR"
 if [ $PR -eq 0 ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$OUT/launches.csv" \
     python tools/prof_run.py > "$OUT/ncu_launch.log" 2>&1; echo "launch list exit $?"
   for k in "${KERNELS[@]}"; do
-    timeout 400 ncu --set full --clock-control none --import-source on -k "regex:$k" -s 1 -c 1 -f -o "$OUT/full_$k" \
+    timeout 400 ncu --set full --clock-control none --import-source on -k "regex:$k" -s 2 -c 1 -f -o "$OUT/full_$k" \
       python tools/prof_run.py > "$OUT/ncu_$k.log" 2>&1; echo "ncu $k exit $?"
   done
 fi
