@@ -198,6 +198,7 @@ def main_ours(args):
     eng = BAEngine(a.model_id, dtype=dtype, comm=comm)
     eng.set_problem(*pinned_np)
     pat = eng.schur_pattern()
+    mv_owned, mv_total = eng.matvec_units()
     for _ in range(args.warmup):
         eng.step()
     saved_params = eng.get_params()
@@ -248,6 +249,8 @@ def main_ours(args):
         eff = pcg_iters_prof if name == "pcg_spmv" else t["launches"]
         per_launch_ms = t["ms"] / max(eff, 1)
         ab = algorithmic_bytes(name, a.n_obs, a.n_pt, a.n_cam, d, pat["n_pairs"], (pat["nnzb"] - a.n_cam) // 2, pat["nnzb"])
+        if name == "pcg_spmv":
+            ab *= mv_owned / max(mv_total, 1)   # split mat-vec: this rank streams only its own unit range
         kernels[name] = {"ms_per_step": t["ms"] / prof_steps, "launches_per_step": t["launches"] / prof_steps,
                          "us_per_launch": per_launch_ms * 1e3,
                          "achieved_gbs": (ab / (per_launch_ms * 1e-3) / 1e9) if ab and per_launch_ms > 0 else None}
@@ -301,7 +304,12 @@ def main_ours(args):
                            "pcg_tol": 1e-6, "schur_blocks": pat["nnzb"], "schur_pairs": pat["n_pairs"]},
                 "lm_iters_per_sec": args.steps / (ms_total * 1e-3), "final_rmse_px": rmse, "final_robust_cost": rob,
                 "pcg_iters_per_step": float(np.mean([s["pcg_iters"] for s in stats])),
+                "pcg_iters": [int(s["pcg_iters"]) for s in stats], "losses": [float(x) for x in losses],
                 "rejects": int(sum(s["rejects"] for s in stats)),
+                "matvec_split": (None if world == 1 else {"units_owned_rank0": mv_owned, "units_total": mv_total,
+                                                          "note": "identical block pattern on every rank: summed E reduce-scattered by unit "
+                                                                  "ranges once per trial, each rank multiplies its own range"
+                                                                  if mv_owned < mv_total else "every rank multiplies its own partial E_g"}),
                 "pcg_exchange": (None if world == 1 else ("peer-memory push over NVLink fused into the PCG kernels (device-side WHILE graph)"
                                                           if comm.peer_enabled else "ncclAllReduce per iteration")),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,

@@ -160,6 +160,11 @@ int isfm_ba_get_structure(isfm_ba* h, int32_t* obs_perm, int64_t* point_offsets,
 int isfm_ba_get_schur_pattern(isfm_ba* h, int64_t* nnzb_out, int64_t* n_pairs_out,
                               int64_t* row_ptr, int32_t* col_idx);
 
+/* Mat-vec work units of the reduced camera system this rank multiplies per PCG iteration and
+ * their total: equal unless the ranks share one block pattern and the summed matrix has been
+ * split across them ("split mat-vec").                                */
+int isfm_ba_get_matvec_units(isfm_ba* h, int64_t* owned_out, int64_t* total_out);
+
 /* Kernel-level outputs for parity tests, in the ORIGINAL observation / point / camera
  * order.  `what` selects the buffer; `dst` must hold the documented element count of the
  * handle's dtype.  Runs the producing kernels at the current parameters and damping.      */

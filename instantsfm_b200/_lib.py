@@ -60,6 +60,7 @@ SIGNATURES = {
     "isfm_ba_cost": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "isfm_ba_get_structure": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "isfm_ba_get_schur_pattern": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p, c_void_p]),
+    "isfm_ba_get_matvec_units": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "isfm_ba_debug_get": (c_int, [c_void_p, c_int32, c_void_p]),
     "isfm_ba_get_timers": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64)]),
     "isfm_ba_reset_timers": (c_int, [c_void_p, c_int32]),

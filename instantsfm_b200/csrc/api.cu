@@ -76,6 +76,14 @@ void isfm_ba_destroy(isfm_ba* h) {
   delete h;
 }
 
+int isfm_ba_get_matvec_units(isfm_ba* h, int64_t* owned_out, int64_t* total_out) {
+  ISFM_TRY
+  ISFM_REQUIRE(h && h->impl, ISFM_EINVAL, "isfm_ba_get_matvec_units: null handle");
+  if (owned_out) *owned_out = h->impl->matvec_units_owned;
+  if (total_out) *total_out = h->impl->matvec_units_total;
+  ISFM_CATCH
+}
+
 int isfm_ba_set_problem(isfm_ba* h, int64_t n_cam, int64_t n_pt, int64_t n_obs, const void* cam, const void* pp,
                         const void* pts, const void* obs, const int32_t* cam_idx, const int32_t* pt_idx) {
   ISFM_TRY

@@ -48,6 +48,7 @@ struct BASolverBase {
   virtual void debug_get(int what, void* dst) = 0;
   KernelTimers timers;
   bool has_problem = false;
+  int64_t matvec_units_owned = 0, matvec_units_total = 0;   // isfm_ba_get_matvec_units
 };
 
 template <typename T, int MODEL>
@@ -80,6 +81,14 @@ struct BASolver : BASolverBase {
   bool fused_ok = false;      // every track fits one CTA of the fused K1 (<= FUSED_TPB observations)
   int n_fused_cta = 0;        // tiles of whole points with <= FUSED_TPB observations
   DeviceBuffer<int4> fused_tiles;   // {first point, end point, first observation, observations} per CTA
+  // Multi-rank, identical block pattern on every rank (dense co-visibility): the summed E is
+  // reduce-scattered by ranges of mat-vec units once per trial and each rank multiplies only its
+  // own range in every PCG iteration (see setup_matvec_split).
+  bool split_matvec = false;
+  int64_t unit_lo = 0, unit_hi = -1;
+  std::vector<size_t> split_off, split_cnt;   // element ranges of E per owner rank
+  DeviceBuffer<T> E_own;                      // sum over ranks of this rank's range of E
+  bool union_pattern = false;                 // the block pattern is the union over ranks (zero blocks where no local pairs)
   double min_damping = 0.0;   // floor on the LM damping used to build the systems (see DESIGN.md, fp32 conditioning)
 
   explicit BASolver(const isfm_ba_desc& d) : desc(d) {
@@ -150,18 +159,113 @@ struct BASolver : BASolverBase {
     part_a.alloc(n_part); part_b.alloc(n_part); part_c.alloc(n_part);
     scalars.alloc(4); fail.alloc(1); fail.zero(s);
     if (desc.optimize_poses) {
-      build_schur_pattern(sp, ix, s, timers);
+      UnionKeys hook(this);
+      build_schur_pattern(sp, ix, s, timers, comm_world(comm) > 1 ? &hook : nullptr);
       mark("build_schur_pattern");
       HCC_GC.alloc((size_t)nc * (D * D + D)); HD.alloc((size_t)nc * D * D);
       E.alloc((size_t)sp.nnzu * D * D); E.zero(s);   // padding slots stay zero
       HME.alloc((size_t)nc * (D * D + 2 * D));
       MINV.alloc((size_t)nc * D * D); bvec.alloc((size_t)nc * D); DCQ.alloc((size_t)nc * BacksubCfg<T, D>::DQ);
       pcg.resize((int)nc, sp.n_off, sp.n_chunks, comm, s);
+      setup_matvec_split();
+      matvec_units_total = sp.n_chunks;
+      matvec_units_owned = split_matvec ? unit_hi - unit_lo : sp.n_chunks;
       mark("Schur / PCG allocs + E.zero");
     }
     ISFM_CUDA(cudaStreamSynchronize(s));
     cur = 0; have_loss = false; has_problem = true;
     tr.init(desc.tr_radius, desc.tr_max, desc.tr_up, desc.tr_down);
+  }
+
+  // Multi-rank pattern hook: all-gathers every rank's block keys; when the ranks' patterns
+  // overlap heavily (sum of the local block counts >= 1.5 x the size of their union: dense
+  // co-visibility) every rank builds the UNION pattern so that the mat-vec can be split
+  // (setup_matvec_split); otherwise each rank keeps its own local pattern (Variant N).
+  // COLLECTIVE; ISFM_SPLIT_MATVEC=0 disables, =1 forces the union.
+  struct UnionKeys : PatternKeyHook {
+    BASolver* self;
+    explicit UnionKeys(BASolver* s_) : self(s_) {}
+    int64_t extra_keys(const uint64_t* list_key, int64_t n_lists, int64_t n_cam, DeviceBuffer<uint64_t>& out,
+                       cudaStream_t s) override {
+      isfm_comm* comm = self->comm;
+      self->union_pattern = false;
+      const int world = comm_world(comm), rank = comm_rank(comm);
+      const char* env = getenv("ISFM_SPLIT_MATVEC");
+      if (world <= 1 || (env && atoi(env) == 0)) return 0;
+      // counts of every rank (exact in fp64)
+      std::vector<double> cnt((size_t)world, 0.0);
+      cnt[rank] = (double)n_lists;
+      DeviceBuffer<double> d_cnt; d_cnt.alloc(world);
+      ISFM_CUDA(cudaMemcpyAsync(d_cnt.get(), cnt.data(), world * sizeof(double), cudaMemcpyHostToDevice, s));
+      comm_allreduce_sum(comm, d_cnt.get(), world, true, s);
+      ISFM_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt.get(), world * sizeof(double), cudaMemcpyDeviceToHost, s));
+      ISFM_CUDA(cudaStreamSynchronize(s));
+      int64_t max_cnt = 0, sum_cnt = 0;
+      for (double c : cnt) { max_cnt = std::max<int64_t>(max_cnt, (int64_t)c); sum_cnt += (int64_t)c; }
+      if (max_cnt == 0) return 0;
+      DeviceBuffer<uint64_t> mine;
+      mine.alloc(max_cnt); out.alloc((size_t)max_cnt * world);
+      ISFM_CUDA(cudaMemsetAsync(mine.get(), 0xff, (size_t)max_cnt * sizeof(uint64_t), s));   // padding: ~0 = ignored
+      if (n_lists > 0) ISFM_CUDA(cudaMemcpyAsync(mine.get(), list_key, (size_t)n_lists * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+      comm_allgather_bytes(comm, mine.get(), out.get(), (size_t)max_cnt * sizeof(uint64_t), s);
+      const int64_t n_union = count_unique_upper_keys(out.get(), max_cnt * world, n_cam, s);
+      const bool overlap = (double)sum_cnt >= 1.5 * (double)std::max<int64_t>(n_union, 1);
+      if (!(env ? atoi(env) != 0 : overlap)) { out.release(); return 0; }
+      self->union_pattern = true;
+      return max_cnt * world;
+    }
+  };
+
+  // Variant R of SURVEY 8(e), for the case where it pays: when every rank has the SAME block
+  // pattern (BAL-like scenes: every camera pair co-observes points of every shard), each rank's
+  // partial E_g is a full-size matrix and Variant N makes every rank stream all of it in every
+  // PCG iteration -- the mat-vec, 70 % of a step, would not scale at all.  Instead the mat-vec
+  // units are cut into `world` contiguous ranges of (almost) equal slot counts; once per trial
+  // the ranks sum E range by range into the owner (comm_reduce_ranges) and every PCG iteration
+  // multiplies 1 / world of the matrix per rank.  The per-iteration exchange of y is unchanged:
+  // partials and deposits of the units a rank does not own stay zero.
+  // COLLECTIVE: every rank takes the same decision (signatures are compared through an all-reduce).
+  void setup_matvec_split() {
+    split_matvec = false; unit_lo = 0; unit_hi = -1;
+    const int world = comm_world(comm), rank = comm_rank(comm);
+    if (world <= 1) return;
+    const char* env = getenv("ISFM_SPLIT_MATVEC");   // "0": never, "1": whenever the patterns agree
+    uint64_t sig[2];
+    schur_pattern_signature(sp, n_cam, s, sig);
+    // every rank writes its (nnzu, n_chunks, hash, hash) into its own row of a zero table; after
+    // the sum every rank holds every row (all values < 2^48: exact in fp64)
+    std::vector<double> table((size_t)world * 4, 0.0);
+    table[(size_t)rank * 4 + 0] = (double)sp.nnzu; table[(size_t)rank * 4 + 1] = (double)sp.n_chunks;
+    table[(size_t)rank * 4 + 2] = (double)sig[0]; table[(size_t)rank * 4 + 3] = (double)sig[1];
+    DeviceBuffer<double> d_table;
+    d_table.alloc(table.size());
+    ISFM_CUDA(cudaMemcpyAsync(d_table.get(), table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    comm_allreduce_sum(comm, d_table.get(), table.size(), true, s);
+    ISFM_CUDA(cudaMemcpyAsync(table.data(), d_table.get(), table.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));
+    bool same = true;
+    for (int r = 1; r < world; ++r)
+      for (int k = 0; k < 4; ++k) same = same && table[(size_t)r * 4 + k] == table[k];
+    const bool worth = (size_t)sp.nnzu * D * D * sizeof(T) >= ((size_t)8 << 20);   // below that the reduce costs more than it saves
+    if (!same || (env ? atoi(env) == 0 : !(worth || union_pattern)) || sp.n_chunks < world) return;
+    // unit boundaries: first unit whose first slot >= r * nnzu / world
+    std::vector<int64_t> ub((size_t)world + 1);
+    int64_t u = 0;
+    for (int r = 0; r <= world; ++r) {
+      const int64_t target = (int64_t)((__int128)r * sp.nnzu / world);
+      while (u < sp.n_chunks && sp.h_chunk_beg[(size_t)u] < target) ++u;
+      ub[r] = (r == world) ? sp.n_chunks : u;
+    }
+    split_off.assign(world, 0); split_cnt.assign(world, 0);
+    for (int r = 0; r < world; ++r) {
+      const int64_t lo = ub[r] < sp.n_chunks ? sp.h_chunk_beg[(size_t)ub[r]] : sp.nnzu;
+      const int64_t hi = ub[r + 1] < sp.n_chunks ? sp.h_chunk_beg[(size_t)ub[r + 1]] : sp.nnzu;
+      split_off[r] = (size_t)lo * D * D; split_cnt[r] = (size_t)(hi - lo) * D * D;
+    }
+    unit_lo = ub[rank]; unit_hi = ub[rank + 1];
+    pcg.yup.zero(s); pcg.C.zero(s);   // never written for the units of other ranks
+    E_own.alloc(std::max<size_t>(split_cnt[rank], 1));
+    split_matvec = true;
   }
 
   void pack_cameras(int which) {
@@ -275,12 +379,18 @@ struct BASolver : BASolverBase {
       TimerScope ts(timers, T_COMM);
       comm_allreduce_sum(comm, HME.get(), (size_t)n_cam * (D * D + 2 * D), sizeof(T) == 8, s);
     }
+    if (split_matvec) {
+      TimerScope ts(timers, T_COMM);
+      comm_reduce_ranges(comm, E.get(), E_own.get(), split_off.data(), split_cnt.data(), sizeof(T) == 8, s);
+    }
     { TimerScope ts(timers, T_PRECOND);
       precond_kernel<T, D><<<div_up(n_cam, 64), 64, 0, s>>>((int)n_cam, HME.get(), mu, HD.get(), MINV.get(), bvec.get(),
                                                             fail.get()); }
     int max_iter = desc.pcg_max_iter > 0 ? desc.pcg_max_iter : (int)std::min<int64_t>(10 * n_cam * D, 5000);
-    return pcg.solve(sp, E.get(), HD.get(), MINV.get(),
-                     bvec.get(), desc.pcg_tol, max_iter, comm, s, timers, pcg_status);
+    // split mat-vec: the kernel indexes blocks by their global slot, E_own starts at this rank's first slot
+    const T* Emat = split_matvec ? E_own.get() - split_off[comm_rank(comm)] : E.get();
+    return pcg.solve(sp, Emat, HD.get(), MINV.get(),
+                     bvec.get(), desc.pcg_tol, max_iter, comm, s, timers, pcg_status, unit_lo, unit_hi);
   }
 
   void step(double* loss_out, isfm_step_stats* st) override {

@@ -17,6 +17,9 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -37,6 +40,9 @@ NcclApi& api() {
   LOAD(CommDestroy, "ncclCommDestroy");
   LOAD(AllReduce, "ncclAllReduce");
   LOAD(AllGather, "ncclAllGather");
+  LOAD(Reduce, "ncclReduce");
+  LOAD(GroupStart, "ncclGroupStart");
+  LOAD(GroupEnd, "ncclGroupEnd");
   LOAD(GetErrorString, "ncclGetErrorString");
 #undef LOAD
   return a;
@@ -53,6 +59,27 @@ void comm_allreduce_sum(isfm_comm* comm, void* buf, size_t count, bool is_double
   g_launch_count++;
   check(api().AllReduce(buf, buf, count, is_double ? ncclDouble : ncclFloat, ncclSum,
                         static_cast<ncclComm_t>(comm->nccl_comm), stream), "ncclAllReduce");
+}
+
+void comm_reduce_ranges(isfm_comm* comm, const void* buf, void* own_out, const size_t* elem_off, const size_t* elem_cnt,
+                        bool is_double, cudaStream_t stream) {
+  if (!comm || comm->world <= 1) return;
+  const size_t es = is_double ? 8 : 4;
+  g_launch_count++;
+  check(api().GroupStart(), "ncclGroupStart");
+  for (int r = 0; r < comm->world; ++r) {
+    if (elem_cnt[r] == 0) continue;
+    const void* p = static_cast<const unsigned char*>(buf) + elem_off[r] * es;
+    check(api().Reduce(p, own_out, elem_cnt[r], is_double ? ncclDouble : ncclFloat, ncclSum, r,
+                       static_cast<ncclComm_t>(comm->nccl_comm), stream), "ncclReduce");   // own_out is read at the root only
+  }
+  check(api().GroupEnd(), "ncclGroupEnd");
+}
+
+void comm_allgather_bytes(isfm_comm* comm, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t stream) {
+  ISFM_REQUIRE(comm && comm->world > 1, ISFM_EINVAL, "comm_allgather_bytes without a communicator");
+  g_launch_count++;
+  check(api().AllGather(send, recv, bytes_per_rank, ncclChar, static_cast<ncclComm_t>(comm->nccl_comm), stream), "ncclAllGather");
 }
 
 namespace {

@@ -53,6 +53,14 @@ void comm_allreduce_sum(isfm_comm* comm, void* buf, size_t count, bool is_double
 inline int comm_world(const isfm_comm* c) { return c ? c->world : 1; }
 inline int comm_rank(const isfm_comm* c) { return c ? c->rank : 0; }
 
+// Reduce-scatter over uneven ranges: range r of `buf` ([elem_off[r], elem_off[r] + elem_cnt[r])
+// elements) is summed over all ranks into rank r's `own_out` (elem_cnt[rank] elements); `buf` is
+// not modified (one grouped ncclReduce per range).
+void comm_reduce_ranges(isfm_comm* comm, const void* buf, void* own_out, const size_t* elem_off, const size_t* elem_cnt,
+                        bool is_double, cudaStream_t stream);
+// recv[r * bytes_per_rank ...] = rank r's `send` (ncclAllGather)
+void comm_allgather_bytes(isfm_comm* comm, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t stream);
+
 // COLLECTIVE (every rank, same argument): makes sure the peer exchange exists with at least
 // `slot_bytes` per (parity, source) slot.  Returns false -- on every rank alike -- when peer
 // memory is unavailable (world > ISFM_MAX_PEERS, IPC refused, ISFM_NO_PEER set); the caller then

@@ -85,6 +85,26 @@ __global__ void upper_keys_kernel(const uint64_t* __restrict__ list_key, int64_t
   }
 }
 
+constexpr int64_t EXTRA_TAG = INT64_MIN;   // entry that exists only because another rank has pairs for it
+
+// extra (foreign) keys appended behind the local entries: strictly-upper ones survive
+__global__ void extra_keys_kernel(const uint64_t* __restrict__ extra, int64_t n_extra, int64_t n_cam, uint64_t* keys, int64_t* tags) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_extra) return;
+  const uint64_t k = extra[t];
+  const bool ok = k != ~0ull && k < (uint64_t)n_cam * (uint64_t)n_cam && (k / (uint64_t)n_cam) < (k % (uint64_t)n_cam);
+  keys[t] = ok ? k : ~0ull;
+  tags[t] = EXTRA_TAG;
+}
+
+// after a STABLE sort by key: every entry equal to its predecessor is a duplicate (local entries
+// were ahead of the extras in the input, so the survivor of a run is the local one)
+__global__ void dedupe_keys_kernel(const uint64_t* __restrict__ sorted, int64_t n, uint64_t* out) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  out[t] = (t > 0 && sorted[t] == sorted[t - 1]) ? ~0ull : sorted[t];
+}
+
 __global__ void count_valid_kernel(const uint64_t* __restrict__ keys, int64_t n, unsigned long long* count) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t < n && keys[t] != ~0ull) atomicAdd(count, 1ull);  // set-up only; integer, order-free
@@ -98,6 +118,7 @@ __global__ void upper_scatter_kernel(const uint64_t* __restrict__ keys, const in
   ucol[e] = (int32_t)(k % (uint64_t)n_cam);
   row_of[e] = (int32_t)(k / (uint64_t)n_cam);
   int64_t tag = tags[e];
+  if (tag == EXTRA_TAG) return;   // block of the union pattern without local pairs
   if (tag < 0) diag_slot[-tag - 1] = (int32_t)e;
   else list_slot[tag] = (int32_t)e;
 }
@@ -218,7 +239,22 @@ void build_obs_index(ObsIndex& ix, int64_t n_cam, int64_t n_pt, int64_t n_obs, c
   ISFM_CUDA(cudaStreamSynchronize(s));
 }
 
-void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, KernelTimers& kt) {
+int64_t count_unique_upper_keys(const uint64_t* keys, int64_t n, int64_t n_cam, cudaStream_t s) {
+  if (n <= 0) return 0;
+  DeviceBuffer<uint64_t> a, b; DeviceBuffer<int64_t> ta, tb;
+  a.alloc(n); b.alloc(n); ta.alloc(n); tb.alloc(n);
+  extra_keys_kernel<<<div_up(n, TPB), TPB, 0, s>>>(keys, n, n_cam, a.get(), ta.get());
+  sort_pairs(a.get(), b.get(), ta.get(), tb.get(), n, 64, s);
+  dedupe_keys_kernel<<<div_up(n, TPB), TPB, 0, s>>>(b.get(), n, a.get());
+  DeviceBuffer<unsigned long long> valid; valid.alloc(1); valid.zero(s);
+  count_valid_kernel<<<div_up(n, TPB), TPB, 0, s>>>(a.get(), n, valid.get());
+  unsigned long long c = 0;
+  ISFM_CUDA(cudaMemcpyAsync(&c, valid.get(), sizeof c, cudaMemcpyDeviceToHost, s));
+  ISFM_CUDA(cudaStreamSynchronize(s));
+  return (int64_t)c;
+}
+
+void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, KernelTimers& kt, PatternKeyHook* hook) {
   TimerScope ts(kt, T_INDEX_PREP);
   const int64_t n = ix.n_obs, n_cam = ix.n_cam;
   const int g = div_up(n, TPB);
@@ -276,11 +312,23 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
   }
   sp.n_lists = n_lists;
   // 4. upper BSR pattern: strictly-upper lists + every diagonal block
-  const int64_t n_ent = n_lists + n_cam;
+  DeviceBuffer<uint64_t> extra;
+  const int64_t n_extra = hook ? hook->extra_keys(list_key.get(), n_lists, n_cam, extra, s) : 0;
+  const int64_t n_own = n_lists + n_cam, n_ent = n_own + n_extra;
   DeviceBuffer<uint64_t> ekeys, ekeys_s; DeviceBuffer<int64_t> etags, etags_s;
   ekeys.alloc(n_ent); ekeys_s.alloc(n_ent); etags.alloc(n_ent); etags_s.alloc(n_ent);
-  upper_keys_kernel<<<div_up(n_ent, TPB), TPB, 0, s>>>(list_key.get(), n_lists, n_cam, ekeys.get(), etags.get());
+  upper_keys_kernel<<<div_up(n_own, TPB), TPB, 0, s>>>(list_key.get(), n_lists, n_cam, ekeys.get(), etags.get());
+  if (n_extra > 0)
+    extra_keys_kernel<<<div_up(n_extra, TPB), TPB, 0, s>>>(extra.get(), n_extra, n_cam, ekeys.get() + n_own, etags.get() + n_own);
   sort_pairs(ekeys.get(), ekeys_s.get(), etags.get(), etags_s.get(), n_ent, 64, s);
+  if (n_extra > 0) {
+    // drop the duplicates (stable sort: the local entry of a run comes first), then sort the
+    // survivors to the front again
+    dedupe_keys_kernel<<<div_up(n_ent, TPB), TPB, 0, s>>>(ekeys_s.get(), n_ent, ekeys.get());
+    std::swap(etags.ptr, etags_s.ptr); std::swap(etags.count, etags_s.count);
+    sort_pairs(ekeys.get(), ekeys_s.get(), etags.get(), etags_s.get(), n_ent, 64, s);
+    extra.release();
+  }
   DeviceBuffer<unsigned long long> valid; valid.alloc(1); valid.zero(s);
   count_valid_kernel<<<div_up(n_ent, TPB), TPB, 0, s>>>(ekeys_s.get(), n_ent, valid.get());
   unsigned long long nnzu = 0;
@@ -351,6 +399,7 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
     }
     cptr[n_cam] = (int32_t)crow.size();
     sp.n_chunks = (int64_t)crow.size();
+    sp.h_chunk_beg = cbeg;
     sp.chunk_row.alloc(crow.size()); sp.chunk_beg.alloc(cbeg.size()); sp.chunk_ptr.alloc(cptr.size());
     ISFM_CUDA(cudaMemcpyAsync(sp.chunk_row.get(), crow.data(), crow.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ISFM_CUDA(cudaMemcpyAsync(sp.chunk_beg.get(), cbeg.data(), cbeg.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
@@ -359,6 +408,31 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
   }
   ISFM_CUDA(cudaGetLastError());
   ISFM_CUDA(cudaStreamSynchronize(s));
+}
+
+namespace {
+__global__ void pattern_hash_kernel(const int32_t* __restrict__ v, int64_t n, uint64_t salt, unsigned long long* out) {
+  uint64_t a = 0, b = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t x = (uint64_t)(uint32_t)v[i] + 1u, k = (uint64_t)i + salt;
+    a += x * (k * 0x9E3779B97F4A7C15ull + 0x7F4A7C15ull);
+    b += (x ^ (x << 17)) * (k * 0xC2B2AE3D27D4EB4Full + 0x165667B1ull);
+  }
+  // integer atomics: the sum does not depend on the order
+  atomicAdd(out, (unsigned long long)a);
+  atomicAdd(out + 1, (unsigned long long)b);
+}
+}  // namespace
+
+void schur_pattern_signature(const SchurPattern& sp, int64_t n_cam, cudaStream_t s, uint64_t sig_out[2]) {
+  DeviceBuffer<unsigned long long> acc;
+  acc.alloc(2); acc.zero(s);
+  if (sp.nnzu > 0) pattern_hash_kernel<<<div_up(sp.nnzu, 256 * 8), 256, 0, s>>>(sp.ucol.get(), sp.nnzu, 1u, acc.get());
+  pattern_hash_kernel<<<div_up(n_cam + 1, 256), 256, 0, s>>>(sp.urow_ptr.get(), n_cam + 1, 0x100000000ull, acc.get());
+  unsigned long long h[2];
+  ISFM_CUDA(cudaMemcpyAsync(h, acc.get(), sizeof h, cudaMemcpyDeviceToHost, s));
+  ISFM_CUDA(cudaStreamSynchronize(s));
+  sig_out[0] = h[0] >> 16; sig_out[1] = h[1] >> 16;
 }
 
 }  // namespace isfm

@@ -48,12 +48,28 @@ struct SchurPattern {
   DeviceBuffer<int32_t> chunk_row;   // [n_chunks]
   DeviceBuffer<int32_t> chunk_beg;   // [n_chunks] first upper slot of the chunk
   DeviceBuffer<int32_t> chunk_ptr;   // [n_cam + 1] first chunk of each row
+  std::vector<int32_t> h_chunk_beg;  // host copy of chunk_beg (splitting the units across ranks)
 };
 constexpr int SPMV_CHUNK = 48;   // slots per mat-vec work unit (one warp); multiple of 4
 
 // cam_idx / pt_idx: device int32 [n_obs] in the caller's order.
 void build_obs_index(ObsIndex& ix, int64_t n_cam, int64_t n_pt, int64_t n_obs, const int32_t* cam_idx,
                      const int32_t* pt_idx, cudaStream_t stream, KernelTimers& kt);
-void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t stream, KernelTimers& kt);
+// Optional hook called once the local pair lists are known: may return extra block keys
+// (i * n_cam + j; anything with i >= j or ~0 is ignored, duplicates are fine) that must exist in
+// the pattern even without local pairs -- the multi-rank solver passes the other ranks' keys so
+// that every rank builds the UNION pattern (zero blocks where it has no pairs).
+struct PatternKeyHook {
+  virtual ~PatternKeyHook() {}
+  virtual int64_t extra_keys(const uint64_t* list_key, int64_t n_lists, int64_t n_cam, DeviceBuffer<uint64_t>& out,
+                             cudaStream_t stream) = 0;
+};
+void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t stream, KernelTimers& kt,
+                         PatternKeyHook* hook = nullptr);
+// number of distinct valid strictly-upper keys (i < j) in `keys` (device, n entries; sorts a copy)
+int64_t count_unique_upper_keys(const uint64_t* keys, int64_t n, int64_t n_cam, cudaStream_t stream);
+// Two 48-bit order-independent hashes of the upper BSR pattern (row pointers and columns): equal
+// on two ranks <=> (with overwhelming probability) identical patterns.  Synchronises the stream.
+void schur_pattern_signature(const SchurPattern& sp, int64_t n_cam, cudaStream_t stream, uint64_t sig_out[2]);
 
 }  // namespace isfm

@@ -470,6 +470,7 @@ struct BlockPCG {
   bool graph_disabled = false;
   const T* g_E = nullptr; const T* g_Hd = nullptr; const T* g_Minv = nullptr; double g_tol2 = 0.0; int64_t g_units = -1;
   const void* g_peer_base = nullptr;   // the graph bakes the exchange pointers in
+  int64_t g_unit_lo = 0, g_unit_hi = -1;
 
   ~BlockPCG() {
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -495,9 +496,14 @@ struct BlockPCG {
 
   // Solves S x = b.  Returns iterations; result in x.  status: 1 converged, 0 hit max_iter,
   // 2 breakdown.
+  // unit_lo / unit_hi: the mat-vec work units this rank multiplies (all of them unless the ranks
+  // share one block pattern and the summed E has been reduce-scattered by unit ranges; the
+  // partials and deposits of the other units are zero, see BASolver::setup_matvec_split)
   int solve(const SchurPattern& sp, const T* E,
             const T* Hd, const T* Minv, const T* b, double tol, int max_iter, isfm_comm* comm, cudaStream_t s,
-            KernelTimers& kt, int* status_out) {
+            KernelTimers& kt, int* status_out, int64_t unit_lo = 0, int64_t unit_hi = -1) {
+    if (unit_hi < 0) unit_hi = sp.n_chunks;
+    const int n_units = (int)(unit_hi - unit_lo);
     const int nb = div_up(n_cam, PCG_TPB);
     const int nb_upd = div_up(n_cam, UPD_TPB / D), nb_dir = div_up((int64_t)n_cam * D, PCG_TPB);
     const int nb_comb = (n_cam + 1) / 2, nb_diag = div_up(n_cam, PCG_TPB / D);
@@ -511,10 +517,11 @@ struct BlockPCG {
       pcg_init_state_kernel<D><<<1, 256, 0, s>>>(n_cam, max_iter, part_a.get(), part_b.get(), state.get()); }
     const double tol2 = tol * tol;
     auto launch_iteration = [&](cudaGraphConditionalHandle cond, int use_cond) {
-      { TimerScope ts(kt, T_PCG_SPMV);
-        pcg_spmv_upper_kernel<T, D><<<div_up(sp.n_chunks, SpmvCfg<T, D>::NW), PCG_TPB, SpmvCfg<T, D>::SMEM, s>>>(
-            (int)sp.n_chunks, sp.chunk_row.get(), sp.chunk_beg.get(), sp.urow_ptr.get(), sp.ucol.get(), sp.tpos.get(), E,
-            p.get(), yup.get(), C.get(), state.get()); }
+      if (n_units > 0) {
+        TimerScope ts(kt, T_PCG_SPMV);
+        pcg_spmv_upper_kernel<T, D><<<div_up(n_units, SpmvCfg<T, D>::NW), PCG_TPB, SpmvCfg<T, D>::SMEM, s>>>(
+            n_units, sp.chunk_row.get() + unit_lo, sp.chunk_beg.get() + unit_lo, sp.urow_ptr.get(), sp.ucol.get(), sp.tpos.get(), E,
+            p.get(), yup.get() + (size_t)unit_lo * D, C.get(), state.get()); }
       if (!multi) {
         TimerScope ts(kt, T_PCG_VEC);
         pcg_combine_kernel<T, D, COMB_FUSED><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(),
@@ -552,7 +559,7 @@ struct BlockPCG {
     // No per-kernel timing and no NCCL call inside the loop (single rank, or the peer-memory
     // exchange): device-side WHILE graph.
     bool use_graph = (!multi || peer) && !kt.enabled && !graph_disabled && !getenv("ISFM_NO_GRAPH");
-    if (use_graph && !(graph_exec && g_E == E && g_Hd == Hd && g_Minv == Minv && g_tol2 == tol2 && g_units == sp.n_chunks &&
+    if (use_graph && !(graph_exec && g_E == E && g_Hd == Hd && g_Minv == Minv && g_tol2 == tol2 && g_units == sp.n_chunks && g_unit_lo == unit_lo && g_unit_hi == unit_hi &&
                        g_peer_base == (peer ? (const void*)comm->px.base[0] : nullptr))) {
       if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
       const int64_t lc = g_launch_count;
@@ -583,7 +590,7 @@ struct BlockPCG {
       if (!ok) { graph_exec = nullptr; graph_disabled = true; cudaGetLastError(); }   // plain launches + host polling instead
       g_launch_count = lc;                       // captured, not executed
       for (int i = 0; i < ISFM_N_TIMERS; ++i) kt.launches[i] = saved[i];
-      g_E = E; g_Hd = Hd; g_Minv = Minv; g_tol2 = tol2; g_units = sp.n_chunks;
+      g_E = E; g_Hd = Hd; g_Minv = Minv; g_tol2 = tol2; g_units = sp.n_chunks; g_unit_lo = unit_lo; g_unit_hi = unit_hi;
       g_peer_base = peer ? (const void*)comm->px.base[0] : nullptr;
       use_graph = graph_exec != nullptr;
     }

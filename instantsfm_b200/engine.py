@@ -191,6 +191,13 @@ class BAEngine(_EngineBase):
                                              cperm.ctypes.data_as(c_void_p), coff.ctypes.data_as(c_void_p)))
         return {"obs_perm": perm, "point_offsets": poff, "cam_perm": cperm, "cam_offsets": coff}
 
+    def matvec_units(self):
+        """(owned, total) mat-vec work units of this rank per PCG iteration (owned < total when the
+        ranks share one block pattern and the summed matrix is split across them)."""
+        owned, total = c_int64(), c_int64()
+        check(self.lib.isfm_ba_get_matvec_units(self.handle, byref(owned), byref(total)))
+        return owned.value, total.value
+
     def schur_pattern(self):
         nnzb, npairs = c_int64(), c_int64()
         check(self.lib.isfm_ba_get_schur_pattern(self.handle, byref(nnzb), byref(npairs), None, None))

@@ -26,6 +26,12 @@ def main():
                                      a.point_indices, rank, world)
         multi = BAEngine(a.model_id, dtype=dtype, comm=comm, pcg_tol=1e-10 if dtype == np.float64 else 1e-6)
         multi.set_problem(*local_t)
+        owned, total = multi.matvec_units()
+        if os.environ.get("ISFM_SPLIT_MATVEC") == "1":
+            # dense co-visibility: both ranks have the same block pattern, the mat-vec is split
+            assert 0 < owned < total, (owned, total)
+        else:
+            assert owned == total
         single = BAEngine(a.model_id, dtype=dtype, pcg_tol=1e-10 if dtype == np.float64 else 1e-6)
         single.set_problem(a.camera_params, a.camera_pps, a.points_3d, a.points_2d, a.camera_indices, a.point_indices)
         for it in range(8):
@@ -81,7 +87,8 @@ def main():
     if os.environ.get("ISFM_REQUIRE_PEER"):
         assert comm.peer_enabled == want_peer, "peer-memory exchange was expected to be %s" % ("on" if want_peer else "off")
     if rank == 0:
-        print("MULTIGPU_OK world", world, "transport", "peer" if comm.peer_enabled else "nccl")
+        print("MULTIGPU_OK world", world, "transport", "peer" if comm.peer_enabled else "nccl",
+              "split" if os.environ.get("ISFM_SPLIT_MATVEC") == "1" else "nosplit")
     dist.destroy_process_group()
 
 

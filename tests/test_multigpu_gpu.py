@@ -8,10 +8,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("transport", ["peer", "nccl"])
-def test_two_rank_solve_matches_single_rank(transport):
+@pytest.mark.parametrize("transport,split", [("peer", False), ("nccl", False), ("peer", True), ("nccl", True)])
+def test_two_rank_solve_matches_single_rank(transport, split):
     """Both transports of the per-iteration sum (peer-memory exchange fused into the PCG kernels,
-    ncclAllReduce) must reproduce the single-rank solve."""
+    ncclAllReduce), with and without the split mat-vec (summed E reduce-scattered by unit ranges
+    when the ranks share one block pattern), must reproduce the single-rank solve."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
@@ -22,6 +23,7 @@ def test_two_rank_solve_matches_single_rank(transport):
     env.pop("ISFM_NO_PEER", None)
     if transport == "nccl":
         env["ISFM_NO_PEER"] = "1"
+    env["ISFM_SPLIT_MATVEC"] = "1" if split else "0"
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and "MULTIGPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
-    assert ("transport " + transport) in out.stdout, out.stdout[-2000:]
+    assert ("transport " + transport + (" split" if split else " nosplit")) in out.stdout, out.stdout[-2000:]

@@ -14,12 +14,13 @@ run() { # name, extra env
 import json, sys
 try:
     d = json.load(open(sys.argv[1]))
-    print({k: d.get(k) for k in ("value", "ms_per_step", "pcg_iters_per_step", "pcg_exchange", "n_gpus", "scaling")})
+    print({k: d.get(k) for k in ("value", "ms_per_step", "pcg_iters_per_step", "pcg_exchange", "matvec_split", "n_gpus", "scaling", "final_robust_cost")})
     print({k: (round(v["ms_per_step"], 3), round(v["us_per_launch"], 1)) for k, v in d["kernels"].items()})
 except Exception as e:
     print("no bench line", e)
 P
 }
-run peer "ISFM_X=1" ""
-run nccl "ISFM_NO_PEER=1" ""
+run split "ISFM_X=1" ""
+run nosplit "ISFM_SPLIT_MATVEC=0" ""
+if [ "${4:-}" = nccl ]; then run nccl "ISFM_NO_PEER=1 ISFM_SPLIT_MATVEC=0" ""; fi
 ls "$OUT"
