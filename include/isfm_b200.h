@@ -259,6 +259,20 @@ int isfm_filter_triangulation_angle(int64_t n_trk, int64_t n_obs, int64_t n_img,
                                     const double* centers, const double* xyz,
                                     double cos_threshold, uint8_t* remove_out, void* stream);
 
+/* ------------------------------------------------------------------------------------ */
+/* batched reprojection test: the arithmetic of complete_tracks,        */
+/* instantsfm/processors/track_retriangulation.py:81-91, fp64 like the reference.          */
+/* cam [n_cam, 7 + n_intr] = [t, q_xyzw, intrinsics without pp] per IMAGE, pp [n_cam, 2],  */
+/* pts [n_pt, 3], obs [n_obs, 2] observed pixels, cam_idx / pt_idx int32 [n_obs]; host or  */
+/* device pointers.  pass_out[a] = (||reproject(X, cam, pp) - obs|| <= max_error) &&       */
+/* (rotate_quat(X, cam).z > min_depth); err_out (may be NULL) receives the error norm.     */
+/* ------------------------------------------------------------------------------------ */
+int isfm_reprojection_test(int32_t model_id, int64_t n_obs, int64_t n_cam, int64_t n_pt,
+                           const double* cam, const double* pp, const double* pts,
+                           const double* obs, const int32_t* cam_idx, const int32_t* pt_idx,
+                           double max_error, double min_depth, uint8_t* pass_out,
+                           double* err_out, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

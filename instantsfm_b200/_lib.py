@@ -77,6 +77,8 @@ SIGNATURES = {
     "isfm_gp_reset_timers": (c_int, [c_void_p, c_int32]),
     "isfm_filter_observations": (c_int, [c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_double, c_void_p, c_void_p]),
+    "isfm_reprojection_test": (c_int, [c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "isfm_filter_triangulation_angle": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                                 c_void_p, c_void_p]),
 }

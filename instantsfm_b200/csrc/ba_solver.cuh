@@ -265,6 +265,7 @@ struct BASolver : BASolverBase {
     unit_lo = ub[rank]; unit_hi = ub[rank + 1];
     pcg.yup.zero(s); pcg.C.zero(s);   // never written for the units of other ranks
     E_own.alloc(std::max<size_t>(split_cnt[rank], 1));
+    pcg.set_owned_slots(sp, (int64_t)(split_off[rank] / (D * D)), (int64_t)((split_off[rank] + split_cnt[rank]) / (D * D)), s);
     split_matvec = true;
   }
 

@@ -182,7 +182,8 @@ constexpr int COMB_PLAIN = 0, COMB_FUSED = 1, COMB_PUSH = 2;
 
 template <typename T, int D, int MODE>
 __global__ void __launch_bounds__(COMB_TPB)
-pcg_combine_kernel(int n_cam, const int32_t* __restrict__ lrow_ptr, const int32_t* __restrict__ chunk_ptr,
+pcg_combine_kernel(int n_cam, const int32_t* __restrict__ dep_beg, const int32_t* __restrict__ dep_end,
+                   const int32_t* __restrict__ chunk_ptr, int unit_lo, int unit_hi,
                    const T* __restrict__ yup_part, const T* __restrict__ C, const T* __restrict__ Hd,
                    const T* __restrict__ p, T* __restrict__ out, double* __restrict__ partial,
                    PcgState* __restrict__ st, const PeerExchange px) {
@@ -205,9 +206,11 @@ pcg_combine_kernel(int n_cam, const int32_t* __restrict__ lrow_ptr, const int32_
     halves = half + 1;
     if (g < G) {
       T acc = T(0);
-      for (int k = chunk_ptr[row] + g; k < chunk_ptr[row + 1]; k += G) acc += yup_part[(size_t)k * D + c];
-      const int end = lrow_ptr[row + 1];
-      int k = lrow_ptr[row] + g;
+      // only the units / deposits this rank produced (all of them unless the mat-vec is split)
+      const int ke = min(chunk_ptr[row + 1], unit_hi);
+      for (int k = max(chunk_ptr[row], unit_lo) + g; k < ke; k += G) acc += yup_part[(size_t)k * D + c];
+      const int end = dep_end[row];
+      int k = dep_beg[row] + g;
       T a[MLP];
 #pragma unroll
       for (int u = 0; u < MLP; ++u) a[u] = T(0);
@@ -456,6 +459,21 @@ pcg_direction_kernel(int n_cam, int n_part, double tol2, const double* __restric
   if (blockIdx.x == 0 && threadIdx.x == 0) pcg_finish_iteration(st, rho_new, rr, tol2, false, cond, use_cond);
 }
 
+// deposit positions written by the upper slots [slot_lo, slot_hi): min / max per destination row
+static __global__ void own_deposit_range_kernel(int slot_lo, int slot_hi, const int32_t* __restrict__ ucol,
+                                                const int32_t* __restrict__ tpos, int32_t* beg, int32_t* end) {
+  const int e = slot_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= slot_hi) return;
+  const int k = tpos[e];
+  if (k < 0) return;   // diagonal or padding slot: no deposit
+  atomicMin(beg + ucol[e], k);
+  atomicMax(end + ucol[e], k + 1);
+}
+static __global__ void own_deposit_fix_kernel(int n, int32_t* beg, int32_t* end) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n && end[j] == 0) beg[j] = 0;   // row without own deposits: empty range
+}
+
 template <typename T, int D>
 struct BlockPCG {
   int n_cam = 0;
@@ -470,6 +488,10 @@ struct BlockPCG {
   bool graph_disabled = false;
   const T* g_E = nullptr; const T* g_Hd = nullptr; const T* g_Minv = nullptr; double g_tol2 = 0.0; int64_t g_units = -1;
   const void* g_peer_base = nullptr;   // the graph bakes the exchange pointers in
+  // split mat-vec: [own_dep_beg[j], own_dep_end[j]) = the deposits of lower row j that come from
+  // this rank's units (contiguous: deposits of a row are ordered by source row)
+  DeviceBuffer<int32_t> own_dep_beg, own_dep_end;
+  bool own_valid = false;
   int64_t g_unit_lo = 0, g_unit_hi = -1;
 
   ~BlockPCG() {
@@ -488,9 +510,24 @@ struct BlockPCG {
     C.alloc((size_t)std::max<int64_t>(n_off, 1) * D);
     part_pq.alloc(n); part_a.alloc(n); part_b.alloc(n);
     state.alloc(1);
+    own_valid = false;
     ISFM_CUDA(cudaFuncSetAttribute(pcg_spmv_upper_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)SpmvCfg<T, D>::SMEM));
     if (!h_state) ISFM_CUDA(cudaMallocHost(&h_state, sizeof(PcgState)));
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+  }
+
+  // split mat-vec set-up: restrict the combine kernel to the deposits of the upper slots [slot_lo, slot_hi)
+  void set_owned_slots(const SchurPattern& sp, int64_t slot_lo, int64_t slot_hi, cudaStream_t s) {
+    own_dep_beg.alloc(n_cam); own_dep_end.alloc(n_cam);
+    ISFM_CUDA(cudaMemsetAsync(own_dep_beg.get(), 0x7f, (size_t)n_cam * sizeof(int32_t), s));   // 0x7f7f7f7f: larger than any position
+    ISFM_CUDA(cudaMemsetAsync(own_dep_end.get(), 0, (size_t)n_cam * sizeof(int32_t), s));
+    if (slot_hi > slot_lo)
+      own_deposit_range_kernel<<<div_up(slot_hi - slot_lo, 256), 256, 0, s>>>((int)slot_lo, (int)slot_hi, sp.ucol.get(), sp.tpos.get(),
+                                                                             own_dep_beg.get(), own_dep_end.get());
+    own_deposit_fix_kernel<<<div_up(n_cam, 256), 256, 0, s>>>(n_cam, own_dep_beg.get(), own_dep_end.get());
+    ISFM_CUDA(cudaGetLastError());
+    own_valid = true;
     if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
   }
 
@@ -504,6 +541,10 @@ struct BlockPCG {
             KernelTimers& kt, int* status_out, int64_t unit_lo = 0, int64_t unit_hi = -1) {
     if (unit_hi < 0) unit_hi = sp.n_chunks;
     const int n_units = (int)(unit_hi - unit_lo);
+    // deposit range of every row: the whole lower row, or (split mat-vec) the part this rank writes
+    const bool own_ranges = own_dep_beg.get() != nullptr && own_valid;
+    const int32_t* dep_beg = own_ranges ? own_dep_beg.get() : sp.lrow_ptr.get();
+    const int32_t* dep_end = own_ranges ? own_dep_end.get() : sp.lrow_ptr.get() + 1;
     const int nb = div_up(n_cam, PCG_TPB);
     const int nb_upd = div_up(n_cam, UPD_TPB / D), nb_dir = div_up((int64_t)n_cam * D, PCG_TPB);
     const int nb_comb = (n_cam + 1) / 2, nb_diag = div_up(n_cam, PCG_TPB / D);
@@ -524,18 +565,18 @@ struct BlockPCG {
             p.get(), yup.get() + (size_t)unit_lo * D, C.get(), state.get()); }
       if (!multi) {
         TimerScope ts(kt, T_PCG_VEC);
-        pcg_combine_kernel<T, D, COMB_FUSED><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(),
+        pcg_combine_kernel<T, D, COMB_FUSED><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, dep_beg, dep_end, sp.chunk_ptr.get(), (int)unit_lo, (int)unit_hi, yup.get(),
                                                                          C.get(), Hd, p.get(), q.get(), part_pq.get(), state.get(), px);
       } else if (peer) {
         // all-reduce of y over peer memory: pushed by the combine epilogue, summed by the next kernel
         { TimerScope ts(kt, T_PCG_VEC);
-          pcg_combine_kernel<T, D, COMB_PUSH><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(),
+          pcg_combine_kernel<T, D, COMB_PUSH><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, dep_beg, dep_end, sp.chunk_ptr.get(), (int)unit_lo, (int)unit_hi, yup.get(),
                                                                           C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get(), px); }
         { TimerScope ts(kt, T_COMM);
           pcg_apply_diag_kernel<T, D, true><<<nb_diag, PCG_TPB, 0, s>>>(n_cam, Hd, p.get(), y.get(), q.get(), part_pq.get(), state.get(), px); }
       } else {
         { TimerScope ts(kt, T_PCG_VEC);
-          pcg_combine_kernel<T, D, COMB_PLAIN><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, sp.lrow_ptr.get(), sp.chunk_ptr.get(), yup.get(),
+          pcg_combine_kernel<T, D, COMB_PLAIN><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, dep_beg, dep_end, sp.chunk_ptr.get(), (int)unit_lo, (int)unit_hi, yup.get(),
                                                                            C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get(), px); }
         { TimerScope ts(kt, T_COMM);
           comm_allreduce_sum(comm, y.get(), (size_t)n_cam * D, sizeof(T) == 8, s); }

@@ -56,6 +56,16 @@ f = lambda: _lib.check(lib.isfm_filter_triangulation_angle(n_trk, n_obs, n_img, 
 ms = timed(f)
 out["triangulation_angle"] = {"ms": ms, "tracks_per_s": n_trk / ms * 1e3, "achieved_gbs": (4.0 * n_obs + 33.0 * n_trk) / ms / 1e6,
                               "removed": int(d_rem.sum().item())}
+# batched reprojection test of complete_tracks (RADIAL, fp64): 25 B / candidate (pixel 16 + ids 8 + flag 1)
+cam = np.zeros((n_img, 10)); cam[:, :3] = w2c[:, :3, 3]; cam[:, 6] = 1.0; cam[:, 7] = 1000.0; cam[:, 8] = 0.01; cam[:, 9] = 0.001
+pix = rng.normal(0, 50, (n_obs, 2))
+d_cam, d_pp, d_pix = dev(cam), dev(np.zeros((n_img, 2))), dev(pix)
+d_pass = torch.zeros(n_obs, dtype=torch.uint8, device="cuda")
+f = lambda: _lib.check(lib.isfm_reprojection_test(3, n_obs, n_img, n_trk, d_cam.data_ptr(), d_pp.data_ptr(), d_xyz.data_ptr(), d_pix.data_ptr(),
+                                                  d_ids.data_ptr(), d_tix.data_ptr(), 20.0, 1e-7, d_pass.data_ptr(), None, None))
+ms = timed(f)
+out["reprojection_test"] = {"ms": ms, "obs_per_s": n_obs / ms * 1e3, "achieved_gbs": 25.0 * n_obs / ms / 1e6, "frac": 25.0 * n_obs / ms / 1e6 / peak,
+                            "passed": int(d_pass.sum().item())}
 # CPU beside it: the same arithmetic vectorised in numpy on the host (the reference's own per-observation
 # Python loop runs ~1e5 observations / s), on a 500 k-observation sample
 m = 500000
