@@ -18,6 +18,8 @@
 // The J-form is kept instead of Hcp = Jc^T Jp (27 floats / obs): every Schur product is
 // Jc_a^T (V_a Jp_b^T) Jc_b with a 2x2 middle factor.
 #pragma once
+#include <cuda.h>   // CUtensorMap (the driver entry point is resolved at run time, no libcuda link)
+
 #include "common.cuh"
 #include "math.cuh"
 
@@ -806,6 +808,186 @@ fused_linearize_kernel(const int4* __restrict__ tiles, const int32_t* __restrict
   }
   // cost partials: wanted on the first LM step only (later steps carry the accepted trial cost)
   if (!want_cost || ISFM_ABL(16)) return;
+  rho_d = block_sum(rho_d);
+  sq_d = block_sum(sq_d);
+  if (t == 0) { part_rho[blockIdx.x] = rho_d; part_sq[blockIdx.x] = sq_d; }
+}
+
+// ---------------------------------------------------------------------------------------
+// The same kernel with the record slab leaving shared memory through the TMA (fp32, 128-byte
+// records).  In the kernel above every thread re-reads eight quads from the staging tile and
+// stores them to HBM (8 LDS.128 + 8 STG.128 per observation) only to make the stores coalesced;
+// that kernel is bound by the LSU pipe (78 % of the wavefront budget), not by HBM.  Here the tile
+// is laid out as the TMA's SWIZZLE_128B pattern -- 16-byte chunk c of row t lives at chunk
+// c ^ (t & 7): the thread-per-record STS.128 are conflict-free without padding -- and the slab is
+// stored by bulk tensor copies (cp.async.bulk.tensor.2d, boxes of 8 records = 1 KB, issued by the
+// first lanes, un-swizzled by the copy engine); only the < 8 records of a tile's tail are stored
+// by threads.  `tmap`: 2-D tensor map over OBS ([n_obs][32] fp32, box {32, 8}, SWIZZLE_128B).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, const void* smem_src) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_src);
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(tmap), "r"(c0), "r"(c1), "r"(sa) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct FusedTmaCfg {
+  static constexpr int REC = 32;                 // floats per record (128 B)
+  static constexpr int BOX_ROWS = 8;             // records per bulk store (1 KB)
+  static constexpr int CQ = 3;                   // quads of per-observation contributions to Hpp (6) and g_p (3)
+  static constexpr size_t TILE_BYTES = (size_t)FUSED_TPB * REC * 4;
+  static constexpr size_t SMEM = TILE_BYTES + (size_t)FUSED_TPB * CQ * 16 + 1024;   // + slack to align the tile to 1 KB
+};
+
+template <int MODEL>
+__global__ void __launch_bounds__(FUSED_TPB, 4 * (256 / FUSED_TPB))
+fused_linearize_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_big, int big_rows,
+                           const int4* __restrict__ tiles,
+                           const int32_t* __restrict__ pt_off, const float* __restrict__ camq, const float* __restrict__ pts,
+                           const float* __restrict__ obs, const int32_t* __restrict__ cam_of, const int32_t* __restrict__ pt_of,
+                           float delta, float mu, float* __restrict__ R, float* __restrict__ OBS, float* __restrict__ HPP,
+                           float* __restrict__ GPT, float* __restrict__ HPPINV, float* __restrict__ TP,
+                           double* __restrict__ part_rho, double* __restrict__ part_sq, int want_cost) {
+  typedef float T;
+  constexpr int NI = ModelTraits<MODEL>::NI;
+  constexpr int D = 6 + NI;
+  constexpr int CW = 7 + NI;
+  constexpr int REC = ObsRec<D>::REC, QR = REC / 4, OJP = ObsRec<D>::JP, OV = ObsRec<D>::V, QV = OV / 4;
+  static_assert(REC == FusedTmaCfg::REC, "TMA path: 128-byte records only");
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  // tile: [FUSED_TPB][32] floats, 1 KB aligned (the swizzle is a function of the shared-memory address)
+  const unsigned base_sa = (unsigned)__cvta_generic_to_shared(fused_smem);
+  T* tile = reinterpret_cast<T*>(fused_smem + (((base_sa + 1023u) & ~1023u) - base_sa));
+  T* contrib = tile + FUSED_TPB * REC;                       // [FUSED_TPB][12], 48-byte stride: conflict-free quads
+  const int t = threadIdx.x;
+  const int sw = t & 7;
+  T* row = tile + (size_t)t * REC;
+  auto chunk = [&](int q) -> T* { return row + ((q ^ sw) << 2); };
+  double rho_d = 0.0, sq_d = 0.0;
+  const int4 tl = __ldg(tiles + blockIdx.x);   // {first point, end point, first observation, observations}
+  const int o0 = tl.z, n = tl.w;
+  const int64_t a = (int64_t)o0 + t;
+  if (t < tl.y - tl.x) {   // a point without observations has no thread below: write its blocks here
+    const int pz = tl.x + t;
+    if (pt_off[pz + 1] == pt_off[pz]) {
+      const T dinv = T(1) / damp_diag(T(0), mu);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { HPP[(size_t)pz * 6 + i] = T(0); HPPINV[(size_t)pz * 6 + i] = (i == 0 || i == 3 || i == 5) ? dinv : T(0); }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { GPT[(size_t)pz * 3 + i] = T(0); TP[(size_t)pz * 3 + i] = T(0); }
+    }
+  }
+  T tail[REC - 4 * QV];          // record elements [4 QV, REC): the end of Jp, V, rho, padding
+  T rw0 = T(0), rw1 = T(0);
+  int p = 0, kb = 0, ke = 0;
+  if (t < n) {
+    const int c = cam_of[a];
+    p = pt_of[a];
+    kb = pt_off[p] - o0; ke = pt_off[p + 1] - o0;
+    T cr[CW], ppv[2], X[3], o[2], r[2], rec[REC];
+    load_camera<T, CW>(camq, c, cr, ppv);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) X[i] = __ldg(pts + 3 * (size_t)p + i);
+    o[0] = obs[2 * a]; o[1] = obs[2 * a + 1];
+    ba_linearize<MODEL, T>(cr, ppv, X, o, r, rec, rec + OJP);
+    T s = r[0] * r[0] + r[1] * r[1], rho, w;
+    huber(s, delta, rho, w);
+    rho_d += (double)rho; sq_d += (double)s;
+    rw0 = w * r[0]; rw1 = w * r[1];
+#pragma unroll
+    for (int i = 0; i < 2 * D + 6; ++i) rec[i] *= w;
+#pragma unroll
+    for (int i = OV; i < REC; ++i) rec[i] = T(0);
+    const T* j = rec + OJP;
+    T cb[12];
+    cb[0] = j[0] * j[0] + j[3] * j[3]; cb[1] = j[0] * j[1] + j[3] * j[4]; cb[2] = j[0] * j[2] + j[3] * j[5];
+    cb[3] = j[1] * j[1] + j[4] * j[4]; cb[4] = j[1] * j[2] + j[4] * j[5]; cb[5] = j[2] * j[2] + j[5] * j[5];
+    cb[6] = j[0] * rw0 + j[3] * rw1; cb[7] = j[1] * rw0 + j[4] * rw1; cb[8] = j[2] * rw0 + j[5] * rw1;
+    cb[9] = cb[10] = cb[11] = T(0);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) QuadIO<T>::st(contrib + (size_t)t * 12 + 4 * q, cb + 4 * q);
+    R[2 * a] = rw0; R[2 * a + 1] = rw1;
+#pragma unroll
+    for (int q = 0; q < QV; ++q) QuadIO<T>::st(chunk(q), rec + 4 * q);
+#pragma unroll
+    for (int i = 0; i < REC - 4 * QV; ++i) tail[i] = rec[4 * QV + i];
+  }
+  __syncthreads();   // contributions are complete
+  if (t < n) {
+    T h[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    for (int k = kb; k < ke; ++k) {
+      T cb[12];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) QuadIO<T>::ld(contrib + (size_t)k * 12 + 4 * q, cb + 4 * q);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) h[i] += cb[i];
+      g[0] += cb[6]; g[1] += cb[7]; g[2] += cb[8];
+    }
+    const bool head = t == kb;
+    if (head) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) HPP[(size_t)p * 6 + i] = h[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) GPT[(size_t)p * 3 + i] = g[i];
+    }
+    h[0] = damp_diag(h[0], mu); h[3] = damp_diag(h[3], mu); h[5] = damp_diag(h[5], mu);
+    T iv[6];
+    sym3_inverse(h, iv);
+    const T t0 = iv[0] * g[0] + iv[1] * g[1] + iv[2] * g[2];
+    const T t1 = iv[1] * g[0] + iv[3] * g[1] + iv[4] * g[2];
+    const T t2 = iv[2] * g[0] + iv[4] * g[1] + iv[5] * g[2];
+    if (head) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) HPPINV[(size_t)p * 6 + i] = iv[i];
+      TP[(size_t)p * 3 + 0] = t0; TP[(size_t)p * 3 + 1] = t1; TP[(size_t)p * 3 + 2] = t2;
+    }
+    // Jp: elements [OJP, OJP + 6) of the record; those below 4 QV were staged (swizzled), re-read them
+    T jp[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int e = OJP + i;
+      jp[i] = (e >= 4 * QV) ? tail[e - 4 * QV] : chunk(e >> 2)[e & 3];
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      T a0 = jp[3 * rr], a1 = jp[3 * rr + 1], a2 = jp[3 * rr + 2];
+      tail[OV - 4 * QV + 3 * rr + 0] = a0 * iv[0] + a1 * iv[1] + a2 * iv[2];
+      tail[OV - 4 * QV + 3 * rr + 1] = a0 * iv[1] + a1 * iv[3] + a2 * iv[4];
+      tail[OV - 4 * QV + 3 * rr + 2] = a0 * iv[2] + a1 * iv[4] + a2 * iv[5];
+    }
+    tail[ObsRec<D>::RHO - 4 * QV] = rw0 - (jp[0] * t0 + jp[1] * t1 + jp[2] * t2);
+    tail[ObsRec<D>::RHO - 4 * QV + 1] = rw1 - (jp[3] * t0 + jp[4] * t1 + jp[5] * t2);
+#pragma unroll
+    for (int q = QV; q < QR; ++q) QuadIO<T>::st(chunk(q), tail + 4 * (q - QV));
+  }
+  fence_proxy_async_smem();   // this thread's tile writes become visible to the copy engine ...
+  __syncthreads();            // ... and every thread has made them
+  // big boxes (big_rows records, a multiple of 8; 0 = none) first, then boxes of 8 records
+  const int n_big = big_rows > 0 ? n / big_rows : 0;
+  const int rb = n_big * big_rows;
+  const int n_box = (n - rb) / FusedTmaCfg::BOX_ROWS;
+  // one thread issues every store of the tile and waits once: the stores pipeline in the copy
+  // engine (issued from several lanes they would be serialised together with their waits); the
+  // thread sits in the LAST warp so that the hand-written tail below is not held up behind it
+  if (t == FUSED_TPB - 1) {
+    for (int i = 0; i < n_big; ++i) tma_store_2d(&tmap_big, 0, o0 + i * big_rows, tile + (size_t)i * big_rows * REC);
+    for (int i = 0; i < n_box; ++i)
+      tma_store_2d(&tmap, 0, o0 + rb + i * FusedTmaCfg::BOX_ROWS, tile + (size_t)(rb + i * FusedTmaCfg::BOX_ROWS) * REC);
+    tma_store_commit_and_wait_read();   // shared memory must stay intact until the engine has read it
+  }
+  // tail of the tile (< 8 records): un-swizzle by hand, one quad per thread
+  const int r0 = rb + n_box * FusedTmaCfg::BOX_ROWS;
+  if (t < (n - r0) * QR) {
+    const int rr = r0 + t / QR, q = t % QR;
+    T v[4];
+    QuadIO<T>::ld(tile + (size_t)rr * REC + ((q ^ (rr & 7)) << 2), v);
+    QuadIO<T>::st(OBS + ((size_t)o0 + rr) * REC + 4 * q, v);
+  }
+  if (!want_cost) return;
   rho_d = block_sum(rho_d);
   sq_d = block_sum(sq_d);
   if (t == 0) { part_rho[blockIdx.x] = rho_d; part_sq[blockIdx.x] = sq_d; }

@@ -78,6 +78,10 @@ struct BASolver : BASolverBase {
   bool have_loss = false;
   double loss = 0.0;
   double mu_last = 1.0;
+  CUtensorMap obs_tmap;       // OBS as a 2-D tensor (TMA store of the record slabs), valid when tma_ok
+  CUtensorMap obs_tmap_big;   // the same tensor with boxes of tma_big_rows records
+  int tma_big_rows = 0;
+  bool tma_ok = false;
   bool fused_ok = false;      // every track fits one CTA of the fused K1 (<= FUSED_TPB observations)
   int n_fused_cta = 0;        // tiles of whole points with <= FUSED_TPB observations
   DeviceBuffer<int4> fused_tiles;   // {first point, end point, first observation, observations} per CTA
@@ -153,6 +157,7 @@ struct BASolver : BASolverBase {
     DP.alloc((size_t)np * 3);
     mark("obs gather + allocs");
     build_fused_partition();
+    if (fused_ok) build_obs_tensor_map();
     mark("fused tile partition");
     if (getenv("ISFM_NO_FUSED")) fused_ok = false;
     const int64_t n_part = std::max<int64_t>(std::max<int64_t>(RED_BLOCKS, nc), n_fused_cta);
@@ -297,13 +302,68 @@ struct BASolver : BASolverBase {
   }
 
   // fused K1 + point solve of the first trial; returns the number of cost partials
+  // 2-D tensor map over OBS ([n_obs][32] fp32 = 128-byte records), boxes of 8 records, 128-byte
+  // swizzle: the fused K1 stores its record slab with bulk tensor copies (fused_linearize_tma_kernel).
+  // cuTensorMapEncodeTiled is resolved through the runtime (no link against libcuda).
+  bool build_obs_tensor_map() {
+    tma_ok = false;
+    if constexpr (sizeof(T) != 4 || REC != FusedTmaCfg::REC) {
+      return false;
+    } else {
+    if (getenv("ISFM_NO_TMA") || n_obs <= 0) return false;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) { cudaGetLastError(); return false; }
+    const cuuint64_t dims[2] = {(cuuint64_t)FusedTmaCfg::REC, (cuuint64_t)n_obs};
+    const cuuint64_t strides[1] = {(cuuint64_t)FusedTmaCfg::REC * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)FusedTmaCfg::REC, (cuuint32_t)FusedTmaCfg::BOX_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = reinterpret_cast<EncodeFn>(fn)(&obs_tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, OBS.get(), dims, strides, box, estr,
+                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    tma_big_rows = 64;   // measured: 8 / 32 / 64-record boxes 268 / 254 / 254 us on C3
+    if (const char* e = getenv("ISFM_TMA_BOX")) tma_big_rows = atoi(e);
+    if (tma_big_rows % 8 != 0 || tma_big_rows < 0 || tma_big_rows > 256) tma_big_rows = 0;
+    obs_tmap_big = obs_tmap;
+    if (tma_big_rows > 0) {
+      const cuuint32_t box_big[2] = {(cuuint32_t)FusedTmaCfg::REC, (cuuint32_t)tma_big_rows};
+      if (reinterpret_cast<EncodeFn>(fn)(&obs_tmap_big, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, OBS.get(), dims, strides, box_big, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { tma_big_rows = 0; obs_tmap_big = obs_tmap; }
+    }
+    if (cudaFuncSetAttribute(fused_linearize_tma_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)FusedTmaCfg::SMEM) != cudaSuccess) { cudaGetLastError(); return false; }
+    tma_ok = true;
+    return true;
+    }
+  }
+
   int run_fused_linearize(T mu, bool want_cost) {
     TimerScope ts(timers, T_LINEARIZE);
+    if (tma_ok) {
+      launch_fused_tma(mu, want_cost);
+      return n_fused_cta;
+    }
     fused_linearize_kernel<T, MODEL><<<n_fused_cta, FUSED_TPB, FusedCfg<T, D>::SMEM, s>>>(
         fused_tiles.get(), ix.pt_off.get(), camq[cur].get(), pts[cur].get(), obs.get(), ix.cam_of.get(),
         ix.pt_of.get(), (T)desc.huber_delta, mu, R.get(), OBS.get(), HPP.get(), GPT.get(), HPPINV.get(), TP.get(),
         part_a.get(), part_b.get(), want_cost ? 1 : 0, 0);
     return n_fused_cta;
+  }
+
+  // (the kernel exists for float records only; the double build never takes this path)
+  void launch_fused_tma(T mu, bool want_cost) {
+    if constexpr (sizeof(T) == 4 && REC == FusedTmaCfg::REC) {
+      fused_linearize_tma_kernel<MODEL><<<n_fused_cta, FUSED_TPB, FusedTmaCfg::SMEM, s>>>(
+          obs_tmap, obs_tmap_big, tma_big_rows, fused_tiles.get(), ix.pt_off.get(), camq[cur].get(), pts[cur].get(), obs.get(), ix.cam_of.get(),
+          ix.pt_of.get(), (float)desc.huber_delta, mu, R.get(), OBS.get(), HPP.get(), GPT.get(), HPPINV.get(), TP.get(),
+          part_a.get(), part_b.get(), want_cost ? 1 : 0);
+    }
   }
 
   // greedy packing of whole points into CTAs of <= FUSED_TPB observations (host, one pass)

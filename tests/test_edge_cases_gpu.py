@@ -92,3 +92,27 @@ def test_opencv_fisheye_ignored_k4_is_held_by_the_diagonal_clamp():
 def test_two_steps_for_every_other_model(model_id):
     a = make_ba_problem(8, 150, 700, seed=70 + model_id, model_id=model_id)
     _run(a, steps=2, tol=1e-7)
+
+
+def test_fused_linearize_tma_and_plain_store_agree(monkeypatch):
+    """The fused K1 has two ways of storing its record slab (bulk tensor copies through the TMA,
+    and per-thread 128-bit stores): both must produce bit-identical trajectories."""
+    import numpy as np
+    from instantsfm_b200.engine import BAEngine
+    from instantsfm_b200.synthetic import make_ba_problem
+    a = make_ba_problem(24, 2500, 13000, seed=123)
+    out = []
+    for env in ({"ISFM_NO_TMA": "1"}, {"ISFM_TMA_BOX": "0"}, {}):
+        for k in ("ISFM_NO_TMA", "ISFM_TMA_BOX"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = BAEngine(a.model_id, dtype=np.float32)
+        eng.set_problem(a.camera_params, a.camera_pps, a.points_3d, a.points_2d, a.camera_indices, a.point_indices)
+        losses = [eng.step()[0] for _ in range(4)]
+        cam, pts = eng.get_params()
+        out.append((losses, cam, pts))
+        eng.close()
+    for losses, cam, pts in out[1:]:
+        assert losses == out[0][0]
+        assert np.array_equal(cam, out[0][1]) and np.array_equal(pts, out[0][2])
