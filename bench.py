@@ -44,7 +44,7 @@ UNIT = "obs/s"
 CPU_SAMPLE_SCALE = 0.02   # cpu_baseline: config with points/observations scaled by this factor
 # dram__bytes_read.sum + dram__bytes_write.sum per launch on config C3 (1 GPU, full size), from the
 # `ncu --set full` captures summarised in profiles/r1_ncu_full_summary.txt (ncu cannot run inside the bench)
-NCU_TRAFFIC_C3 = {"pcg_spmv": 535.1e6, "schur_offdiag": 2887.5e6, "linearize": 787.2e6, "camera_blocks": 664.7e6,
+NCU_TRAFFIC_C3 = {"pcg_spmv": 535.1e6, "schur_offdiag": 2887.5e6, "linearize": 788.6e6, "camera_blocks": 664.7e6,
                   "backsub": 800.7e6}
 
 

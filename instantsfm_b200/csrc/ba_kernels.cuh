@@ -838,13 +838,16 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 struct FusedTmaCfg {
   static constexpr int REC = 32;                 // floats per record (128 B)
   static constexpr int BOX_ROWS = 8;             // records per bulk store (1 KB)
-  static constexpr int CQ = 3;                   // quads of per-observation contributions to Hpp (6) and g_p (3)
   static constexpr size_t TILE_BYTES = (size_t)FUSED_TPB * REC * 4;
-  static constexpr size_t SMEM = TILE_BYTES + (size_t)FUSED_TPB * CQ * 16 + 1024;   // + slack to align the tile to 1 KB
+  static constexpr size_t PART_BYTES = (size_t)(FUSED_TPB / 32) * 2 * 12 * 4;   // per warp: parts of its first and last point (Hpp 6 | g_p 3 | pad)
+  static constexpr size_t SMEM = TILE_BYTES + PART_BYTES + 1024;                // + slack to align the tile to 1 KB
 };
 
+#ifndef ISFM_FUSED_TMA_MINB
+#define ISFM_FUSED_TMA_MINB 5
+#endif
 template <int MODEL>
-__global__ void __launch_bounds__(FUSED_TPB, 4 * (256 / FUSED_TPB))
+__global__ void __launch_bounds__(FUSED_TPB, ISFM_FUSED_TMA_MINB * (256 / FUSED_TPB))
 fused_linearize_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_big, int big_rows,
                            const int4* __restrict__ tiles,
                            const int32_t* __restrict__ pt_off, const float* __restrict__ camq, const float* __restrict__ pts,
@@ -862,7 +865,7 @@ fused_linearize_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
   // tile: [FUSED_TPB][32] floats, 1 KB aligned (the swizzle is a function of the shared-memory address)
   const unsigned base_sa = (unsigned)__cvta_generic_to_shared(fused_smem);
   T* tile = reinterpret_cast<T*>(fused_smem + (((base_sa + 1023u) & ~1023u) - base_sa));
-  T* contrib = tile + FUSED_TPB * REC;                       // [FUSED_TPB][12], 48-byte stride: conflict-free quads
+  T* contrib = tile + FUSED_TPB * REC;                       // [FUSED_TPB / 32][2][12]: per-warp parts of the point sums
   const int t = threadIdx.x;
   const int sw = t & 7;
   T* row = tile + (size_t)t * REC;
@@ -883,7 +886,10 @@ fused_linearize_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
   }
   T tail[REC - 4 * QV];          // record elements [4 QV, REC): the end of Jp, V, rho, padding
   T rw0 = T(0), rw1 = T(0);
-  int p = 0, kb = 0, ke = 0;
+  // this observation's contribution to Hpp (6) and g_p (3); a thread without observation is a
+  // segment of its own with a zero contribution
+  T cb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int p = 0, kb = t, ke = t + 1;
   if (t < n) {
     const int c = cam_of[a];
     p = pt_of[a];
@@ -903,29 +909,64 @@ fused_linearize_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __gri
 #pragma unroll
     for (int i = OV; i < REC; ++i) rec[i] = T(0);
     const T* j = rec + OJP;
-    T cb[12];
     cb[0] = j[0] * j[0] + j[3] * j[3]; cb[1] = j[0] * j[1] + j[3] * j[4]; cb[2] = j[0] * j[2] + j[3] * j[5];
     cb[3] = j[1] * j[1] + j[4] * j[4]; cb[4] = j[1] * j[2] + j[4] * j[5]; cb[5] = j[2] * j[2] + j[5] * j[5];
     cb[6] = j[0] * rw0 + j[3] * rw1; cb[7] = j[1] * rw0 + j[4] * rw1; cb[8] = j[2] * rw0 + j[5] * rw1;
-    cb[9] = cb[10] = cb[11] = T(0);
-#pragma unroll
-    for (int q = 0; q < 3; ++q) QuadIO<T>::st(contrib + (size_t)t * 12 + 4 * q, cb + 4 * q);
     R[2 * a] = rw0; R[2 * a + 1] = rw1;
 #pragma unroll
     for (int q = 0; q < QV; ++q) QuadIO<T>::st(chunk(q), rec + 4 * q);
 #pragma unroll
     for (int i = 0; i < REC - 4 * QV; ++i) tail[i] = rec[4 * QV + i];
   }
-  __syncthreads();   // contributions are complete
+  // Segmented sum over the observations of a point (they are consecutive threads).  Inside a warp:
+  // inclusive scan by shuffles restricted to the segment, then the value of the segment's last lane
+  // = the part of the point that lives in this warp.  Every warp publishes the part of its first
+  // and of its last segment; a point that straddles warps adds the published parts in warp order
+  // (the same sequence in every thread of the point: bit-identical Hpp in all of them).  The old
+  // loop ran to the longest track of each warp (~15 trips of 3 LDS.128 + 9 FADD for a mean track
+  // length of 5); this is 5 shuffle steps.
+  {
+    const int lane = t & 31, wbase = t & ~31, w = t >> 5;
+    const int lo = max(kb, wbase) - wbase, hi = min(ke, wbase + 32) - 1 - wbase;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const bool take = lane - d >= lo;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const T v = __shfl_up_sync(0xffffffffu, cb[i], d);
+        if (take) cb[i] += v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) cb[i] = __shfl_sync(0xffffffffu, cb[i], hi);
+    if (lane == 0 || lane == 31) {
+      T* dst = contrib + (size_t)(2 * w + (lane == 31 ? 1 : 0)) * 12;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) dst[i] = cb[i];
+    }
+  }
+  __syncthreads();   // per-warp parts are published
   if (t < n) {
-    T h[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-    for (int k = kb; k < ke; ++k) {
-      T cb[12];
+    T h[6], g[3];
+    const int wb = kb >> 5, we = (ke - 1) >> 5;
+    if (wb == we) {
 #pragma unroll
-      for (int q = 0; q < 3; ++q) QuadIO<T>::ld(contrib + (size_t)k * 12 + 4 * q, cb + 4 * q);
+      for (int i = 0; i < 6; ++i) h[i] = cb[i];
+      g[0] = cb[6]; g[1] = cb[7]; g[2] = cb[8];
+    } else {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) h[i] += cb[i];
-      g[0] += cb[6]; g[1] += cb[7]; g[2] += cb[8];
+      for (int i = 0; i < 6; ++i) h[i] = T(0);
+      g[0] = g[1] = g[2] = T(0);
+      for (int ww = wb; ww <= we; ++ww) {
+        // first warp of the point: the part of that warp's LAST segment; later warps: of their FIRST
+        const T* src = contrib + (size_t)(2 * ww + (ww == wb ? 1 : 0)) * 12;
+        T c4[12];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) QuadIO<T>::ld(src + 4 * q, c4 + 4 * q);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) h[i] += c4[i];
+        g[0] += c4[6]; g[1] += c4[7]; g[2] += c4[8];
+      }
     }
     const bool head = t == kb;
     if (head) {

@@ -95,14 +95,16 @@ def test_two_steps_for_every_other_model(model_id):
 
 
 def test_fused_linearize_tma_and_plain_store_agree(monkeypatch):
-    """The fused K1 has two ways of storing its record slab (bulk tensor copies through the TMA,
-    and per-thread 128-bit stores): both must produce bit-identical trajectories."""
+    """The fused K1 exists twice: TMA kernel (record slab stored by bulk tensor copies, per-point
+    sums by a warp-shuffle segmented scan) and the plain kernel (per-thread stores, per-point sums
+    by a loop).  The two box sizes of the TMA kernel must agree bit for bit; the plain kernel sums
+    the same numbers in another order, so it agrees to fp32 rounding."""
     import numpy as np
     from instantsfm_b200.engine import BAEngine
     from instantsfm_b200.synthetic import make_ba_problem
     a = make_ba_problem(24, 2500, 13000, seed=123)
     out = []
-    for env in ({"ISFM_NO_TMA": "1"}, {"ISFM_TMA_BOX": "0"}, {}):
+    for env in ({}, {"ISFM_TMA_BOX": "0"}, {"ISFM_NO_TMA": "1"}):
         for k in ("ISFM_NO_TMA", "ISFM_TMA_BOX"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
@@ -113,6 +115,8 @@ def test_fused_linearize_tma_and_plain_store_agree(monkeypatch):
         cam, pts = eng.get_params()
         out.append((losses, cam, pts))
         eng.close()
-    for losses, cam, pts in out[1:]:
-        assert losses == out[0][0]
-        assert np.array_equal(cam, out[0][1]) and np.array_equal(pts, out[0][2])
+    assert out[1][0] == out[0][0]
+    assert np.array_equal(out[1][1], out[0][1]) and np.array_equal(out[1][2], out[0][2])
+    assert np.allclose(out[2][0], out[0][0], rtol=1e-5)
+    assert np.abs(out[2][1] - out[0][1]).max() <= 1e-3 * np.abs(out[0][1]).max()
+    assert np.abs(out[2][2] - out[0][2]).max() <= 1e-3 * np.abs(out[0][2]).max()
