@@ -269,6 +269,42 @@ pcg_combine_kernel(int n_cam, const int32_t* __restrict__ dep_beg, const int32_t
   }
 }
 
+// Large camera systems: the combine kernel writes y locally (COMB_PLAIN) and this kernel pushes
+// it to every rank's exchange slot with coalesced 16-byte remote stores from the whole grid (the
+// 36-byte row pieces the combine CTAs would store themselves are too small for NVLink once the
+// vector is hundreds of KB); the CTA that finishes last publishes the sequence number.
+constexpr int PUSH_TPB = 256;
+template <typename T>
+__global__ void __launch_bounds__(PUSH_TPB)
+pcg_push_kernel(size_t n, const T* __restrict__ y, PcgState* __restrict__ st, const PeerExchange px) {
+  if (st->done) return;
+  const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(peer_seq(px)) + 1u;
+  const int parity = (int)(seq & 1u);
+  constexpr int VE = 16 / sizeof(T);
+  const size_t nv = n / VE;
+  for (size_t i = blockIdx.x * (size_t)PUSH_TPB + threadIdx.x; i < nv; i += (size_t)gridDim.x * PUSH_TPB) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(y) + i);
+    for (int dst = 0; dst < px.world; ++dst) reinterpret_cast<float4*>(peer_slot<T>(px, dst, parity, px.rank))[i] = v;
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = nv * VE + threadIdx.x; i < n; i += PUSH_TPB) {
+      const T v = y[i];
+      for (int dst = 0; dst < px.world; ++dst) peer_slot<T>(px, dst, parity, px.rank)[i] = v;
+    }
+  __syncthreads();
+  __shared__ bool last_push__;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last_push__ = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last_push__) {
+    __threadfence_system();
+    if ((int)threadIdx.x < px.world) st_release_sys(peer_flags(px, threadIdx.x, parity) + px.rank, seq);
+    if (threadIdx.x == 0) { *peer_seq(px) = seq; st->ticket = 0u; }
+  }
+}
+
 // multi-rank second half: q = Hd p - y, per-row partial of p.q.  y is either the NCCL
 // all-reduced vector or (PEER) the sum, in rank order, of the `world` partial vectors the ranks
 // pushed into this rank's exchange slots: every rank adds the same numbers in the same order, so
@@ -551,6 +587,9 @@ struct BlockPCG {
     const bool multi = comm_world(comm) > 1;
     const bool peer = multi && comm->peer_ready && (size_t)n_cam * D * sizeof(T) <= comm->px.slot_bytes;
     const PeerExchange px = peer ? comm->px : PeerExchange{};
+    // ISFM_PEER_PUSH = "grid" / "fused" forces the push variant (tests); default: by vector size
+    const char* push_env = getenv("ISFM_PEER_PUSH");
+    const bool big_push = peer && (push_env ? push_env[0] == 'g' : (size_t)n_cam * D * sizeof(T) > ((size_t)128 << 10));
     const bool merged = (int64_t)n_cam * D <= 4096;   // the last CTA of the update kernel also builds p
     { TimerScope ts(kt, T_PCG_VEC);
       pcg_init_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, b, Minv, x.get(), r.get(), p.get(), part_a.get(), part_b.get()); }
@@ -568,10 +607,20 @@ struct BlockPCG {
         pcg_combine_kernel<T, D, COMB_FUSED><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, dep_beg, dep_end, sp.chunk_ptr.get(), (int)unit_lo, (int)unit_hi, yup.get(),
                                                                          C.get(), Hd, p.get(), q.get(), part_pq.get(), state.get(), px);
       } else if (peer) {
-        // all-reduce of y over peer memory: pushed by the combine epilogue, summed by the next kernel
-        { TimerScope ts(kt, T_PCG_VEC);
+        // all-reduce of y over peer memory: pushed by the combine epilogue (small systems) or by a
+        // grid-wide copy kernel (large ones), summed by the next kernel
+        if (big_push) {
+          { TimerScope ts(kt, T_PCG_VEC);
+            pcg_combine_kernel<T, D, COMB_PLAIN><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, dep_beg, dep_end, sp.chunk_ptr.get(), (int)unit_lo, (int)unit_hi, yup.get(),
+                                                                             C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get(), px); }
+          { TimerScope ts(kt, T_COMM);
+            const size_t len = (size_t)n_cam * D;
+            pcg_push_kernel<T><<<(int)std::min<size_t>(div_up(len, PUSH_TPB * (16 / sizeof(T))), 148), PUSH_TPB, 0, s>>>(len, y.get(), state.get(), px); }
+        } else {
+          TimerScope ts(kt, T_PCG_VEC);
           pcg_combine_kernel<T, D, COMB_PUSH><<<nb_comb, COMB_TPB, 0, s>>>(n_cam, dep_beg, dep_end, sp.chunk_ptr.get(), (int)unit_lo, (int)unit_hi, yup.get(),
-                                                                          C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get(), px); }
+                                                                          C.get(), Hd, p.get(), y.get(), part_pq.get(), state.get(), px);
+        }
         { TimerScope ts(kt, T_COMM);
           pcg_apply_diag_kernel<T, D, true><<<nb_diag, PCG_TPB, 0, s>>>(n_cam, Hd, p.get(), y.get(), q.get(), part_pq.get(), state.get(), px); }
       } else {
@@ -596,7 +645,7 @@ struct BlockPCG {
                                                                state.get(), cond, use_cond); }
       }
     };
-    const int vec_per_iter = (merged ? 2 : 3) + (multi ? 1 : 0);
+    const int vec_per_iter = (merged ? 2 : 3) + (multi ? 1 : 0) + (big_push ? 1 : 0);
     // No per-kernel timing and no NCCL call inside the loop (single rank, or the peer-memory
     // exchange): device-side WHILE graph.
     bool use_graph = (!multi || peer) && !kt.enabled && !graph_disabled && !getenv("ISFM_NO_GRAPH");

@@ -8,8 +8,9 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("transport,split", [("peer", False), ("nccl", False), ("peer", True), ("nccl", True)])
-def test_two_rank_solve_matches_single_rank(transport, split):
+@pytest.mark.parametrize("transport,split,push", [("peer", False, None), ("nccl", False, None), ("peer", True, None),
+                                                  ("nccl", True, None), ("peer", False, "grid"), ("peer", True, "grid")])
+def test_two_rank_solve_matches_single_rank(transport, split, push):
     """Both transports of the per-iteration sum (peer-memory exchange fused into the PCG kernels,
     ncclAllReduce), with and without the split mat-vec (summed E reduce-scattered by unit ranges
     when the ranks share one block pattern), must reproduce the single-rank solve."""
@@ -24,6 +25,9 @@ def test_two_rank_solve_matches_single_rank(transport, split):
     if transport == "nccl":
         env["ISFM_NO_PEER"] = "1"
     env["ISFM_SPLIT_MATVEC"] = "1" if split else "0"
+    env.pop("ISFM_PEER_PUSH", None)
+    if push:
+        env["ISFM_PEER_PUSH"] = push   # "grid": the grid-wide push kernel large camera systems use
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and "MULTIGPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
     assert ("transport " + transport + (" split" if split else " nosplit")) in out.stdout, out.stdout[-2000:]

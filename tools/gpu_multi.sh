@@ -20,7 +20,9 @@ except Exception as e:
     print("no bench line", e)
 P
 }
+if [ "${4:-}" != nobench ]; then
 run split "ISFM_X=1" ""
 run nosplit "ISFM_SPLIT_MATVEC=0" ""
+fi
 if [ "${4:-}" = nccl ]; then run nccl "ISFM_NO_PEER=1 ISFM_SPLIT_MATVEC=0" ""; fi
 ls "$OUT"
