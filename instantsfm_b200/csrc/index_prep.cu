@@ -325,7 +325,7 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
     // drop the duplicates (stable sort: the local entry of a run comes first), then sort the
     // survivors to the front again
     dedupe_keys_kernel<<<div_up(n_ent, TPB), TPB, 0, s>>>(ekeys_s.get(), n_ent, ekeys.get());
-    std::swap(etags.ptr, etags_s.ptr); std::swap(etags.count, etags_s.count);
+    etags.swap(etags_s);
     sort_pairs(ekeys.get(), ekeys_s.get(), etags.get(), etags_s.get(), n_ent, 64, s);
     extra.release();
   }
@@ -387,9 +387,9 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
     remap_slots_kernel<<<div_up(n_cam, TPB), TPB, 0, s>>>(n_cam, sp.diag_slot.get(), slot_of.get());
     ISFM_CUDA(cudaGetLastError());
     ISFM_CUDA(cudaStreamSynchronize(s));
-    std::swap(sp.ucol.ptr, ucol_p.ptr); std::swap(sp.ucol.count, ucol_p.count);
-    std::swap(sp.tpos.ptr, tpos_p.ptr); std::swap(sp.tpos.count, tpos_p.count);
-    std::swap(sp.urow_ptr.ptr, d_upp.ptr); std::swap(sp.urow_ptr.count, d_upp.count);
+    sp.ucol.swap(ucol_p);
+    sp.tpos.swap(tpos_p);
+    sp.urow_ptr.swap(d_upp);
     sp.n_blocks = sp.nnzu;
     sp.nnzu = nnzp;
     up = upp;
