@@ -9,6 +9,7 @@
 #include <iterator>
 #include <map>
 #include <mutex>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -131,31 +132,39 @@ inline void ensure_pool_configured() {
 // their size.  Safe because every handle works on one stream and synchronises it before it dies.
 struct BufferCache {
   std::mutex m;
-  std::multimap<size_t, void*> blocks;
+  std::multimap<std::pair<int, size_t>, void*> blocks;   // (device, bytes) -> block: never handed across devices
   size_t cached = 0;
   static constexpr size_t MIN_BYTES = (size_t)1 << 20, LIMIT = (size_t)16 << 30;
   bool enabled = getenv("ISFM_NO_BUFFER_CACHE") == nullptr;
   void* take(size_t bytes, size_t* got) {
     if (!enabled || bytes < MIN_BYTES) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     std::lock_guard<std::mutex> lk(m);
-    auto it = blocks.lower_bound(bytes);
-    if (it == blocks.end() || it->first > bytes + bytes / 8) return nullptr;
+    auto it = blocks.lower_bound(std::make_pair(dev, bytes));
+    if (it == blocks.end() || it->first.first != dev || it->first.second > bytes + bytes / 8) return nullptr;
     void* p = it->second;
-    *got = it->first;
-    cached -= it->first;
+    *got = it->first.second;
+    cached -= it->first.second;
     blocks.erase(it);
     return p;
   }
   void give(void* p, size_t bytes) {
-    if (enabled && bytes >= MIN_BYTES) {
+    int dev = 0;
+    if (enabled && bytes >= MIN_BYTES && cudaGetDevice(&dev) == cudaSuccess) {
+      // (blocks are released under the device they were allocated on: a handle lives on one device)
       std::lock_guard<std::mutex> lk(m);
-      blocks.emplace(bytes, p);
+      blocks.emplace(std::make_pair(dev, bytes), p);
       cached += bytes;
-      while (cached > LIMIT && !blocks.empty()) {
-        auto last = std::prev(blocks.end());
-        cudaFreeAsync(last->second, 0);
-        cached -= last->first;
-        blocks.erase(last);
+      // over the limit: the largest blocks of THIS device go back to the pool
+      while (cached > LIMIT) {
+        auto it = blocks.lower_bound(std::make_pair(dev + 1, (size_t)0));
+        if (it == blocks.begin()) break;
+        --it;
+        if (it->first.first != dev) break;
+        cudaFreeAsync(it->second, 0);
+        cached -= it->first.second;
+        blocks.erase(it);
       }
       return;
     }
