@@ -59,6 +59,10 @@ typedef struct isfm_step_stats {
   int32_t rejects;
   int32_t pcg_iters;    /* total PCG iterations over all trials                          */
   int32_t accepted;     /* 1 if the final trial was kept                                 */
+  int32_t pcg_status;   /* last trial's PCG: 1 converged, 0 hit pcg_max_iter, 2 breakdown
+                           (non-positive curvature / non-finite: x holds the last good
+                           iterate; bae prints and breaks, bundle_adjustment.py:132)      */
+  int32_t reserved;
 } isfm_step_stats;
 
 /* ------------------------------------------------------------------------------------ */
@@ -68,6 +72,14 @@ const char* isfm_version(void);
 const char* isfm_last_error(void);
 /* number of kernel launches issued by this library in this process (bench: gpu_launches) */
 int64_t isfm_launch_count(void);
+/* Device memory: the library allocates from a PRIVATE stream-ordered pool per device (never the
+ * device's default pool, which torch's allocator may share) and keeps freed blocks >= 1 MB in a
+ * process-wide cache for the next handle (the pipeline creates solver after solver of the same
+ * size).  isfm_trim_cache() returns everything to the driver (call it at stage boundaries when
+ * other GPU stages need the memory); isfm_set_cache_limit() bounds the cache (default 4 GB,
+ * also ISFM_CACHE_LIMIT_MB; 0 disables caching).                                             */
+void isfm_trim_cache(void);
+void isfm_set_cache_limit(uint64_t bytes);
 
 /* ------------------------------------------------------------------------------------ */
 /* communicator (multi-GPU; one process per GPU).  No reference counterpart: the           */
@@ -191,6 +203,11 @@ int isfm_ba_debug_get(isfm_ba* h, int32_t what, void* dst);
 int isfm_ba_get_timers(isfm_ba* h, double ms_out[ISFM_N_TIMERS], int64_t launches_out[ISFM_N_TIMERS]);
 int isfm_ba_reset_timers(isfm_ba* h, int32_t enable);
 const char* isfm_timer_name(int32_t i);
+/* Persistent PCG kernel: time (ms, as seen by CTA 0) accumulated per phase since creation --
+ * [0] mat-vec, [1] combine, [2] peer exchange (push + wait + q), [3] update, [4] coarse
+ * correction, [5] direction; *solves_out = PCG solves run by that kernel; *two_level_out = 1 when
+ * the two-level preconditioner (cluster similarity modes) is active.                          */
+int isfm_ba_get_pcg_phases(isfm_ba* h, double ms_out[8], int64_t* solves_out, int32_t* two_level_out);
 
 /* ------------------------------------------------------------------------------------ */
 /* global positioning  (replaces the body of TorchGP.Optimize below the tensor set-up)     */

@@ -18,7 +18,7 @@ class IsfmError(RuntimeError):
 class StepStats(Structure):
     _fields_ = [("loss_before", c_double), ("loss", c_double), ("damping", c_double), ("quality", c_double),
                 ("model_term", c_double), ("step_norm_cam", c_double), ("trials", c_int32), ("rejects", c_int32),
-                ("pcg_iters", c_int32), ("accepted", c_int32)]
+                ("pcg_iters", c_int32), ("accepted", c_int32), ("pcg_status", c_int32), ("reserved", c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -42,6 +42,9 @@ SIGNATURES = {
     "isfm_version": (c_char_p, []),
     "isfm_last_error": (c_char_p, []),
     "isfm_launch_count": (c_int64, []),
+    "isfm_trim_cache": (None, []),
+    "isfm_set_cache_limit": (None, [ctypes.c_uint64]),
+    "isfm_ba_get_pcg_phases": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), POINTER(c_int32)]),
     "isfm_timer_name": (c_char_p, [c_int32]),
     "isfm_comm_unique_id": (c_int, [POINTER(c_uint8)]),
     "isfm_comm_create": (c_int, [POINTER(c_uint8), c_int, c_int, POINTER(c_void_p)]),

@@ -1137,6 +1137,24 @@ backsub_tiles_kernel(const int4* __restrict__ tiles, const int32_t* __restrict__
   if (t == 0) part_m[blockIdx.x] = msum;
 }
 
+// rows of y = E p that can be non-zero on this rank: upper rows with an off-diagonal block and the
+// columns of those blocks (their transposed products); diagonal lists (duplicate cameras in a track)
+static __global__ void touched_rows_kernel(int n_cam, const int32_t* __restrict__ urow_ptr, const int32_t* __restrict__ ucol, uint8_t* touched) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n_cam) return;
+  bool any = false;
+  for (int e = urow_ptr[row] + lane; e < urow_ptr[row + 1]; e += 32) {
+    const int j = ucol[e];
+    if (j != row) { any = true; touched[j] = 1; }   // same value from every writer
+  }
+  if (__any_sync(0xffffffffu, any) && lane == 0) touched[row] = 1;
+}
+static __global__ void touched_diag_lists_kernel(int64_t n_lists, const uint8_t* __restrict__ list_diag, const int32_t* __restrict__ list_slot,
+                                                 const int32_t* __restrict__ ucol, uint8_t* touched) {
+  const int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (u < n_lists && list_diag[u]) touched[ucol[list_slot[u]]] = 1;   // a diagonal slot's column is its row
+}
+
 // gather rows: dst[i] = src[idx[i]] with row width W (set-up only)
 template <typename T>
 __global__ void gather_rows_kernel(int64_t n, int W, const T* __restrict__ src, const int32_t* __restrict__ idx, T* __restrict__ dst) {

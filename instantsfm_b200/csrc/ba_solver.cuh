@@ -9,6 +9,7 @@
 #include "ba_kernels.cuh"
 #include <chrono>
 
+#include "coarse.cuh"
 #include "comm.cuh"
 #include "index_prep.cuh"
 #include "pcg.cuh"
@@ -46,6 +47,7 @@ struct BASolverBase {
   virtual void get_structure(int32_t* obs_perm, int64_t* pt_off, int32_t* cam_perm, int64_t* cam_off) = 0;
   virtual void get_schur_pattern(int64_t* nnzb, int64_t* n_pairs, int64_t* row_ptr, int32_t* col_idx) = 0;
   virtual void debug_get(int what, void* dst) = 0;
+  virtual void get_pcg_phases(double* ms_out, int64_t* solves_out, int32_t* two_level_out) = 0;
   KernelTimers timers;
   bool has_problem = false;
   int64_t matvec_units_owned = 0, matvec_units_total = 0;   // isfm_ba_get_matvec_units
@@ -59,7 +61,6 @@ struct BASolver : BASolverBase {
 
   isfm_ba_desc desc;
   cudaStream_t s;
-  cudaStream_t own_stream = nullptr;
   isfm_comm* comm;
   TrustRegionState tr;
   int64_t n_cam = 0, n_pt = 0, n_obs = 0;
@@ -74,6 +75,7 @@ struct BASolver : BASolverBase {
   DeviceBuffer<int> fail;
   double* h_scalars = nullptr;  // pinned [4]
   BlockPCG<T, D> pcg;
+  CoarseLevel<T, D> coarse;   // two-level preconditioner (chain-like camera graphs), see coarse.cuh
   int cur = 0;
   bool have_loss = false;
   double loss = 0.0;
@@ -93,25 +95,21 @@ struct BASolver : BASolverBase {
   std::vector<size_t> split_off, split_cnt;   // element ranges of E per owner rank
   DeviceBuffer<T> E_own;                      // sum over ranks of this rank's range of E
   bool union_pattern = false;                 // the block pattern is the union over ranks (zero blocks where no local pairs)
+  bool debug = false, no_tile_backsub = false;   // environment switches, read once at creation
   double min_damping = 0.0;   // floor on the LM damping used to build the systems (see DESIGN.md, fp32 conditioning)
 
   explicit BASolver(const isfm_ba_desc& d) : desc(d) {
-    s = static_cast<cudaStream_t>(d.stream);
-    if (s == nullptr) {
-      // the legacy default stream cannot be captured into a CUDA graph: work on an own BLOCKING
-      // stream, which stays implicitly ordered with the caller's legacy-stream work
-      ISFM_CUDA(cudaStreamCreate(&own_stream));
-      s = own_stream;
-    }
+    s = static_cast<cudaStream_t>(d.stream);   // never the legacy default stream: isfm_ba_create substitutes an own stream
     comm = d.comm;
     timers.stream = s;
     tr.init(d.tr_radius, d.tr_max, d.tr_up, d.tr_down);
     ISFM_CUDA(cudaMallocHost(&h_scalars, 4 * sizeof(double)));
     if (const char* e = getenv("ISFM_MIN_DAMPING")) min_damping = atof(e);
+    debug = getenv("ISFM_DEBUG") != nullptr;
+    no_tile_backsub = getenv("ISFM_NO_TILE_BACKSUB") != nullptr;
   }
   ~BASolver() override {
     cudaStreamSynchronize(s);   // buffers go back to the stream-ordered pool after all work has finished
-    if (own_stream) cudaStreamDestroy(own_stream);
     if (h_scalars) cudaFreeHost(h_scalars);
   }
 
@@ -173,6 +171,8 @@ struct BASolver : BASolverBase {
       MINV.alloc((size_t)nc * D * D); bvec.alloc((size_t)nc * D); DCQ.alloc((size_t)nc * BacksubCfg<T, D>::DQ);
       pcg.resize((int)nc, sp.n_off, sp.n_chunks, comm, s);
       setup_matvec_split();
+      setup_exchange_ring();
+      setup_coarse();
       matvec_units_total = sp.n_chunks;
       matvec_units_owned = split_matvec ? unit_hi - unit_lo : sp.n_chunks;
       mark("Schur / PCG allocs + E.zero");
@@ -272,6 +272,76 @@ struct BASolver : BASolverBase {
     E_own.alloc(std::max<size_t>(split_cnt[rank], 1));
     pcg.set_owned_slots(sp, (int64_t)(split_off[rank] / (D * D)), (int64_t)((split_off[rank] + split_cnt[rank]) / (D * D)), s);
     split_matvec = true;
+  }
+
+  // Multi-rank, local patterns (street scenes): the rows of y = E_g p this rank can be non-zero in
+  // form (almost) one arc of the camera ring.  Every rank publishes the smallest circular range
+  // [lo, lo + len) covering its rows; the PCG exchange pushes and sums only those rows.
+  // COLLECTIVE.
+  void setup_exchange_ring() {
+    pcg.ring_valid = false;
+    const int world = comm_world(comm), rank = comm_rank(comm);
+    if (world <= 1 || world > ISFM_MAX_PEERS) return;
+    int lo = 0, len = (int)n_cam;
+    if (!split_matvec && !union_pattern && n_cam >= 64 && !getenv("ISFM_FULL_EXCHANGE")) {
+      DeviceBuffer<uint8_t> touched;
+      touched.alloc((size_t)n_cam);
+      ISFM_CUDA(cudaMemsetAsync(touched.get(), 0, (size_t)n_cam, s));
+      touched_rows_kernel<<<div_up(n_cam, 8), 256, 0, s>>>((int)n_cam, sp.urow_ptr.get(), sp.ucol.get(), touched.get());
+      if (sp.n_lists > 0)
+        touched_diag_lists_kernel<<<div_up(sp.n_lists, 256), 256, 0, s>>>(sp.n_lists, sp.list_diag.get(), sp.list_slot.get(), sp.ucol.get(), touched.get());
+      std::vector<uint8_t> h((size_t)n_cam);
+      ISFM_CUDA(cudaMemcpyAsync(h.data(), touched.get(), (size_t)n_cam, cudaMemcpyDeviceToHost, s));
+      ISFM_CUDA(cudaStreamSynchronize(s));
+      // largest circular gap of untouched rows; the ring is its complement
+      const int n = (int)n_cam;
+      int best_len = 0, best_end = 0, run = 0;
+      for (int k = 0; k < 2 * n; ++k) {
+        if (!h[(size_t)(k % n)]) { if (++run > best_len && run <= n) { best_len = run; best_end = k; } }
+        else run = 0;
+      }
+      if (best_len >= n) { lo = 0; len = 0; }   // nothing touched at all
+      else if (best_len > 0) {
+        lo = (best_end + 1) % n;
+        len = n - best_len;
+        const int lo4 = lo / 4 * 4;
+        len = (len + (lo - lo4) + 3) / 4 * 4;
+        lo = lo4;
+      }
+      if (len >= n * 6 / 10) { lo = 0; len = n; }   // not worth the bookkeeping
+    }
+    int32_t mine[2] = {lo, len};
+    DeviceBuffer<int32_t> d_mine, d_all;
+    d_mine.alloc(2); d_all.alloc((size_t)2 * world);
+    ISFM_CUDA(cudaMemcpyAsync(d_mine.get(), mine, sizeof mine, cudaMemcpyHostToDevice, s));
+    comm_allgather_bytes(comm, d_mine.get(), d_all.get(), sizeof mine, s);
+    std::vector<int32_t> all((size_t)2 * world);
+    ISFM_CUDA(cudaMemcpyAsync(all.data(), d_all.get(), all.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));
+    for (int r = 0; r < world; ++r) { pcg.row_lo[r] = all[(size_t)2 * r]; pcg.row_len[r] = all[(size_t)2 * r + 1]; }
+    pcg.ring_valid = true;
+    (void)rank;
+  }
+
+  // Two-level preconditioner: decided from the GLOBAL sparsity (sum of the ranks' block counts) so
+  // that every rank builds the same clusters.  COLLECTIVE.
+  void setup_coarse() {
+    double n_off_sum = (double)sp.n_off;
+    if (comm_world(comm) > 1) {
+      DeviceBuffer<double> d; d.alloc(1);
+      ISFM_CUDA(cudaMemcpyAsync(d.get(), &n_off_sum, sizeof(double), cudaMemcpyHostToDevice, s));
+      comm_allreduce_sum(comm, d.get(), 1, true, s);
+      ISFM_CUDA(cudaMemcpyAsync(&n_off_sum, d.get(), sizeof(double), cudaMemcpyDeviceToHost, s));
+      ISFM_CUDA(cudaStreamSynchronize(s));
+      if (union_pattern) n_off_sum /= comm_world(comm);   // every rank holds the whole pattern
+    }
+    coarse.setup(sp, (int64_t)n_off_sum, n_cam, s, timers);
+    pcg.coarse = typename BlockPCG<T, D>::CoarseRef{};
+    if (coarse.enabled) {
+      pcg.coarse.enabled = 1; pcg.coarse.cs = coarse.g.cs; pcg.coarse.ncl = coarse.g.ncl; pcg.coarse.ncp = coarse.g.ncp;
+      pcg.coarse.Pm = coarse.Pm.get(); pcg.coarse.Ainv = coarse.Ainv.get(); pcg.coarse.rc = coarse.rc.get();
+      pcg.coarse.fail = coarse.fail.get();
+    }
   }
 
   void pack_cameras(int which) {
@@ -447,6 +517,7 @@ struct BASolver : BASolverBase {
     { TimerScope ts(timers, T_PRECOND);
       precond_kernel<T, D><<<div_up(n_cam, 64), 64, 0, s>>>((int)n_cam, HME.get(), mu, HD.get(), MINV.get(), bvec.get(),
                                                             fail.get()); }
+    coarse.factor(E.get(), HD.get(), sp, comm, s, timers);   // no-op unless the two-level preconditioner is on
     int max_iter = desc.pcg_max_iter > 0 ? desc.pcg_max_iter : (int)std::min<int64_t>(10 * n_cam * D, 5000);
     // split mat-vec: the kernel indexes blocks by their global slot, E_own starts at this rank's first slot
     const T* Emat = split_matvec ? E_own.get() - split_off[comm_rank(comm)] : E.get();
@@ -474,6 +545,7 @@ struct BASolver : BASolverBase {
     isfm_step_stats stats;
     memset(&stats, 0, sizeof stats);
     stats.loss_before = last;
+    if (desc.optimize_poses) coarse.update_modes(cam[cur].get(), CW, s, timers);   // cluster modes at the current poses
     double mu = 1.0;
     bool built = false;
     int rejects = 0;
@@ -487,7 +559,8 @@ struct BASolver : BASolverBase {
       if (desc.optimize_poses) {
         int pcg_status = 0;
         stats.pcg_iters += run_schur_and_pcg((T)mu, &pcg_status);
-        if (getenv("ISFM_DEBUG")) {
+        stats.pcg_status = pcg_status;
+        if (debug) {
           int h_fail = 0;
           ISFM_CUDA(cudaMemcpyAsync(&h_fail, fail.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
           ISFM_CUDA(cudaStreamSynchronize(s));
@@ -503,7 +576,7 @@ struct BASolver : BASolverBase {
             ISFM_CUDA(cudaMemsetAsync(fail.get(), 0, sizeof(int), s));
           }
         }
-        if (fused_ok && !getenv("ISFM_NO_TILE_BACKSUB")) {
+        if (fused_ok && !no_tile_backsub) {
           constexpr int DQ = BacksubCfg<T, D>::DQ;
           { TimerScope ts(timers, T_MISC);
             pad_rows_kernel<T><<<div_up(n_cam * DQ, 256), 256, 0, s>>>((int)n_cam, D, DQ, pcg.x.get(), DCQ.get()); }
@@ -544,10 +617,13 @@ struct BASolver : BASolverBase {
       stats.trials++;
       stats.model_term = -mterm;
       stats.quality = tr.update(last, new_loss, mterm);
-      if (getenv("ISFM_DEBUG"))
+      if (debug)
         fprintf(stderr, "[isfm] trial %d mu %.3e last %.17g new %.17g mterm %.6e quality %.4f pcg_iters %d damping->%.3e\n",
                 stats.trials, mu, last, new_loss, mterm, stats.quality, stats.pcg_iters, tr.damping);
       const bool worse = !(new_loss <= last);  // NaN counts as worse (the reference would keep it)
+      // never accept a non-finite state (the reference would; its write-back would then poison the scene)
+      if (!std::isfinite(new_loss) && rejects >= desc.reject)
+        throw IsfmError(ISFM_ENONFINITE, "trial cost is not finite after the last allowed rejection");
       if (worse && rejects < desc.reject) {
         rejects++;
         loss = last;
@@ -567,6 +643,12 @@ struct BASolver : BASolverBase {
     ISFM_CUDA(cudaGetLastError());
     if (loss_out) *loss_out = loss;
     if (st) *st = stats;
+  }
+
+  void get_pcg_phases(double* ms_out, int64_t* solves_out, int32_t* two_level_out) override {
+    if (ms_out) for (int i = 0; i < 8; ++i) ms_out[i] = pcg.phase_ms[i];
+    if (solves_out) *solves_out = pcg.persist_solves;
+    if (two_level_out) *two_level_out = coarse.enabled ? 1 : 0;
   }
 
   void get_params(void* cam_out, void* pts_out) override {

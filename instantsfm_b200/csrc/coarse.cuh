@@ -1,0 +1,334 @@
+// coarse.cuh -- coarse level of the two-level PCG preconditioner for the reduced camera system
+// (see pcg_persistent.cuh).
+//
+// Cameras are grouped into clusters of `cs` consecutive cameras (image ids follow the capture
+// order on the sequences where this matters: street / video).  Every cluster carries the seven
+// similarity modes of a rigid piece of the scene -- world translation v, rotation w about the
+// cluster's centroid, scale s about the centroid -- expressed in each camera's left-perturbation
+// tangent [dtau, dphi] (pose = world2cam (R, t), update T <- Exp(delta) T):
+//     X_w' = c0 + s Exp(w) (X_w - c0) + v   =>   dphi = -R w,  dtau = -R v - tt x (R w) + s tt,
+//     tt = t + R c0  (translation of the camera w.r.t. the shifted world origin c0).
+// Moving a whole cluster rigidly (with its points, which the Schur complement has eliminated)
+// costs almost no energy, so these are the slowest modes of S on long camera chains; block-Jacobi
+// cannot see them.  Ac = P^T S P is formed from the stored upper blocks (deterministic segmented
+// sums, no atomics), all-reduced across ranks, and inverted densely in fp64 by a blocked
+// Gauss-Jordan sweep (SPD, no pivoting) -- the coarse dimension is 7 * clusters <= ~2 100.
+#pragma once
+#include <cub/cub.cuh>
+
+#include "comm.cuh"
+#include "common.cuh"
+#include "index_prep.cuh"
+#include "math.cuh"
+
+namespace isfm {
+
+constexpr int CM = 7;          // coarse modes per cluster (== PCG_MODES)
+constexpr int GJ_B = 32;       // pivot block of the dense inverse
+
+struct CoarseGeom {
+  int n_cam = 0, cs = 0, ncl = 0, ncp = 0;
+  __host__ __device__ int cluster_of(int cam) const { const int c = cam / cs; return c < ncl ? c : ncl - 1; }
+  __host__ __device__ int begin(int cl) const { return cl * cs; }
+  __host__ __device__ int end(int cl) const { return cl == ncl - 1 ? n_cam : (cl + 1) * cs; }
+};
+
+// ---- set-up: upper slots grouped by coarse block (I, J), I <= J ----
+static __global__ void coarse_slot_keys_kernel(CoarseGeom g, const int32_t* __restrict__ urow_ptr, const int32_t* __restrict__ ucol,
+                                               uint32_t* keys, int32_t* vals, int32_t* row_of) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= g.n_cam) return;
+  const int ci = g.cluster_of(row);
+  for (int e = urow_ptr[row] + lane; e < urow_ptr[row + 1]; e += 32) {
+    keys[e] = (uint32_t)(ci * g.ncl + g.cluster_of(ucol[e]));
+    vals[e] = e;
+    row_of[e] = row;
+  }
+}
+static __global__ void coarse_offsets_kernel(const uint32_t* __restrict__ sorted, int64_t n, int32_t* off, int64_t n_keys) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k > n_keys) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (sorted[mid] < (uint32_t)k) lo = mid + 1; else hi = mid;
+  }
+  off[k] = (int32_t)lo;
+}
+
+// ---- per LM step: the prolongation blocks P_i (6 x 7) from the current poses ----
+template <typename T>
+__global__ void coarse_centroid_kernel(CoarseGeom g, int cw, const T* __restrict__ cam, double* __restrict__ c0) {
+  const int cl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cl >= g.ncl) return;
+  double s[3] = {0, 0, 0};
+  for (int i = g.begin(cl); i < g.end(cl); ++i) {
+    const T* c = cam + (size_t)i * cw;
+    double R[9];
+    const double q[4] = {(double)c[3], (double)c[4], (double)c[5], (double)c[6]};
+    quat_to_rot(q, R);
+    // centre = -R^T t
+    for (int k = 0; k < 3; ++k) s[k] -= R[0 * 3 + k] * (double)c[0] + R[1 * 3 + k] * (double)c[1] + R[2 * 3 + k] * (double)c[2];
+  }
+  const double inv = 1.0 / (double)(g.end(cl) - g.begin(cl));
+  for (int k = 0; k < 3; ++k) c0[cl * 3 + k] = s[k] * inv;
+}
+template <typename T>
+__global__ void coarse_modes_kernel(CoarseGeom g, int cw, const T* __restrict__ cam, const double* __restrict__ c0, T* __restrict__ Pm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n_cam) return;
+  const T* c = cam + (size_t)i * cw;
+  const double* o = c0 + g.cluster_of(i) * 3;
+  double R[9];
+  const double q[4] = {(double)c[3], (double)c[4], (double)c[5], (double)c[6]};
+  quat_to_rot(q, R);
+  double tt[3];
+  for (int k = 0; k < 3; ++k) tt[k] = (double)c[k] + R[k * 3 + 0] * o[0] + R[k * 3 + 1] * o[1] + R[k * 3 + 2] * o[2];
+  const double tx[9] = {0, -tt[2], tt[1], tt[2], 0, -tt[0], -tt[1], tt[0], 0};
+  T* P = Pm + (size_t)i * (6 * CM);
+  for (int r = 0; r < 3; ++r) {
+    for (int k = 0; k < 3; ++k) {
+      P[r * CM + k] = (T)(-R[r * 3 + k]);                                                                   // dtau / v
+      P[r * CM + 3 + k] = (T)(-(tx[r * 3 + 0] * R[0 * 3 + k] + tx[r * 3 + 1] * R[1 * 3 + k] + tx[r * 3 + 2] * R[2 * 3 + k]));   // dtau / w
+      P[(3 + r) * CM + k] = T(0);                                                                           // dphi / v
+      P[(3 + r) * CM + 3 + k] = (T)(-R[r * 3 + k]);                                                         // dphi / w
+    }
+    P[r * CM + 6] = (T)tt[r];                                                                               // dtau / s
+    P[(3 + r) * CM + 6] = T(0);
+  }
+}
+
+// ---- per trial: G = P^T E P (dense [ncp][ncp], fp64), one CTA per coarse block (I <= J) ----
+// A group of 8 lanes (7 working) owns one member block at a time; lane k forms column k of
+// X = P_i^T B P_j and keeps 7 fp64 accumulators.  The groups' sums are added in group order.
+constexpr int GAL_TPB = 128;
+template <typename T, int D>
+__global__ void __launch_bounds__(GAL_TPB)
+coarse_galerkin_kernel(CoarseGeom g, const int32_t* __restrict__ coff, const int32_t* __restrict__ cslot,
+                       const int32_t* __restrict__ row_of, const int32_t* __restrict__ ucol, const T* __restrict__ E,
+                       const T* __restrict__ Pm, double* __restrict__ G) {
+  const int I = blockIdx.x / g.ncl, J = blockIdx.x % g.ncl;
+  if (I > J) return;
+  constexpr int NG = GAL_TPB / 8;
+  __shared__ double part[NG][2][CM * CM];   // [group][off-diagonal members | diagonal members][r * CM + k]
+  const int grp = threadIdx.x >> 3, k = threadIdx.x & 7;
+  double acc[CM], accd[CM];
+#pragma unroll
+  for (int r = 0; r < CM; ++r) { acc[r] = 0.0; accd[r] = 0.0; }
+  const int beg = coff[I * g.ncl + J], end = coff[I * g.ncl + J + 1];
+  if (k < CM) {
+    for (int m = beg + grp; m < end; m += NG) {
+      const int e = cslot[m], i = row_of[e], j = ucol[e];
+      const T* __restrict__ B = E + (size_t)e * (D * D);
+      const T* __restrict__ Pi = Pm + (size_t)i * (6 * CM);
+      const T* __restrict__ Pj = Pm + (size_t)j * (6 * CM);
+      double t[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s += (double)B[r * D + c] * (double)Pj[c * CM + k];
+        t[r] = s;
+      }
+      const bool dg = i == j;
+#pragma unroll
+      for (int r = 0; r < CM; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s += (double)Pi[c * CM + r] * t[c];
+        if (dg) accd[r] += s; else acc[r] += s;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < CM; ++r) { part[grp][0][r * CM + k] = acc[r]; part[grp][1][r * CM + k] = accd[r]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < CM * CM) {
+    const int r = threadIdx.x / CM, c = threadIdx.x % CM;
+    double x = 0.0, xt = 0.0, xd = 0.0;
+    for (int q = 0; q < NG; ++q) { x += part[q][0][r * CM + c]; xt += part[q][0][c * CM + r]; xd += part[q][1][r * CM + c]; }
+    if (I == J) {
+      G[(size_t)(I * CM + r) * g.ncp + J * CM + c] = x + xt + xd;   // pairs (i, j) and (j, i) of one cluster, diagonal blocks once
+    } else {
+      G[(size_t)(I * CM + r) * g.ncp + J * CM + c] = x + xd;
+      G[(size_t)(J * CM + c) * g.ncp + I * CM + r] = x + xd;        // mirrored coarse block
+    }
+  }
+}
+
+// A = P^T Hd P - G  (Hd: the damped diagonal blocks S_ii; added once, after the all-reduce of G);
+// padding rows / columns: identity.  One CTA per coarse row block.
+template <typename T, int D>
+__global__ void __launch_bounds__(128)
+coarse_assemble_kernel(CoarseGeom g, const T* __restrict__ Hd, const T* __restrict__ Pm, const double* __restrict__ G, double* __restrict__ A) {
+  __shared__ double H[CM * CM];
+  const int I = blockIdx.x;
+  if (I < g.ncl) {
+    if (threadIdx.x < CM * CM) {
+      const int r = threadIdx.x / CM, c = threadIdx.x % CM;
+      double s = 0.0;
+      for (int i = g.begin(I); i < g.end(I); ++i) {
+        const T* __restrict__ h = Hd + (size_t)i * (D * D);
+        const T* __restrict__ P = Pm + (size_t)i * (6 * CM);
+        for (int a = 0; a < 6; ++a) {
+          double t = 0.0;
+          for (int b = 0; b < 6; ++b) t += (double)h[a * D + b] * (double)P[b * CM + c];
+          s += (double)P[a * CM + r] * t;
+        }
+      }
+      H[threadIdx.x] = s;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < CM * g.ncp; idx += blockDim.x) {
+      const int r = idx / g.ncp, col = idx % g.ncp;
+      const size_t o = (size_t)(I * CM + r) * g.ncp + col;
+      double v = col < g.ncl * CM ? -G[o] : 0.0;
+      if (col / CM == I && col < g.ncl * CM) v += H[r * CM + col % CM];
+      A[o] = v;
+    }
+  } else {
+    // padding rows [ncl * CM, ncp): identity
+    const int r0 = g.ncl * CM;
+    for (size_t idx = threadIdx.x; idx < (size_t)(g.ncp - r0) * g.ncp; idx += blockDim.x) {
+      const int r = r0 + (int)(idx / g.ncp), col = (int)(idx % g.ncp);
+      A[(size_t)r * g.ncp + col] = r == col ? 1.0 : 0.0;
+    }
+  }
+}
+
+// ---- dense SPD inverse, in place, blocked Gauss-Jordan without pivoting (fp64) ----
+// step k, kernel A (CTA per 32-column tile J): Pinv = A[K,K]^-1 (every CTA, in shared memory);
+//   ROW[:, J] = Pinv A[K, J];  COL[J, :] = A[J, K] (copy);  CTA K stores Pinv.
+// step k, kernel B (CTA per 32 x 32 tile (I, J)):
+//   I != K, J != K: A[I,J] -= COL[I] ROW[J];  I == K: A[K,J] = ROW[J];  J == K: A[I,K] = -COL[I] Pinv;  (K,K): Pinv.
+static __global__ void __launch_bounds__(GJ_B * GJ_B)
+gj_panel_kernel(int n, int kb, const double* __restrict__ A, double* __restrict__ ROW, double* __restrict__ COL,
+                double* __restrict__ PINV, int* __restrict__ fail) {
+  __shared__ double M[GJ_B][GJ_B + 1], Inv[GJ_B][GJ_B + 1], Tl[GJ_B][GJ_B + 1];
+  const int tx = threadIdx.x % GJ_B, ty = threadIdx.x / GJ_B, J = blockIdx.x, K = kb;
+  M[ty][tx] = A[(size_t)(K * GJ_B + ty) * n + K * GJ_B + tx];
+  Inv[ty][tx] = ty == tx ? 1.0 : 0.0;
+  Tl[ty][tx] = A[(size_t)(K * GJ_B + ty) * n + J * GJ_B + tx];           // A[K, J] tile
+  COL[(size_t)(J * GJ_B + ty) * GJ_B + tx] = A[(size_t)(J * GJ_B + ty) * n + K * GJ_B + tx];   // A[J, K] tile
+  __syncthreads();
+  // Gauss-Jordan on [M | Inv]
+  for (int p = 0; p < GJ_B; ++p) {
+    const double piv = M[p][p];
+    if (!(piv > 0.0) && threadIdx.x == 0) *fail = 1;
+    const double ip = 1.0 / piv;
+    __syncthreads();
+    if (ty == p) { M[p][tx] *= ip; Inv[p][tx] *= ip; }
+    __syncthreads();
+    const double f = M[ty][p];
+    __syncthreads();
+    if (ty != p) { M[ty][tx] -= f * M[p][tx]; Inv[ty][tx] -= f * Inv[p][tx]; }
+    __syncthreads();
+  }
+  double s = 0.0;
+#pragma unroll 8
+  for (int c = 0; c < GJ_B; ++c) s += Inv[ty][c] * Tl[c][tx];
+  ROW[(size_t)ty * n + J * GJ_B + tx] = s;
+  if (J == K) PINV[ty * GJ_B + tx] = Inv[ty][tx];
+}
+static __global__ void __launch_bounds__(GJ_B * GJ_B)
+gj_update_kernel(int n, int kb, double* __restrict__ A, const double* __restrict__ ROW, const double* __restrict__ COL,
+                 const double* __restrict__ PINV) {
+  __shared__ double Cs[GJ_B][GJ_B + 1], Rs[GJ_B][GJ_B + 1];
+  const int tx = threadIdx.x % GJ_B, ty = threadIdx.x / GJ_B, I = blockIdx.y, J = blockIdx.x, K = kb;
+  double* dst = A + (size_t)(I * GJ_B + ty) * n + J * GJ_B + tx;
+  if (I == K && J == K) { *dst = PINV[ty * GJ_B + tx]; return; }
+  if (I == K) { *dst = ROW[(size_t)ty * n + J * GJ_B + tx]; return; }
+  Cs[ty][tx] = COL[(size_t)(I * GJ_B + ty) * GJ_B + tx];
+  Rs[ty][tx] = J == K ? PINV[ty * GJ_B + tx] : ROW[(size_t)ty * n + J * GJ_B + tx];
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll 8
+  for (int c = 0; c < GJ_B; ++c) s += Cs[ty][c] * Rs[c][tx];
+  *dst = J == K ? -s : *dst - s;
+}
+template <typename T>
+__global__ void coarse_store_kernel(size_t n, const double* __restrict__ A, T* __restrict__ out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (T)A[i];
+}
+
+template <typename T, int D>
+struct CoarseLevel {
+  bool enabled = false;
+  CoarseGeom g;
+  DeviceBuffer<int32_t> coff, cslot, row_of;
+  DeviceBuffer<double> c0, G, A, ROW, COL, PINV, rc;
+  DeviceBuffer<T> Pm, Ainv;
+  DeviceBuffer<int> fail;
+
+  // decides whether the coarse level pays (sparse, chain-like camera graph) and builds the slot lists
+  // n_off_global: strictly-upper blocks of the whole reduced system (all ranks)
+  void setup(const SchurPattern& sp, int64_t n_off_global, int64_t n_cam, cudaStream_t s, KernelTimers& kt) {
+    enabled = false;
+    if (D < CM) return;
+    const char* env = getenv("ISFM_TWO_LEVEL");   // "0": never, "1": always, unset: by sparsity
+    if (env && atoi(env) == 0) return;
+    const double density = (double)n_off_global / std::max(1.0, 0.5 * (double)n_cam * (double)(n_cam - 1));
+    const bool sparse_chain = n_cam >= 512 && density < 0.15;
+    if (!(env ? atoi(env) != 0 : sparse_chain) || n_cam < 8) return;
+    // cluster size: a quarter of the mean upper row length (~ the co-visibility window), at most ~292 clusters
+    int cs = (int)std::max<int64_t>(4, n_off_global / std::max<int64_t>(n_cam, 1) / 4);
+    if (const char* e = getenv("ISFM_COARSE_CS")) cs = std::max(2, atoi(e));
+    cs = std::max<int>(cs, (int)((n_cam + 291) / 292));
+    cs = (int)std::min<int64_t>(cs, std::max<int64_t>(n_cam / 2, 2));
+    g.n_cam = (int)n_cam; g.cs = cs; g.ncl = std::max(1, (int)(n_cam / cs));
+    g.ncp = (g.ncl * CM + GJ_B - 1) / GJ_B * GJ_B;
+    TimerScope ts(kt, T_INDEX_PREP);
+    const int64_t nnzu = sp.nnzu;
+    DeviceBuffer<uint32_t> keys, keys_s; DeviceBuffer<int32_t> vals;
+    keys.alloc(nnzu); keys_s.alloc(nnzu); vals.alloc(nnzu); cslot.alloc(nnzu); row_of.alloc(nnzu);
+    coarse_slot_keys_kernel<<<div_up(n_cam, 8), 256, 0, s>>>(g, sp.urow_ptr.get(), sp.ucol.get(), keys.get(), vals.get(), row_of.get());
+    size_t bytes = 0;
+    int end_bit = 1;
+    while ((1ll << end_bit) < (int64_t)g.ncl * g.ncl) ++end_bit;
+    ISFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.get(), keys_s.get(), vals.get(), cslot.get(), nnzu, 0, end_bit, s));
+    DeviceBuffer<uint8_t> tmp; tmp.alloc(bytes);
+    ISFM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), bytes, keys.get(), keys_s.get(), vals.get(), cslot.get(), nnzu, 0, end_bit, s));
+    const int64_t nk = (int64_t)g.ncl * g.ncl;
+    coff.alloc(nk + 1);
+    coarse_offsets_kernel<<<div_up(nk + 1, 256), 256, 0, s>>>(keys_s.get(), nnzu, coff.get(), nk);
+    ISFM_CUDA(cudaGetLastError());
+    ISFM_CUDA(cudaStreamSynchronize(s));   // temporaries go out of scope
+    const size_t nn = (size_t)g.ncp * g.ncp;
+    c0.alloc((size_t)g.ncl * 3); G.alloc(nn); A.alloc(nn); ROW.alloc((size_t)GJ_B * g.ncp); COL.alloc((size_t)g.ncp * GJ_B);
+    PINV.alloc(GJ_B * GJ_B); rc.alloc(g.ncp); Pm.alloc((size_t)n_cam * 6 * CM); Ainv.alloc(nn); fail.alloc(1);
+    enabled = true;
+  }
+
+  // prolongation from the current camera rows ([n_cam][cw], t | q_xyzw | ...): once per LM step
+  void update_modes(const T* cam, int cw, cudaStream_t s, KernelTimers& kt) {
+    if (!enabled) return;
+    TimerScope ts(kt, T_PRECOND);
+    coarse_centroid_kernel<T><<<div_up(g.ncl, 128), 128, 0, s>>>(g, cw, cam, c0.get());
+    coarse_modes_kernel<T><<<div_up(g.n_cam, 128), 128, 0, s>>>(g, cw, cam, c0.get(), Pm.get());
+  }
+
+  // Ac^-1 for the current damped system: once per trial.  E: this rank's (partial) upper blocks.
+  void factor(const T* E, const T* Hd, const SchurPattern& sp, isfm_comm* comm, cudaStream_t s, KernelTimers& kt) {
+    if (!enabled) return;
+    { TimerScope ts(kt, T_PRECOND);
+      ISFM_CUDA(cudaMemsetAsync(G.get(), 0, (size_t)g.ncp * g.ncp * sizeof(double), s));
+      coarse_galerkin_kernel<T, D><<<g.ncl * g.ncl, GAL_TPB, 0, s>>>(g, coff.get(), cslot.get(), row_of.get(), sp.ucol.get(), E, Pm.get(), G.get()); }
+    if (comm_world(comm) > 1) {
+      TimerScope ts(kt, T_COMM);
+      comm_allreduce_sum(comm, G.get(), (size_t)g.ncp * g.ncp, true, s);
+    }
+    TimerScope ts(kt, T_PRECOND);
+    coarse_assemble_kernel<T, D><<<g.ncl + 1, 128, 0, s>>>(g, Hd, Pm.get(), G.get(), A.get());
+    ISFM_CUDA(cudaMemsetAsync(fail.get(), 0, sizeof(int), s));
+    const int nb = g.ncp / GJ_B;
+    for (int k = 0; k < nb; ++k) {
+      gj_panel_kernel<<<nb, GJ_B * GJ_B, 0, s>>>(g.ncp, k, A.get(), ROW.get(), COL.get(), PINV.get(), fail.get());
+      gj_update_kernel<<<dim3(nb, nb), GJ_B * GJ_B, 0, s>>>(g.ncp, k, A.get(), ROW.get(), COL.get(), PINV.get());
+    }
+    coarse_store_kernel<T><<<div_up((int64_t)g.ncp * g.ncp, 256), 256, 0, s>>>((size_t)g.ncp * g.ncp, A.get(), Ainv.get());
+    ISFM_CUDA(cudaGetLastError());
+  }
+};
+
+}  // namespace isfm

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <iterator>
 #include <map>
@@ -44,7 +45,9 @@ struct IsfmError : std::runtime_error {
   } while (0)
 
 // global launch counter (isfm_launch_count) -- the bench reports it as gpu_launches
-extern int64_t g_launch_count;
+extern std::atomic<int64_t> g_launch_count;
+// false while a thread records kernels into a CUDA graph (captured, not executed)
+inline bool& tl_count_launches() { static thread_local bool on = true; return on; }
 
 enum Timer {
   T_LINEARIZE = 0, T_POINT_BLOCKS, T_POINT_SOLVE, T_CAMERA_BLOCKS, T_SCHUR_OFFDIAG, T_PRECOND,
@@ -55,6 +58,8 @@ static_assert(T_SPARE + 1 == ISFM_N_TIMERS, "timer table size");
 // Optional per-kernel-family CUDA-event timing on the handle's stream.
 struct KernelTimers {
   bool enabled = false;
+  bool fine = false;   // per-iteration kernels instead of the persistent PCG kernel (ISFM_TIMERS_FINE=1)
+  bool enabled_fine() const { return enabled && fine; }
   cudaStream_t stream = nullptr;
   double ms[ISFM_N_TIMERS] = {0};
   int64_t launches[ISFM_N_TIMERS] = {0};
@@ -68,7 +73,7 @@ struct KernelTimers {
   }
   void begin(int id) {
     launches[id]++;
-    g_launch_count++;
+    if (tl_count_launches()) g_launch_count++;
     if (!enabled) return;
     Pending p{get_event(), get_event(), id};
     ISFM_CUDA(cudaEventRecord(p.a, stream));
@@ -93,6 +98,7 @@ struct KernelTimers {
     resolve();
     for (int i = 0; i < ISFM_N_TIMERS; ++i) { ms[i] = 0; launches[i] = 0; }
     enabled = enable;
+    fine = getenv("ISFM_TIMERS_FINE") != nullptr;
   }
   ~KernelTimers() {
     for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -107,20 +113,71 @@ struct TimerScope {
   ~TimerScope() { t.end(); }
 };
 
-// Device memory comes from the device's default stream-ordered pool with an unlimited release
-// threshold: buffers freed by one handle are re-used by the next (the reference's pipeline
-// creates three BA solvers back to back) instead of going back to the driver.
-inline void ensure_pool_configured() {
-  static bool done = false;
-  if (done) return;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    uint64_t threshold = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+// ---------------------------------------------------------------------------------------
+// Device / stream context of the calling host thread.  Every C entry point (destroy included)
+// opens a CtxGuard with the handle's device and stream: the device becomes current for the call
+// and every DeviceBuffer allocated or released inside it is ordered on that stream.
+// ---------------------------------------------------------------------------------------
+struct DeviceCtx {
+  int dev = -1;
+  cudaStream_t stream = nullptr;
+  bool synced = false;   // the stream has been synchronised and receives no more work (handle teardown)
+};
+inline DeviceCtx& tl_ctx() { static thread_local DeviceCtx c; return c; }
+
+struct CtxGuard {
+  DeviceCtx saved;
+  int prev_dev = -1, dev = -1;
+  CtxGuard(int dev_, cudaStream_t s) : dev(dev_) {
+    saved = tl_ctx();
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; } }
+    if (cudaGetDevice(&prev_dev) != cudaSuccess) { cudaGetLastError(); prev_dev = -1; }
+    if (prev_dev != dev) cudaSetDevice(dev);
+    tl_ctx() = DeviceCtx{dev, s, false};
   }
-  done = true;
+  void mark_synced() { tl_ctx().synced = true; }
+  ~CtxGuard() {
+    tl_ctx() = saved;
+    if (prev_dev >= 0 && prev_dev != dev) cudaSetDevice(prev_dev);
+  }
+  CtxGuard(const CtxGuard&) = delete;
+  CtxGuard& operator=(const CtxGuard&) = delete;
+};
+
+// Device memory comes from a PRIVATE stream-ordered pool per device (never the device's default
+// pool, which torch's cudaMallocAsync backend shares): its release threshold is unlimited so that
+// buffers freed by one handle are re-used by the next (the reference's pipeline creates three BA
+// solvers back to back), and isfm_trim_cache() hands everything back to the driver.
+constexpr int ISFM_MAX_DEVICES = 64;
+struct DevicePools {
+  std::mutex m;
+  cudaMemPool_t pool[ISFM_MAX_DEVICES] = {nullptr};
+  cudaMemPool_t get(int dev) {
+    if (dev < 0 || dev >= ISFM_MAX_DEVICES) return nullptr;
+    std::lock_guard<std::mutex> lk(m);
+    if (pool[dev]) return pool[dev];
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t p = nullptr;
+    if (cudaMemPoolCreate(&p, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    uint64_t threshold = ~0ull;
+    cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &threshold);
+    pool[dev] = p;
+    return p;
+  }
+};
+inline DevicePools& device_pools() { static DevicePools* p = new DevicePools(); return *p; }
+
+inline void* pool_alloc(int dev, size_t bytes, cudaStream_t s) {
+  void* p = nullptr;
+  cudaMemPool_t pool = device_pools().get(dev);
+  if (pool) ISFM_CUDA(cudaMallocFromPoolAsync(&p, bytes, pool, s));
+  else ISFM_CUDA(cudaMallocAsync(&p, bytes, s));
+  return p;
 }
 
 // Process-wide cache of large device blocks.  The pipeline creates solver after solver of (almost)
@@ -128,47 +185,96 @@ inline void ensure_pool_configured() {
 // handle straight to the next avoids the pool's sub-allocation of big free chunks by small
 // requests, which fragments it and makes later handles map new physical memory -- measured as
 // set-up stalls of up to 0.9 s on a 5 M-observation problem.  Blocks of >= 1 MB are kept (up to
-// 16 GB in total, then the largest go back to the pool) and re-used for requests of 88..100 % of
-// their size.  Safe because every handle works on one stream and synchronises it before it dies.
+// `limit` bytes per process, default 4 GB, ISFM_CACHE_LIMIT_MB / isfm_set_cache_limit; beyond it
+// the largest go back to the pool) and re-used for requests of 88..100 % of their size.
+// Stream safety: a block is filed under the device it was allocated on together with an event
+// recorded on the stream that released it; whoever takes it makes its own stream wait on that
+// event first, so a block handed to another handle / stream is never written while work of the
+// previous owner is still in flight.  Blocks released during handle teardown (stream already
+// synchronised) carry no event.
 struct BufferCache {
+  struct Block { void* p; cudaEvent_t ev; cudaStream_t stream; };
   std::mutex m;
-  std::multimap<std::pair<int, size_t>, void*> blocks;   // (device, bytes) -> block: never handed across devices
+  std::multimap<std::pair<int, size_t>, Block> blocks;   // (device, bytes) -> block
   size_t cached = 0;
-  static constexpr size_t MIN_BYTES = (size_t)1 << 20, LIMIT = (size_t)16 << 30;
+  static constexpr size_t MIN_BYTES = (size_t)1 << 20;
+  size_t limit = (size_t)4 << 30;
   bool enabled = getenv("ISFM_NO_BUFFER_CACHE") == nullptr;
-  void* take(size_t bytes, size_t* got) {
+  BufferCache() { if (const char* e = getenv("ISFM_CACHE_LIMIT_MB")) limit = (size_t)atoll(e) << 20; }
+  void* take(int dev, size_t bytes, cudaStream_t s, size_t* got) {
     if (!enabled || bytes < MIN_BYTES) return nullptr;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    std::lock_guard<std::mutex> lk(m);
-    auto it = blocks.lower_bound(std::make_pair(dev, bytes));
-    if (it == blocks.end() || it->first.first != dev || it->first.second > bytes + bytes / 8) return nullptr;
-    void* p = it->second;
-    *got = it->first.second;
-    cached -= it->first.second;
-    blocks.erase(it);
-    return p;
-  }
-  void give(void* p, size_t bytes) {
-    int dev = 0;
-    if (enabled && bytes >= MIN_BYTES && cudaGetDevice(&dev) == cudaSuccess) {
-      // (blocks are released under the device they were allocated on: a handle lives on one device)
+    Block b;
+    {
       std::lock_guard<std::mutex> lk(m);
-      blocks.emplace(std::make_pair(dev, bytes), p);
-      cached += bytes;
-      // over the limit: the largest blocks of THIS device go back to the pool
-      while (cached > LIMIT) {
-        auto it = blocks.lower_bound(std::make_pair(dev + 1, (size_t)0));
-        if (it == blocks.begin()) break;
-        --it;
-        if (it->first.first != dev) break;
-        cudaFreeAsync(it->second, 0);
-        cached -= it->first.second;
-        blocks.erase(it);
+      auto it = blocks.lower_bound(std::make_pair(dev, bytes));
+      if (it == blocks.end() || it->first.first != dev || it->first.second > bytes + bytes / 8) return nullptr;
+      b = it->second;
+      *got = it->first.second;
+      cached -= it->first.second;
+      blocks.erase(it);
+    }
+    if (b.ev) {
+      if (b.stream != s) cudaStreamWaitEvent(s, b.ev, 0);   // same stream: already ordered
+      cudaEventDestroy(b.ev);
+    }
+    return b.p;
+  }
+  // `s` = stream the block was used on; `synced` = that stream is idle for good (no event needed)
+  void give(int dev, void* p, size_t bytes, cudaStream_t s, bool synced) {
+    if (enabled && bytes >= MIN_BYTES && limit > 0) {
+      Block b{p, nullptr, s};
+      if (!synced) {
+        if (cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(b.ev, s) != cudaSuccess) {
+          cudaGetLastError();
+          if (b.ev) cudaEventDestroy(b.ev);
+          cudaFreeAsync(p, s);
+          return;
+        }
       }
+      std::vector<Block> evicted;
+      {
+        std::lock_guard<std::mutex> lk(m);
+        blocks.emplace(std::make_pair(dev, bytes), b);
+        cached += bytes;
+        // over the limit: the largest blocks of THIS device go back to the pool
+        while (cached > limit) {
+          auto it = blocks.lower_bound(std::make_pair(dev + 1, (size_t)0));
+          if (it == blocks.begin()) break;
+          --it;
+          if (it->first.first != dev) break;
+          evicted.push_back(it->second);
+          cached -= it->first.second;
+          blocks.erase(it);
+        }
+      }
+      for (auto& e : evicted) free_block(e, s);
       return;
     }
-    cudaFreeAsync(p, 0);
+    if (synced) cudaFree(p); else cudaFreeAsync(p, s);
+  }
+  // frees a cached block of the CURRENT device on stream `s`, after the work of its last user
+  static void free_block(const Block& b, cudaStream_t s) {
+    if (b.ev) { if (b.stream != s) cudaStreamWaitEvent(s, b.ev, 0); cudaEventDestroy(b.ev); }
+    cudaFreeAsync(b.p, s);
+  }
+  // every cached block back to its pool, the pools back to the driver (isfm_trim_cache)
+  void trim() {
+    std::multimap<std::pair<int, size_t>, Block> all;
+    { std::lock_guard<std::mutex> lk(m); all.swap(blocks); cached = 0; }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (auto& kv : all) {
+      cudaSetDevice(kv.first.first);
+      if (kv.second.ev) { cudaEventSynchronize(kv.second.ev); cudaEventDestroy(kv.second.ev); }
+      cudaFree(kv.second.p);
+    }
+    for (int d = 0; d < ISFM_MAX_DEVICES; ++d) {
+      cudaMemPool_t p;
+      { std::lock_guard<std::mutex> lk(device_pools().m); p = device_pools().pool[d]; }
+      if (p) { cudaSetDevice(d); cudaDeviceSynchronize(); cudaMemPoolTrimTo(p, 0); }
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
   }
 };
 inline BufferCache& buffer_cache() { static BufferCache* c = new BufferCache(); return *c; }   // never destroyed: outlives every handle
@@ -178,27 +284,45 @@ struct DeviceBuffer {
   T* ptr = nullptr;
   size_t count = 0;
   size_t block_bytes = 0;   // size of the underlying block (>= count * sizeof(T) when it came from the cache)
+  int dev = -1;             // device and stream the block was allocated under (the handle's)
+  cudaStream_t stream = nullptr;
   DeviceBuffer() {}
   DeviceBuffer(const DeviceBuffer&) = delete;
   DeviceBuffer& operator=(const DeviceBuffer&) = delete;
   ~DeviceBuffer() { release(); }
-  void release() { if (ptr) buffer_cache().give(ptr, block_bytes); ptr = nullptr; count = 0; block_bytes = 0; }
+  void release() {
+    if (ptr) {
+      const DeviceCtx& c = tl_ctx();
+      const bool synced = c.synced && c.dev == dev && c.stream == stream;
+      int cur = -1;
+      const bool switch_dev = cudaGetDevice(&cur) == cudaSuccess && cur != dev && dev >= 0;
+      if (switch_dev) cudaSetDevice(dev);
+      buffer_cache().give(dev, ptr, block_bytes, stream, synced);
+      if (switch_dev) cudaSetDevice(cur);
+    }
+    ptr = nullptr; count = 0; block_bytes = 0;
+  }
   void alloc(size_t n) {
     if (n <= count && ptr) return;
     release();
     if (n == 0) n = 1;
-    ensure_pool_configured();
+    const DeviceCtx& c = tl_ctx();
+    dev = c.dev; stream = c.stream;
+    if (dev < 0) { ISFM_CUDA(cudaGetDevice(&dev)); }
     size_t got = 0;
-    if (void* p = buffer_cache().take(n * sizeof(T), &got)) {
+    if (void* p = buffer_cache().take(dev, n * sizeof(T), stream, &got)) {
       ptr = static_cast<T*>(p); block_bytes = got; count = n;
       return;
     }
-    ISFM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ptr), n * sizeof(T), 0));
+    ptr = static_cast<T*>(pool_alloc(dev, n * sizeof(T), stream));
     count = n; block_bytes = n * sizeof(T);
   }
   void zero(cudaStream_t s) { if (ptr) ISFM_CUDA(cudaMemsetAsync(ptr, 0, count * sizeof(T), s)); }
   T* get() const { return ptr; }
-  void swap(DeviceBuffer& o) { std::swap(ptr, o.ptr); std::swap(count, o.count); std::swap(block_bytes, o.block_bytes); }
+  void swap(DeviceBuffer& o) {
+    std::swap(ptr, o.ptr); std::swap(count, o.count); std::swap(block_bytes, o.block_bytes);
+    std::swap(dev, o.dev); std::swap(stream, o.stream);
+  }
 };
 
 inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

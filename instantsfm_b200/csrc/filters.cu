@@ -149,6 +149,7 @@ extern "C" int isfm_filter_observations(int32_t mode, int64_t n_obs, int64_t n_i
   ISFM_REQUIRE(world2cam && xyz && features_undist && image_ids && track_idx && valid_out, ISFM_EINVAL, "isfm_filter_observations: null");
   require_device();
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CtxGuard guard__(-1, s);   // buffers below are ordered on the caller's stream, on the current device
   Staged<double> M, X, F; Staged<int32_t> I, T;
   M.in(world2cam, (size_t)n_img * 16, s); X.in(xyz, (size_t)n_trk * 3, s); F.in(features_undist, (size_t)n_obs * 3, s);
   I.in(image_ids, (size_t)n_obs, s); T.in(track_idx, (size_t)n_obs, s);
@@ -179,6 +180,7 @@ extern "C" int isfm_filter_triangulation_angle(int64_t n_trk, int64_t n_obs, int
   ISFM_REQUIRE(track_off && centers && xyz && remove_out && (image_ids || n_obs == 0), ISFM_EINVAL, "isfm_filter_triangulation_angle: null");
   require_device();
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CtxGuard guard__(-1, s);   // buffers below are ordered on the caller's stream, on the current device
   Staged<int64_t> O; Staged<int32_t> I; Staged<double> C, X;
   O.in(track_off, (size_t)n_trk + 1, s); I.in(image_ids, (size_t)std::max<int64_t>(n_obs, 1), s);
   C.in(centers, (size_t)std::max<int64_t>(n_img, 1) * 3, s); X.in(xyz, (size_t)n_trk * 3, s);

@@ -312,7 +312,6 @@ template <typename T>
 struct GPSolver : GPSolverBase {
   isfm_gp_desc desc;
   cudaStream_t s;
-  cudaStream_t own_stream = nullptr;
   isfm_comm* comm;
   TrustRegionState tr;
   int64_t n_cam = 0, n_pt = 0, n_obs = 0;
@@ -331,13 +330,7 @@ struct GPSolver : GPSolverBase {
   double loss = 0.0;
 
   explicit GPSolver(const isfm_gp_desc& d) : desc(d) {
-    s = static_cast<cudaStream_t>(d.stream);
-    if (s == nullptr) {
-      // the legacy default stream cannot be captured into a CUDA graph: work on an own BLOCKING
-      // stream, which stays implicitly ordered with the caller's legacy-stream work
-      ISFM_CUDA(cudaStreamCreate(&own_stream));
-      s = own_stream;
-    }
+    s = static_cast<cudaStream_t>(d.stream);   // never the legacy default stream: isfm_gp_create substitutes an own stream
     comm = d.comm;
     timers.stream = s;
     tr.init(d.tr_radius, d.tr_max, d.tr_up, d.tr_down);
@@ -345,7 +338,6 @@ struct GPSolver : GPSolverBase {
   }
   ~GPSolver() override {
     cudaStreamSynchronize(s);   // buffers go back to the stream-ordered pool after all work has finished
-    if (own_stream) cudaStreamDestroy(own_stream);
     if (h_scalars) cudaFreeHost(h_scalars);
   }
 

@@ -27,6 +27,9 @@ struct PcgState {
   unsigned int ticket;
   unsigned int ticket2;   // last-CTA election of the merged update / direction kernel
   int max_iter;
+  unsigned int bar;       // persistent kernel: grid-barrier arrivals (monotonic within a solve)
+  int abort;              // persistent kernel: a barrier or a peer wait timed out
+  unsigned long long phase_ns[8];   // persistent kernel: time per phase of CTA 0 (PcgPhase), this solve
 };
 
 // The CTA that finishes last sums the per-CTA partials in index order (deterministic) and
@@ -382,7 +385,8 @@ __global__ void pcg_init_state_kernel(int n, int max_iter, const double* __restr
   double bb = reduce_partials(part_bb, n);
   if (threadIdx.x == 0) {
     st->rho = rz; st->rho_next = 0.0; st->has_next = 0; st->bb = bb; st->rr = bb; st->iters = 0; st->pq = 0.0;
-    st->ticket = 0u; st->ticket2 = 0u; st->max_iter = max_iter;
+    st->ticket = 0u; st->ticket2 = 0u; st->max_iter = max_iter; st->bar = 0u; st->abort = 0;
+    for (int i = 0; i < 8; ++i) st->phase_ns[i] = 0ull;
     st->done = (bb == 0.0) ? 1 : ((isfinite(rz) && isfinite(bb)) ? 0 : 2);
   }
 }
@@ -423,7 +427,17 @@ pcg_update_kernel(int n_cam, double tol2, const T* __restrict__ Minv, T* __restr
   }
   constexpr int CPB = UPD_TPB / D;
   const double rho = st->rho;
-  const T alpha = (T)(rho / st->pq);
+  const double pq_now = st->pq;
+  if (!(pq_now > 0.0) || !isfinite(pq_now)) {
+    // breakdown (non-positive curvature / non-finite): x keeps the last good iterate; the solve
+    // ends with status 2 (uniform: every CTA reads the same scalar)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      st->done = 2;
+      if (use_cond) cudaGraphSetConditional(cond, 0u);
+    }
+    return;
+  }
+  const T alpha = (T)(rho / pq_now);
   const int cam = blockIdx.x * CPB + threadIdx.x / D, k = threadIdx.x % D;
   const bool on = threadIdx.x < CPB * D && cam < n_cam;
   T rv[D];
@@ -495,6 +509,10 @@ pcg_direction_kernel(int n_cam, int n_part, double tol2, const double* __restric
   if (blockIdx.x == 0 && threadIdx.x == 0) pcg_finish_iteration(st, rho_new, rr, tol2, false, cond, use_cond);
 }
 
+}  // namespace isfm
+#include "pcg_persistent.cuh"
+namespace isfm {
+
 // deposit positions written by the upper slots [slot_lo, slot_hi): min / max per destination row
 static __global__ void own_deposit_range_kernel(int slot_lo, int slot_hi, const int32_t* __restrict__ ucol,
                                                 const int32_t* __restrict__ tpos, int32_t* beg, int32_t* end) {
@@ -513,8 +531,16 @@ static __global__ void own_deposit_fix_kernel(int n, int32_t* beg, int32_t* end)
 template <typename T, int D>
 struct BlockPCG {
   int n_cam = 0;
-  DeviceBuffer<T> x, r, z, p, q, y, yup, C;
+  DeviceBuffer<T> x, r, z, p, pp, q, y, yup, C;
   DeviceBuffer<double> part_pq, part_a, part_b;
+  // persistent kernel (pcg_persistent.cuh): grid size (0 = unavailable), accumulated phase times
+  int persist_grid = 0;
+  double phase_ms[8] = {0};
+  int64_t persist_solves = 0;
+  // two-level preconditioner and sparse exchange ranges, set by the owner before solve()
+  struct CoarseRef { int enabled = 0, cs = 0, ncl = 0, ncp = 0; const T* Pm = nullptr; const T* Ainv = nullptr; double* rc = nullptr; const int* fail = nullptr; } coarse;
+  int row_lo[ISFM_MAX_PEERS] = {0}, row_len[ISFM_MAX_PEERS] = {0};
+  bool ring_valid = false;
   DeviceBuffer<PcgState> state;
   PcgState* h_state = nullptr;  // pinned
   // The whole iteration loop of a single-rank solve is ONE graph launch: a conditional WHILE node
@@ -542,11 +568,29 @@ struct BlockPCG {
     if (comm_world(comm) > 1) comm_peer_ensure(comm, (size_t)n * D * sizeof(T), s);
     size_t len = (size_t)n * D;
     x.alloc(len); r.alloc(len); z.alloc(len); p.alloc(len); q.alloc(len); y.alloc(len);
+    pp.alloc((size_t)n * PersistCfg<T, D>::DP); pp.zero(s);
     yup.alloc((size_t)std::max<int64_t>(n_chunks, 1) * D);
     C.alloc((size_t)std::max<int64_t>(n_off, 1) * D);
-    part_pq.alloc(n); part_a.alloc(n); part_b.alloc(n);
+    const size_t n_part = (size_t)std::max(n, 1024);   // >= any grid of the persistent kernel
+    part_pq.alloc(n_part); part_a.alloc(n_part); part_b.alloc(n_part);
     state.alloc(1);
     own_valid = false;
+    coarse = CoarseRef{};
+    ring_valid = false;
+    // persistent solve kernel: one CTA per SM, if the device can co-schedule them
+    persist_grid = 0;
+    if (!getenv("ISFM_NO_PERSISTENT")) {
+      int dev = 0, coop = 0, n_sm = 0, per_sm = 0;
+      ISFM_CUDA(cudaGetDevice(&dev));
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      if (coop && cudaFuncSetAttribute(pcg_persistent_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)PersistCfg<T, D>::SMEM) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_persistent_kernel<T, D>, PersistCfg<T, D>::NT,
+                                                        PersistCfg<T, D>::SMEM) == cudaSuccess && per_sm >= 1)
+        persist_grid = n_sm;
+      cudaGetLastError();
+    }
     ISFM_CUDA(cudaFuncSetAttribute(pcg_spmv_upper_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)SpmvCfg<T, D>::SMEM));
     if (!h_state) ISFM_CUDA(cudaMallocHost(&h_state, sizeof(PcgState)));
@@ -596,6 +640,51 @@ struct BlockPCG {
     { TimerScope ts(kt, T_PCG_VEC);
       pcg_init_state_kernel<D><<<1, 256, 0, s>>>(n_cam, max_iter, part_a.get(), part_b.get(), state.get()); }
     const double tol2 = tol * tol;
+    // ---- persistent path: the whole solve in one cooperative kernel (single rank or peer exchange) ----
+    if (persist_grid > 0 && (!multi || peer) && !kt.enabled_fine()) {
+      PcgArgs<T> a;
+      memset(&a, 0, sizeof a);
+      a.n_cam = n_cam; a.unit_lo = (int)unit_lo; a.unit_hi = (int)unit_hi; a.max_iter = max_iter;
+      a.unit_row = sp.chunk_row.get(); a.unit_beg = sp.chunk_beg.get(); a.urow_ptr = sp.urow_ptr.get(); a.ucol = sp.ucol.get();
+      a.tpos = sp.tpos.get(); a.dep_beg = dep_beg; a.dep_end = dep_end; a.chunk_ptr = sp.chunk_ptr.get();
+      a.E = E; a.Hd = Hd; a.Minv = Minv;
+      a.x = x.get(); a.r = r.get(); a.z = z.get(); a.p = p.get(); a.pp = pp.get(); a.q = q.get(); a.y = y.get(); a.yup = yup.get(); a.C = C.get();
+      a.part_pq = part_pq.get(); a.part_a = part_a.get(); a.part_b = part_b.get();
+      a.st = state.get(); a.tol2 = tol2;
+      const int64_t avg_dep = sp.n_off / std::max(n_cam, 1);
+      a.wpr = avg_dep < 192 ? 1 : (avg_dep < 512 ? 2 : 4);
+      if (const char* e = getenv("ISFM_PCG_WPR")) a.wpr = std::max(1, std::min(4, atoi(e)));
+      if (a.wpr == 3) a.wpr = 2;
+      a.cams_per_cta = div_up(n_cam, persist_grid);
+      const int64_t my_slots = n_units > 0 ? (int64_t)std::min<int64_t>((int64_t)n_units * SPMV_CHUNK, sp.nnzu) : 0;
+      a.keep_in_l2 = (size_t)my_slots * D * D * sizeof(T) <= ((size_t)72 << 20) && !getenv("ISFM_NO_L2_KEEP");
+      a.peer = peer ? 1 : 0;
+      a.push_grid = big_push ? 1 : 0;
+      a.px = px;
+      for (int rk = 0; rk < ISFM_MAX_PEERS; ++rk) { a.row_lo[rk] = ring_valid ? row_lo[rk] : 0; a.row_len[rk] = ring_valid ? row_len[rk] : n_cam; }
+      if (peer && ring_valid) {
+        // the push variant follows the bytes this rank actually sends
+        if (!push_env) a.push_grid = (size_t)row_len[comm_rank(comm)] * D * sizeof(T) > ((size_t)128 << 10);
+      }
+      a.coarse = coarse.enabled; a.cs = coarse.cs; a.ncl = coarse.ncl; a.ncp = coarse.ncp;
+      a.kcl = coarse.enabled ? div_up(coarse.ncl, persist_grid) : 0;
+      a.Pm = coarse.Pm; a.Ainv = coarse.Ainv; a.rc = coarse.rc; a.coarse_fail = coarse.fail;
+      a.phase_ns = &state.get()->phase_ns[0];
+      if (coarse.enabled) ISFM_CUDA(cudaMemsetAsync(q.get(), 0, (size_t)n_cam * D * sizeof(T), s));   // alpha = 0 pass reads q
+      { TimerScope ts(kt, T_PCG_SPMV);
+        void* params[] = {&a};
+        ISFM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&pcg_persistent_kernel<T, D>), dim3(persist_grid),
+                                              dim3(PersistCfg<T, D>::NT), params, PersistCfg<T, D>::SMEM, s)); }
+      ISFM_CUDA(cudaMemcpyAsync(h_state, state.get(), sizeof(PcgState), cudaMemcpyDeviceToHost, s));
+      ISFM_CUDA(cudaStreamSynchronize(s));
+      if (h_state->abort || h_state->done == 3)
+        throw IsfmError(ISFM_ENCCL, h_state->done == 3 ? "peer-memory exchange timed out waiting for a rank (PCG)"
+                                                       : "grid barrier timed out inside the persistent PCG kernel");
+      for (int i = 0; i < 8; ++i) phase_ms[i] += (double)h_state->phase_ns[i] * 1e-6;
+      persist_solves++;
+      if (status_out) *status_out = h_state->done;
+      return h_state->iters;
+    }
     auto launch_iteration = [&](cudaGraphConditionalHandle cond, int use_cond) {
       if (n_units > 0) {
         TimerScope ts(kt, T_PCG_SPMV);
@@ -652,7 +741,7 @@ struct BlockPCG {
     if (use_graph && !(graph_exec && g_E == E && g_Hd == Hd && g_Minv == Minv && g_tol2 == tol2 && g_units == sp.n_chunks && g_unit_lo == unit_lo && g_unit_hi == unit_hi &&
                        g_peer_base == (peer ? (const void*)comm->px.base[0] : nullptr))) {
       if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
-      const int64_t lc = g_launch_count;
+      tl_count_launches() = false;                 // captured, not executed
       int64_t saved[ISFM_N_TIMERS];
       for (int i = 0; i < ISFM_N_TIMERS; ++i) saved[i] = kt.launches[i];
       cudaGraph_t graph = nullptr;
@@ -678,7 +767,7 @@ struct BlockPCG {
       if (ok) ok = cudaGraphInstantiate(&graph_exec, graph, 0) == cudaSuccess;
       if (graph) cudaGraphDestroy(graph);
       if (!ok) { graph_exec = nullptr; graph_disabled = true; cudaGetLastError(); }   // plain launches + host polling instead
-      g_launch_count = lc;                       // captured, not executed
+      tl_count_launches() = true;
       for (int i = 0; i < ISFM_N_TIMERS; ++i) kt.launches[i] = saved[i];
       g_E = E; g_Hd = Hd; g_Minv = Minv; g_tol2 = tol2; g_units = sp.n_chunks; g_unit_lo = unit_lo; g_unit_hi = unit_hi;
       g_peer_base = peer ? (const void*)comm->px.base[0] : nullptr;

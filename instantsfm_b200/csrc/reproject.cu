@@ -74,6 +74,7 @@ extern "C" int isfm_reprojection_test(int32_t model_id, int64_t n_obs, int64_t n
     ISFM_CUDA(cudaGetDeviceCount(&n_dev));
     ISFM_REQUIRE(n_dev > 0, ISFM_ECUDA, "no CUDA device: this library has no CPU path");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CtxGuard guard__(-1, s);   // buffers below are ordered on the caller's stream, on the current device
     DeviceBuffer<double> b_cam, b_pp, b_pts, b_obs, b_err; DeviceBuffer<int32_t> b_ci, b_pi; DeviceBuffer<uint8_t> b_pass;
     const double* d_cam = stage_in(b_cam, cam, (size_t)n_cam * (7 + ni), s);
     const double* d_pp = stage_in(b_pp, pp, (size_t)n_cam * 2, s);

@@ -128,6 +128,13 @@ class _EngineBase:
             self._fn("destroy")(self.handle)
             self.handle = c_void_p()
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def __del__(self):
         try:
             self.close()
@@ -198,6 +205,14 @@ class BAEngine(_EngineBase):
         check(self.lib.isfm_ba_get_matvec_units(self.handle, byref(owned), byref(total)))
         return owned.value, total.value
 
+    def pcg_phases(self):
+        """(ms per phase of the persistent PCG kernel accumulated since creation [matvec, combine,
+        exchange, update, coarse, direction, -, -], PCG solves run by it, two-level preconditioner on?)."""
+        ms = (c_double * 8)()
+        solves, two = c_int64(), c_int32()
+        check(self.lib.isfm_ba_get_pcg_phases(self.handle, ms, byref(solves), byref(two)))
+        return [ms[i] for i in range(8)], solves.value, bool(two.value)
+
     def schur_pattern(self):
         nnzb, npairs = c_int64(), c_int64()
         check(self.lib.isfm_ba_get_schur_pattern(self.handle, byref(nnzb), byref(npairs), None, None))
@@ -259,6 +274,17 @@ class GPEngine(_EngineBase):
         check(self.lib.isfm_gp_get_params(self.handle, c.ctypes.data_as(c_void_p), p.ctypes.data_as(c_void_p),
                                           s.ctypes.data_as(c_void_p)))
         return c, p, s
+
+
+def trim_cache():
+    """Return the library's cached device blocks and its private memory pools to the driver
+    (call at pipeline stage boundaries when other GPU stages need the memory)."""
+    _lib.load().isfm_trim_cache()
+
+
+def set_cache_limit(n_bytes):
+    """Bound the process-wide cache of freed device blocks (default 4 GB; 0 disables it)."""
+    _lib.load().isfm_set_cache_limit(int(n_bytes))
 
 
 def partition_points(point_offsets, world):

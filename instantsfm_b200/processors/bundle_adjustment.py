@@ -25,15 +25,25 @@ def _model_value(model_id):
 
 
 def update(cameras, images, tracks, track_keys, unique_cameras, unique_points, remaining_indices, pp_indices,
-           camera_params, camera_pps, points_3d):
+           camera_params, camera_pps, points_3d, write_cameras=True):
     """bundle_adjustment.py:18-36: write the optimised tensors back into the scene objects
-    (images sharing a camera overwrite each other's intrinsics; the last one wins)."""
+    (images sharing a camera overwrite each other's intrinsics; the last one wins).
+    ``write_cameras=False`` (points-only BA, ``optimize_poses=False``): poses and intrinsics were
+    not variables, so the scene keeps its fp64 values untouched instead of a round trip through
+    the solver's precision."""
+    track_objs = list(tracks.values()) if len(unique_points) == len(track_keys) else None
+    if track_objs is not None and np.array_equal(unique_points, np.arange(len(track_keys))):
+        for track, xyz in zip(track_objs, points_3d):       # every track is a variable: no key look-ups
+            track.xyz = xyz
+    else:
+        for key, xyz in zip([track_keys[i] for i in unique_points.tolist()], points_3d):
+            tracks[key].xyz = xyz
+    if not write_cameras:
+        return
     full = np.zeros((camera_params.shape[0], camera_params.shape[1] + 2))
     full[:, remaining_indices] = camera_params
     full[:, pp_indices] = camera_pps
     pose_matrices = pose7_to_matrices(full[:, :7])
-    for i, original_idx in enumerate(unique_points.tolist()):
-        tracks[track_keys[original_idx]].xyz = points_3d[i]
     for i, image_id in enumerate(unique_cameras.tolist()):
         image = images[image_id]
         image.world2cam = pose_matrices[i]
@@ -48,6 +58,7 @@ class TorchBA:
         self.pcg_tol = pcg_tol
         self.loss_history = []
         self.last_stats = []
+        self.last_timing = {}      # seconds per host phase of the last Solve (flatten, set-up, steps, write-back)
 
     # -- tensor set-up, bundle_adjustment.py:66-113 ---------------------------------------
     def _build(self, cameras, images, tracks, options, model_value):
@@ -93,31 +104,48 @@ class TorchBA:
         if model_value not in _PP:
             raise NotImplementedError("Unsupported camera model")
         opts = BUNDLE_ADJUSTER_OPTIONS
+        import time
+        t0 = time.perf_counter()
         t = self._build(cameras, images, tracks, opts, model_value)
+        self.last_timing = {"flatten": time.perf_counter() - t0}
         if t["points_2d"].shape[0] == 0:
             return
 
         import torch
         with torch.cuda.device(device_index(self.device)):
-            engine = BAEngine(model_value, optimize_poses=opts["optimize_poses"],
-                              huber_delta=opts["thres_loss_function"], dtype=self.dtype, pcg_tol=self.pcg_tol)
-            engine.set_problem(t["camera_params"], t["camera_pps"], t["points_3d"], t["points_2d"],
-                               t["camera_indices"], t["point_indices"])
+            t0 = time.perf_counter()
+            # the handle is destroyed on every exit path, under the device it was created on
+            with BAEngine(model_value, optimize_poses=opts["optimize_poses"], huber_delta=opts["thres_loss_function"],
+                          dtype=self.dtype, pcg_tol=self.pcg_tol) as engine:
+                engine.set_problem(t["camera_params"], t["camera_pps"], t["points_3d"], t["points_2d"],
+                                   t["camera_indices"], t["point_indices"])
+                self.last_timing["set_problem"] = time.perf_counter() - t0
+                # the solver works in self.dtype; the scene keeps its fp64 values and receives the
+                # solver's CHANGE (output - input, both in solver precision): parameters the solve left
+                # untouched come back bit-identical instead of rounded through fp32
+                cam_in = t["camera_params"].astype(self.dtype)
+                pts_in = t["points_3d"].astype(self.dtype)
 
-            def write_back():
-                cam, pts = engine.get_params()
-                update(cameras, images, tracks, t["track_keys"], t["unique_cameras"], t["unique_points"],
-                       t["remaining"], t["pp_indices"], cam.astype(np.float64), t["camera_pps"], pts.astype(np.float64))
+                def write_back():
+                    cam, pts = engine.get_params()
+                    cam64 = t["camera_params"] + (cam.astype(np.float64) - cam_in.astype(np.float64))
+                    pts64 = t["points_3d"] + (pts.astype(np.float64) - pts_in.astype(np.float64))
+                    update(cameras, images, tracks, t["track_keys"], t["unique_cameras"], t["unique_points"],
+                           t["remaining"], t["pp_indices"], cam64, t["camera_pps"], pts64,
+                           write_cameras=bool(opts["optimize_poses"]))
 
-            self.loss_history, self.last_stats = [], []
-            for _ in range(opts["max_num_iterations"]):
-                loss, stats = engine.step()
-                self.loss_history.append(loss)
-                self.last_stats.append(stats)
-                if should_stop(self.loss_history, opts["function_tolerance"], identical_test=True):
-                    break
-                if self.visualizer:
-                    write_back()
-                    self.visualizer.add_step(cameras, images, tracks, "bundle_adjustment")
-            write_back()
-            engine.close()
+                t0 = time.perf_counter()
+                self.loss_history, self.last_stats = [], []
+                for _ in range(opts["max_num_iterations"]):
+                    loss, stats = engine.step()
+                    self.loss_history.append(loss)
+                    self.last_stats.append(stats)
+                    if should_stop(self.loss_history, opts["function_tolerance"], identical_test=True):
+                        break
+                    if self.visualizer:
+                        write_back()
+                        self.visualizer.add_step(cameras, images, tracks, "bundle_adjustment")
+                self.last_timing["steps"] = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                write_back()
+                self.last_timing["write_back"] = time.perf_counter() - t0

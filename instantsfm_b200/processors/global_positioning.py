@@ -86,28 +86,28 @@ class TorchGP:
 
         import torch
         with torch.cuda.device(device_index(self.device)):
-            engine = GPEngine(huber_delta=opts["thres_loss_function"], dtype=self.dtype, optimize_scales=not depth_only,
-                              pcg_tol=self.pcg_tol)
-            engine.set_problem(centres, points_3d, scales_t, translations, image_id2idx[image_id].astype(np.int32),
-                               which.astype(np.int32), is_calibrated, fixed_t)
+            # the handle is destroyed on every exit path, under the device it was created on
+            with GPEngine(huber_delta=opts["thres_loss_function"], dtype=self.dtype, optimize_scales=not depth_only,
+                          pcg_tol=self.pcg_tol) as engine:
+                engine.set_problem(centres, points_3d, scales_t, translations, image_id2idx[image_id].astype(np.int32),
+                                   which.astype(np.int32), is_calibrated, fixed_t)
 
-            def write_back():
-                c, X, _ = engine.get_params()
-                c, X = c.astype(np.float64), X.astype(np.float64)
-                for k, track in enumerate(tracks.values()):
-                    track.xyz = X[k]
-                for idx, iid in enumerate(reg_ids.tolist()):
-                    images[iid].world2cam[:3, 3] = c[idx]
-                self.ConvertResults(images)
+                def write_back():
+                    c, X, _ = engine.get_params()
+                    c, X = c.astype(np.float64), X.astype(np.float64)
+                    for track, xyz in zip(tracks.values(), X):
+                        track.xyz = xyz
+                    for idx, iid in enumerate(reg_ids.tolist()):
+                        images[iid].world2cam[:3, 3] = c[idx]
+                    self.ConvertResults(images)
 
-            self.loss_history = []
-            for _ in range(opts["max_num_iterations"]):
-                loss, _ = engine.step()
-                self.loss_history.append(loss)
-                if should_stop(self.loss_history, opts["function_tolerance"], identical_test=False):
-                    break
-                if self.visualizer:
-                    write_back()
-                    self.visualizer.add_step(cameras, images, tracks, "global_positioning")
-            write_back()
-            engine.close()
+                self.loss_history = []
+                for _ in range(opts["max_num_iterations"]):
+                    loss, _ = engine.step()
+                    self.loss_history.append(loss)
+                    if should_stop(self.loss_history, opts["function_tolerance"], identical_test=False):
+                        break
+                    if self.visualizer:
+                        write_back()
+                        self.visualizer.add_step(cameras, images, tracks, "global_positioning")
+                write_back()

@@ -42,6 +42,9 @@ class BAArrays:
     point_indices: np.ndarray      # int32 [N], non-decreasing
     gt_camera_params: np.ndarray = field(default=None, repr=False)
     gt_points_3d: np.ndarray = field(default=None, repr=False)
+    point_range: tuple = None          # (p0, p1) of the global instance held by this object
+    n_pt_total: int = 0                # sizes of the global instance
+    n_obs_total: int = 0
 
     @property
     def n_cam(self):
@@ -162,8 +165,11 @@ def _orbit_cameras(rng, n_cam, radius=30.0):
     return matrices_to_pose7(M), C
 
 
+POINT_CHUNK = 1 << 16   # points per generation chunk: the unit of the per-chunk random streams
+
+
 def _visibility(rng, n_cam, n_pt, n_obs, window, kmin=2, anchor_range=None):
-    """Sorted-by-point observation lists: camera_indices, point_indices (int32).
+    """Sorted-by-point observation lists: camera_indices, point_indices (int32).  (GP problems.)
 
     Slots inside the window are visited with a per-point stride modulo a prime W, so the
     k_p cameras of a point are distinct."""
@@ -174,8 +180,6 @@ def _visibility(rng, n_cam, n_pt, n_obs, window, kmin=2, anchor_range=None):
     if anchor_range is None:
         anchor = rng.integers(0, n_cam, size=n_pt)
     else:
-        # banded problems: points follow the street (sorted anchors), optionally restricted to
-        # one rank's arc, so that contiguous point ranges touch contiguous camera ranges
         anchor = np.sort(rng.integers(anchor_range[0], anchor_range[1], size=n_pt))
     start = rng.integers(0, W, size=n_pt)
     pt = np.repeat(np.arange(n_pt, dtype=np.int64), k)
@@ -209,16 +213,36 @@ def _street_cameras(rng, n_cam, window):
     return matrices_to_pose7(M), radius, spacing
 
 
+def partition_by_observations(point_offsets, world):
+    """numpy twin of isfm_partition_points (include/isfm_b200.h): boundary g = first point whose
+    starting observation offset >= g * n_obs / world (integer arithmetic)."""
+    off = np.asarray(point_offsets, dtype=np.int64)
+    n_obs = int(off[-1])
+    out = np.empty(world + 1, dtype=np.int64)
+    for g in range(world + 1):
+        # first p with off[p] * world >= g * n_obs
+        out[g] = np.searchsorted(off[:-1] * world, g * n_obs, side="left")
+    out[world] = off.shape[0] - 1
+    return out
+
+
 def make_ba_problem(n_cam, n_pt, n_obs, window=None, seed=0, model_id=3, noise_px=0.5,
-                    outlier_frac=0.01, perturb=1.0, point_seed=None, anchor_range=None):
+                    outlier_frac=0.01, perturb=1.0, point_range=None, shard=None):
     """Build a BAL-shaped problem; ``perturb`` scales the initial-state perturbation.
 
     ``window >= n_cam``: object-centric orbit, every camera may see every point (dense reduced
     camera system, BAL-like).  ``window < n_cam``: street geometry, a point is seen only from
     ``window`` consecutive cameras (banded system, city-scale).
-    ``point_seed``: draw points / visibility / noise from their own stream, so that several
-    ranks can generate disjoint point shards over the SAME cameras (multi-GPU bench)."""
-    rng = np.random.default_rng(seed)
+
+    ONE instance per (sizes, seed): the cameras, the track lengths and (street) the anchors come
+    from global random streams; everything else about a point -- visibility pattern, position,
+    observation noise, outliers, initial perturbation -- comes from the stream of its chunk of
+    ``POINT_CHUNK`` consecutive points.  ``point_range = (p0, p1)`` or ``shard = (rank, world)``
+    (contiguous point ranges balanced by observation count, the library's partition) therefore
+    return exactly the slice of the global problem that a full generation would contain:
+    N ranks solve the same problem as one.  Shard results carry ``point_range`` and local point
+    indices; cameras are always the full set."""
+    rng = np.random.default_rng([seed, 0])
     window = n_cam if window is None else window
     street = window < n_cam
     if street:
@@ -239,54 +263,74 @@ def make_ba_problem(n_cam, n_pt, n_obs, window=None, seed=0, model_id=3, noise_p
     cam0[:, 3:7] = quat_mul(dq, cam_gt[:, 3:7])
     cam0[:, :3] += rng.normal(scale=perturb * 0.3 / np.sqrt(3), size=(n_cam, 3))
     cam0[:, 7:7 + nf] *= 1 + rng.normal(scale=perturb * 0.01, size=(n_cam, nf))
-    if point_seed is not None:
-        rng = np.random.default_rng(point_seed)
-    if street and anchor_range is None:
-        anchor_range = (0, n_cam)
-    ci, pi = _visibility(rng, n_cam, n_pt, n_obs, window, anchor_range=anchor_range if street else None)
-    if street:
-        # a point sits on the facade opposite the middle of its camera window, 15..40 deep
-        first = np.searchsorted(pi, np.arange(n_pt))
-        k = np.diff(np.append(first, pi.shape[0]))
-        W = _prev_prime(min(window, n_cam))
-        mid = ci[first].astype(np.int64)                 # any camera of the track fixes the arc position
-        # circular mean of the track's cameras (they span < W << n_cam positions)
-        rel = ((ci.astype(np.int64) - mid[pi] + n_cam // 2) % n_cam) - n_cam // 2
-        centre = mid + np.round(np.bincount(pi, weights=rel, minlength=n_pt) / k)
-        theta = 2 * np.pi * (centre + rng.uniform(-0.5, 0.5, n_pt)) / n_cam
-        rad = radius - rng.uniform(15, 40, n_pt)
-        X = np.stack([rad * np.cos(theta), rad * np.sin(theta), rng.uniform(-6, 6, n_pt)], 1)
-    else:
-        # points in a ball of radius 10 around the origin
-        X = rng.normal(size=(n_pt, 3))
-        X *= (10.0 * rng.uniform(0, 1, (n_pt, 1)) ** (1 / 3)) / np.linalg.norm(X, axis=1, keepdims=True)
-    obs, depth = project_numpy(model_id, X[pi], cam_gt[ci], pps[ci])
-    assert depth.min() > 0.1
-    obs += rng.normal(scale=noise_px, size=obs.shape)
-    n_out = int(outlier_frac * obs.shape[0])
-    if n_out:
-        which = rng.choice(obs.shape[0], size=n_out, replace=False)
-        obs[which] += rng.uniform(-20, 20, size=(n_out, 2))
-    X0 = X + rng.normal(scale=perturb * 0.6 / np.sqrt(3), size=X.shape)   # 2 % of depth
-    return BAArrays(model_id, cam0, pps, X0, obs, ci, pi, cam_gt, X)
+
+    # global per-point streams: track lengths (they fix the partition) and street anchors
+    W = _prev_prime(min(window, n_cam))
+    k_all = _track_lengths(np.random.default_rng([seed, 1]), n_pt, n_obs, min(200, W), 2)
+    off_all = np.concatenate([[0], np.cumsum(k_all)])
+    anchor_all = np.sort(np.random.default_rng([seed, 2]).integers(0, n_cam, size=n_pt)) if street else None
+    if shard is not None:
+        rank, world = shard
+        b = partition_by_observations(off_all, world)
+        point_range = (int(b[rank]), int(b[rank + 1]))
+    p0, p1 = (0, n_pt) if point_range is None else point_range
+
+    ci_l, pi_l, X_l, X0_l, obs_l = [], [], [], [], []
+    for c in range(p0 // POINT_CHUNK, (max(p1, p0 + 1) - 1) // POINT_CHUNK + 1):
+        a, b = c * POINT_CHUNK, min((c + 1) * POINT_CHUNK, n_pt)
+        if a >= b:
+            continue
+        crng = np.random.default_rng([seed, 3, c])
+        m = b - a
+        k = k_all[a:b]
+        stride = crng.integers(max(1, W // 8), W, size=m) if W > 2 else np.ones(m, dtype=np.int64)
+        anchor = anchor_all[a:b] if street else crng.integers(0, n_cam, size=m)
+        start = crng.integers(0, W, size=m)
+        pt = np.repeat(np.arange(m, dtype=np.int64), k)
+        offs = np.cumsum(k) - k
+        j = np.arange(pt.shape[0], dtype=np.int64) - offs[pt]
+        slot = (start[pt] + j * stride[pt]) % W
+        ci = (anchor[pt] + slot - W // 2) % n_cam
+        if street:
+            # a point sits on the facade opposite the middle of its camera window, 15..40 deep
+            mid = ci[offs]                                   # any camera of the track fixes the arc position
+            rel = ((ci - mid[pt] + n_cam // 2) % n_cam) - n_cam // 2
+            centre = mid + np.round(np.bincount(pt, weights=rel, minlength=m) / k)
+            theta = 2 * np.pi * (centre + crng.uniform(-0.5, 0.5, m)) / n_cam
+            rad = radius - crng.uniform(15, 40, m)
+            X = np.stack([rad * np.cos(theta), rad * np.sin(theta), crng.uniform(-6, 6, m)], 1)
+        else:
+            # points in a ball of radius 10 around the origin
+            X = crng.normal(size=(m, 3))
+            X *= (10.0 * crng.uniform(0, 1, (m, 1)) ** (1 / 3)) / np.linalg.norm(X, axis=1, keepdims=True)
+        obs, depth = project_numpy(model_id, X[pt], cam_gt[ci], pps[ci])
+        assert depth.min() > 0.1
+        obs += crng.normal(scale=noise_px, size=obs.shape)
+        out = crng.uniform(size=obs.shape[0]) < outlier_frac
+        obs[out] += crng.uniform(-20, 20, size=(int(out.sum()), 2))
+        X0 = X + crng.normal(scale=perturb * 0.6 / np.sqrt(3), size=X.shape)   # 2 % of depth
+        # cut the chunk to the requested point range
+        lo, hi = max(p0, a) - a, min(p1, b) - a
+        sel = slice(int(offs[lo]) if lo < m else pt.shape[0], int(offs[hi]) if hi < m else pt.shape[0])
+        ci_l.append(ci[sel].astype(np.int32)); pi_l.append((pt[sel] + a - p0).astype(np.int32))
+        X_l.append(X[lo:hi]); X0_l.append(X0[lo:hi]); obs_l.append(obs[sel])
+    cat = lambda xs, shape: np.concatenate(xs, axis=0) if xs else np.zeros(shape)
+    out = BAArrays(model_id, cam0, pps, cat(X0_l, (0, 3)), cat(obs_l, (0, 2)), cat(ci_l, (0,)).astype(np.int32),
+                   cat(pi_l, (0,)).astype(np.int32), cam_gt, cat(X_l, (0, 3)))
+    out.point_range = (p0, p1)
+    out.n_pt_total, out.n_obs_total = int(n_pt), int(n_obs)
+    return out
 
 
 def make_config(name, scale=1.0, model_id=3, shard=None):
     """BASELINE.json config by name ('C1','C2','C3','C5'); ``scale`` shrinks / grows points and
-    observations (cameras fixed).  ``shard = (rank, world)``: this rank's share of the points
-    (1/world of them, own random stream) over the common cameras."""
+    observations (cameras fixed).  ``shard = (rank, world)``: this rank's contiguous range of the
+    points of the ONE global instance (balanced by observation count)."""
     n_cam, n_pt, n_obs, window, seed = CONFIGS[name]
     if scale != 1.0:
         n_pt = max(int(n_pt * scale), 16)
         n_obs = max(int(n_obs * scale), 2 * n_pt)
-    point_seed = anchor_range = None
-    if shard is not None:
-        rank, world = shard
-        n_pt, n_obs = n_pt // world, n_obs // world
-        point_seed = seed * 7919 + 1 + rank
-        if window < n_cam:      # street: this rank's points sit along its own arc of the street
-            anchor_range = (rank * n_cam // world, (rank + 1) * n_cam // world)
-    return make_ba_problem(n_cam, n_pt, n_obs, window, seed, model_id, point_seed=point_seed, anchor_range=anchor_range)
+    return make_ba_problem(n_cam, n_pt, n_obs, window, seed, model_id, shard=shard)
 
 
 @dataclass

@@ -36,6 +36,7 @@ class BAProblem:
         self.optimize_poses = bool(optimize_poses)
         assert self.cam.shape[1] == 7 + self.ni
         self.n_cam, self.n_pt, self.n_obs = self.cam.shape[0], self.pts.shape[0], self.obs.shape[0]
+        self.n_lead = self.n_cam * self.d if self.optimize_poses else 0   # unknowns ahead of the point blocks
 
     # -- residuals: bundle_adjustment.py:59-64 -------------------------------------------
     def residuals(self):

@@ -106,6 +106,28 @@ def direct_solve(A, b):
     return lu.solve(b), 0
 
 
+def schur_direct(A, b, n_lead, block=3):
+    """Exact solve of the damped normal equations through the Schur complement of the trailing
+    block-diagonal part (points, ``block`` x ``block``): same solution as ``direct_solve`` up to
+    rounding, but feasible at BASELINE config 2 size (the full sparse LU is not).  The reduced
+    system is formed densely and solved by LAPACK."""
+    A = A.tocsr()
+    n = A.shape[0]
+    App = A[n_lead:, n_lead:].tocoo()
+    nb = (n - n_lead) // block
+    blocks = np.zeros((nb, block, block))
+    np.add.at(blocks, (App.row // block, App.row % block, App.col % block), App.data)
+    inv = np.linalg.inv(blocks)
+    Hinv = sp.bsr_matrix((inv, np.arange(nb), np.arange(nb + 1)), shape=(n - n_lead, n - n_lead)).tocsr()
+    Acp = A[:n_lead, n_lead:].tocsr()
+    W = (Acp @ Hinv).tocsr()
+    S = A[:n_lead, :n_lead].toarray() - (W @ Acp.T).toarray()
+    rhs = b[:n_lead] - W @ b[n_lead:]
+    xc = np.linalg.solve(S, rhs)
+    xp = Hinv @ (b[n_lead:] - Acp.T @ xc)
+    return np.concatenate([xc, xp]), 0
+
+
 class LM:
     """One ``step`` = one linearisation + >=1 damped solves / trial evaluations."""
 
@@ -120,6 +142,8 @@ class LM:
     def _solve(self, A, b):
         if self.solver == "pcg":
             return pcg_jacobi(A, b, self.pcg_tol)
+        if self.solver == "schur":   # exact, via the point Schur complement (problem.n_lead leading unknowns stay)
+            return schur_direct(A, b, self.problem.n_lead)
         return direct_solve(A, b)
 
     def step(self):

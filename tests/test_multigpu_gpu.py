@@ -8,9 +8,13 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("transport,split,push", [("peer", False, None), ("nccl", False, None), ("peer", True, None),
-                                                  ("nccl", True, None), ("peer", False, "grid"), ("peer", True, "grid")])
-def test_two_rank_solve_matches_single_rank(transport, split, push):
+@pytest.mark.parametrize("transport,split,push,extra", [
+    ("peer", False, None, {}), ("nccl", False, None, {}), ("peer", True, None, {}), ("nccl", True, None, {}),
+    ("peer", False, "grid", {}), ("peer", True, "grid", {}),
+    ("peer", False, None, {"ISFM_TWO_LEVEL": "1"}),        # coarse level all-reduced across ranks (street problem)
+    ("peer", False, None, {"ISFM_NO_PERSISTENT": "1"}),    # the per-iteration WHILE-graph path
+    ("peer", False, "grid", {"ISFM_FULL_EXCHANGE": "1"})])  # whole-vector exchange instead of the touched row ring
+def test_two_rank_solve_matches_single_rank(transport, split, push, extra):
     """Both transports of the per-iteration sum (peer-memory exchange fused into the PCG kernels,
     ncclAllReduce), with and without the split mat-vec (summed E reduce-scattered by unit ranges
     when the ranks share one block pattern), must reproduce the single-rank solve."""
@@ -26,6 +30,9 @@ def test_two_rank_solve_matches_single_rank(transport, split, push):
         env["ISFM_NO_PEER"] = "1"
     env["ISFM_SPLIT_MATVEC"] = "1" if split else "0"
     env.pop("ISFM_PEER_PUSH", None)
+    for k in ("ISFM_TWO_LEVEL", "ISFM_NO_PERSISTENT", "ISFM_FULL_EXCHANGE"):
+        env.pop(k, None)
+    env.update(extra)
     if push:
         env["ISFM_PEER_PUSH"] = push   # "grid": the grid-wide push kernel large camera systems use
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)

@@ -1,0 +1,32 @@
+#!/bin/bash
+# Round-2 exploratory single-GPU run: all GPU tests (no -x), default bench, C5 at N = 1 with and
+# without the two-level preconditioner, persistent vs per-iteration PCG kernels at C3, GP bench.
+# Usage: gpurun --timeout 2400 -- 'bash tools/gpu_r2a.sh r2a'
+TAG=${1:-r2a}
+OUT=gpurun_out/$TAG; mkdir -p "$OUT"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > "$OUT/smi.txt" 2>&1
+nproc > "$OUT/host.txt"; free -g >> "$OUT/host.txt"
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > "$OUT/pytest.log" 2>&1; echo "pytest exit $?" | tee -a "$OUT/pytest.log"
+tail -25 "$OUT/pytest.log"
+timeout 900 python bench.py --steps 10 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench exit $?"; tail -3 "$OUT/bench.err"
+head -c 1500 "$OUT/bench.json"; echo
+ISFM_NO_PERSISTENT=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --quick > "$OUT/bench_graph.json" 2> "$OUT/bench_graph.err"; echo "bench graph-path exit $?"
+timeout 900 python bench.py --config C5 --steps 5 --warmup 2 --no-cpu --quick > "$OUT/c5_n1.json" 2> "$OUT/c5_n1.err"; echo "c5 exit $?"; tail -3 "$OUT/c5_n1.err"
+ISFM_TWO_LEVEL=0 timeout 900 python bench.py --config C5 --steps 5 --warmup 2 --no-cpu --quick > "$OUT/c5_n1_jacobi.json" 2> "$OUT/c5_n1_jacobi.err"; echo "c5 jacobi exit $?"
+timeout 300 python bench.py --config C4 --steps 10 --warmup 3 > "$OUT/gp_c4.json" 2> "$OUT/gp_c4.err"; echo "gp exit $?"
+python - "$OUT" <<'P'
+import json, sys, os
+for f in ("bench", "bench_graph", "c5_n1", "c5_n1_jacobi", "gp_c4"):
+    try:
+        d = json.load(open(os.path.join(sys.argv[1], f + ".json")))
+        print(f, {k: d.get(k) for k in ("value", "ms_per_step", "pcg_iters", "final_robust_cost", "rejects")})
+        print("   work", d.get("work"))
+        print("   kernels", {k: (round(v["ms_per_step"], 3), round(v["us_per_launch"], 1), v.get("frac_algorithmic") and round(v["frac_algorithmic"], 3)) for k, v in d["kernels"].items()})
+        for k in ("e2e", "e2e_dropin", "reference_gpu"):
+            if d.get(k): print("   ", k, {kk: vv for kk, vv in d[k].items() if kk not in ("costs", "what", "includes", "note")})
+        for k in ("cpu_baseline", "c1"):
+            if d.get(k): print("   ", k, d[k].get("ms_per_lm_step"), d[k].get("gpu_same_problem"), d[k].get("parity"))
+    except Exception as e:
+        print(f, "no line", e)
+P
+ls -la "$OUT"
