@@ -51,7 +51,7 @@ struct isfm_gp { GPSolverBase* impl = nullptr; HandleCtx ctx; };
 
 static const char* kTimerNames[ISFM_N_TIMERS] = {
     "linearize", "point_blocks", "point_solve", "camera_blocks", "schur_offdiag", "precond", "pcg_spmv", "pcg_vec",
-    "backsub", "update", "cost", "index_prep", "reduce", "comm", "misc", "spare"};
+    "backsub", "update", "cost", "index_prep", "reduce", "comm", "misc", "coarse"};
 
 extern "C" {
 

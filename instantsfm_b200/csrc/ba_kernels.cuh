@@ -194,6 +194,24 @@ static __global__ void reduce_scalars_kernel(const double* __restrict__ p0, cons
   if (threadIdx.x == 0) out[blockIdx.x] = v;
 }
 
+// first stage for long partial arrays (one per fused-kernel CTA: 234 k at 60 M observations):
+// slice k of array a -> stage[a * RED_SLICES + k]; fixed slices, fixed order: deterministic
+constexpr int RED_SLICES = 64;
+static __global__ void reduce_stage_kernel(const double* __restrict__ p0, const double* __restrict__ p1,
+                                           const double* __restrict__ p2, int n0, int n1, int n2, double* __restrict__ stage) {
+  const int a = blockIdx.y, k = blockIdx.x;
+  const double* p = a == 0 ? p0 : (a == 1 ? p1 : p2);
+  const int n = a == 0 ? n0 : (a == 1 ? n1 : n2);
+  double v = 0.0;
+  if (p) {
+    const int per = (n + RED_SLICES - 1) / RED_SLICES;
+    const int lo = min(n, k * per), hi = min(n, lo + per);
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) v += p[i];
+  }
+  v = block_sum(v);
+  if (threadIdx.x == 0) stage[a * RED_SLICES + k] = v;
+}
+
 // ---------------------------------------------------------------------------------------
 // K2 (point side) + K3 (3x3): one thread per point over its contiguous observation records.
 // BUILD: accumulate Hpp = sum Jp^T Jp and g_p = sum Jp^T R.  Always: damp, invert, TP, V.

@@ -71,7 +71,7 @@ struct BASolver : BASolverBase {
   static constexpr int REC = ObsRec<D>::REC;
   DeviceBuffer<T> R, OBS, HPP, GPT, HPPINV, TP, DP, DCQ;
   DeviceBuffer<T> HCC_GC, HME, HD, E, MINV, bvec;  // HME = [Hcc - E_ii | diag Hcc | g_c - e] per camera: one all-reduce per trial
-  DeviceBuffer<double> part_a, part_b, part_c, scalars;
+  DeviceBuffer<double> part_a, part_b, part_c, scalars, red_stage;
   DeviceBuffer<int> fail;
   double* h_scalars = nullptr;  // pinned [4]
   BlockPCG<T, D> pcg;
@@ -160,10 +160,10 @@ struct BASolver : BASolverBase {
     if (getenv("ISFM_NO_FUSED")) fused_ok = false;
     const int64_t n_part = std::max<int64_t>(std::max<int64_t>(RED_BLOCKS, nc), n_fused_cta);
     part_a.alloc(n_part); part_b.alloc(n_part); part_c.alloc(n_part);
-    scalars.alloc(4); fail.alloc(1); fail.zero(s);
+    scalars.alloc(4); fail.alloc(1); fail.zero(s); red_stage.alloc(3 * RED_SLICES);
     if (desc.optimize_poses) {
       UnionKeys hook(this);
-      build_schur_pattern(sp, ix, s, timers, comm_world(comm) > 1 ? &hook : nullptr);
+      build_schur_pattern(sp, ix, s, timers, comm_world(comm) > 1 ? &hook : nullptr, SpmvCfg<T, D>::WB);
       mark("build_schur_pattern");
       HCC_GC.alloc((size_t)nc * (D * D + D)); HD.alloc((size_t)nc * D * D);
       E.alloc((size_t)sp.nnzu * D * D); E.zero(s);   // padding slots stay zero
@@ -353,8 +353,17 @@ struct BASolver : BASolverBase {
 
   // reduce up to three partial arrays to scalars, all-reduce them, copy to the host
   void fetch_scalars(const double* p0, int n0, const double* p1, int n1, const double* p2, int n2, bool allreduce) {
-    { TimerScope ts(timers, T_REDUCE);
-      reduce_scalars_kernel<<<3, 256, 0, s>>>(p0, p1, p2, n0, n1, n2, scalars.get()); }
+    if (std::max(n0, std::max(n1, n2)) > 8192) {
+      // long partial arrays: 64 slices per array first (a single CTA per array took 0.2 ms at 60 M observations)
+      TimerScope ts(timers, T_REDUCE);
+      reduce_stage_kernel<<<dim3(RED_SLICES, 3), 256, 0, s>>>(p0, p1, p2, n0, n1, n2, red_stage.get());
+      const double* st = red_stage.get();
+      reduce_scalars_kernel<<<3, 64, 0, s>>>(p0 ? st : nullptr, p1 ? st + RED_SLICES : nullptr, p2 ? st + 2 * RED_SLICES : nullptr,
+                                             RED_SLICES, RED_SLICES, RED_SLICES, scalars.get());
+    } else {
+      TimerScope ts(timers, T_REDUCE);
+      reduce_scalars_kernel<<<3, 256, 0, s>>>(p0, p1, p2, n0, n1, n2, scalars.get());
+    }
     if (allreduce && comm_world(comm) > 1) {
       TimerScope ts(timers, T_COMM);
       comm_allreduce_sum(comm, scalars.get(), 3, true, s);

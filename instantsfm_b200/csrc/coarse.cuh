@@ -271,10 +271,14 @@ struct CoarseLevel {
     const double density = (double)n_off_global / std::max(1.0, 0.5 * (double)n_cam * (double)(n_cam - 1));
     const bool sparse_chain = n_cam >= 512 && density < 0.15;
     if (!(env ? atoi(env) != 0 : sparse_chain) || n_cam < 8) return;
-    // cluster size: a quarter of the mean upper row length (~ the co-visibility window), at most ~292 clusters
+    // cluster size: a quarter of the mean upper row length (~ the co-visibility window), at most
+    // ISFM_COARSE_MAX_CLUSTERS clusters (default 160: the dense inverse of the 7 * clusters coarse
+    // matrix is replicated on every rank and costs O(clusters^3) per trial)
     int cs = (int)std::max<int64_t>(4, n_off_global / std::max<int64_t>(n_cam, 1) / 4);
     if (const char* e = getenv("ISFM_COARSE_CS")) cs = std::max(2, atoi(e));
-    cs = std::max<int>(cs, (int)((n_cam + 291) / 292));
+    int max_cl = 160;
+    if (const char* e = getenv("ISFM_COARSE_MAX_CLUSTERS")) max_cl = std::max(1, atoi(e));
+    cs = std::max<int>(cs, (int)((n_cam + max_cl - 1) / max_cl));
     cs = (int)std::min<int64_t>(cs, std::max<int64_t>(n_cam / 2, 2));
     g.n_cam = (int)n_cam; g.cs = cs; g.ncl = std::max(1, (int)(n_cam / cs));
     g.ncp = (g.ncl * CM + GJ_B - 1) / GJ_B * GJ_B;
@@ -303,7 +307,7 @@ struct CoarseLevel {
   // prolongation from the current camera rows ([n_cam][cw], t | q_xyzw | ...): once per LM step
   void update_modes(const T* cam, int cw, cudaStream_t s, KernelTimers& kt) {
     if (!enabled) return;
-    TimerScope ts(kt, T_PRECOND);
+    TimerScope ts(kt, T_MISC);
     coarse_centroid_kernel<T><<<div_up(g.ncl, 128), 128, 0, s>>>(g, cw, cam, c0.get());
     coarse_modes_kernel<T><<<div_up(g.n_cam, 128), 128, 0, s>>>(g, cw, cam, c0.get(), Pm.get());
   }
@@ -311,14 +315,14 @@ struct CoarseLevel {
   // Ac^-1 for the current damped system: once per trial.  E: this rank's (partial) upper blocks.
   void factor(const T* E, const T* Hd, const SchurPattern& sp, isfm_comm* comm, cudaStream_t s, KernelTimers& kt) {
     if (!enabled) return;
-    { TimerScope ts(kt, T_PRECOND);
+    { TimerScope ts(kt, T_COARSE);
       ISFM_CUDA(cudaMemsetAsync(G.get(), 0, (size_t)g.ncp * g.ncp * sizeof(double), s));
       coarse_galerkin_kernel<T, D><<<g.ncl * g.ncl, GAL_TPB, 0, s>>>(g, coff.get(), cslot.get(), row_of.get(), sp.ucol.get(), E, Pm.get(), G.get()); }
     if (comm_world(comm) > 1) {
       TimerScope ts(kt, T_COMM);
       comm_allreduce_sum(comm, G.get(), (size_t)g.ncp * g.ncp, true, s);
     }
-    TimerScope ts(kt, T_PRECOND);
+    TimerScope ts(kt, T_COARSE);
     coarse_assemble_kernel<T, D><<<g.ncl + 1, 128, 0, s>>>(g, Hd, Pm.get(), G.get(), A.get());
     ISFM_CUDA(cudaMemsetAsync(fail.get(), 0, sizeof(int), s));
     const int nb = g.ncp / GJ_B;

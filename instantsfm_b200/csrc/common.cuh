@@ -51,9 +51,9 @@ inline bool& tl_count_launches() { static thread_local bool on = true; return on
 
 enum Timer {
   T_LINEARIZE = 0, T_POINT_BLOCKS, T_POINT_SOLVE, T_CAMERA_BLOCKS, T_SCHUR_OFFDIAG, T_PRECOND,
-  T_PCG_SPMV, T_PCG_VEC, T_BACKSUB, T_UPDATE, T_COST, T_INDEX_PREP, T_REDUCE, T_COMM, T_MISC, T_SPARE
+  T_PCG_SPMV, T_PCG_VEC, T_BACKSUB, T_UPDATE, T_COST, T_INDEX_PREP, T_REDUCE, T_COMM, T_MISC, T_COARSE
 };
-static_assert(T_SPARE + 1 == ISFM_N_TIMERS, "timer table size");
+static_assert(T_COARSE + 1 == ISFM_N_TIMERS, "timer table size");
 
 // Optional per-kernel-family CUDA-event timing on the handle's stream.
 struct KernelTimers {

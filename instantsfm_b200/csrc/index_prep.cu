@@ -254,7 +254,7 @@ int64_t count_unique_upper_keys(const uint64_t* keys, int64_t n, int64_t n_cam, 
   return (int64_t)c;
 }
 
-void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, KernelTimers& kt, PatternKeyHook* hook) {
+void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, KernelTimers& kt, PatternKeyHook* hook, int stage_blocks) {
   TimerScope ts(kt, T_INDEX_PREP);
   const int64_t n = ix.n_obs, n_cam = ix.n_cam;
   const int g = div_up(n, TPB);
@@ -404,6 +404,27 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
     ISFM_CUDA(cudaMemcpyAsync(sp.chunk_row.get(), crow.data(), crow.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ISFM_CUDA(cudaMemcpyAsync(sp.chunk_beg.get(), cbeg.data(), cbeg.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ISFM_CUDA(cudaMemcpyAsync(sp.chunk_ptr.get(), cptr.data(), cptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    // stage table (persistent PCG kernel)
+    sp.stage_blocks = stage_blocks; sp.n_stages = 0;
+    std::vector<int4> stg;
+    sp.h_unit_stage_ptr.assign(crow.size() + 1, 0);
+    if (stage_blocks > 0) {
+      stg.reserve(crow.size() * ((SPMV_CHUNK + stage_blocks - 1) / stage_blocks));
+      for (size_t u = 0; u < crow.size(); ++u) {
+        const int32_t row = crow[u], beg = cbeg[u], end = std::min<int32_t>(beg + SPMV_CHUNK, up[row + 1]);
+        sp.h_unit_stage_ptr[u] = (int32_t)stg.size();
+        for (int32_t b = beg; b < end; b += stage_blocks) {
+          const int32_t nb = std::min<int32_t>(stage_blocks, end - b);
+          stg.push_back(make_int4(row, b, nb | (b == beg ? 1 << 8 : 0) | (b + stage_blocks >= end ? 1 << 9 : 0), (int32_t)u));
+        }
+      }
+      sp.h_unit_stage_ptr[crow.size()] = (int32_t)stg.size();
+      sp.n_stages = (int64_t)stg.size();
+      sp.stages.alloc(std::max<size_t>(stg.size(), 1)); sp.unit_stage_ptr.alloc(sp.h_unit_stage_ptr.size());
+      ISFM_CUDA(cudaMemcpyAsync(sp.stages.get(), stg.data(), stg.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+      ISFM_CUDA(cudaMemcpyAsync(sp.unit_stage_ptr.get(), sp.h_unit_stage_ptr.data(), sp.h_unit_stage_ptr.size() * sizeof(int32_t),
+                                cudaMemcpyHostToDevice, s));
+    }
     ISFM_CUDA(cudaStreamSynchronize(s));
   }
   ISFM_CUDA(cudaGetLastError());

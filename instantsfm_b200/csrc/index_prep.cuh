@@ -49,6 +49,14 @@ struct SchurPattern {
   DeviceBuffer<int32_t> chunk_beg;   // [n_chunks] first upper slot of the chunk
   DeviceBuffer<int32_t> chunk_ptr;   // [n_cam + 1] first chunk of each row
   std::vector<int32_t> h_chunk_beg;  // host copy of chunk_beg (splitting the units across ranks)
+  // Stage table of the persistent PCG kernel: every unit cut into stages of <= stage_blocks slots,
+  // in unit order; one int4 per stage = {row, first slot, slots | first-of-unit << 8 | last-of-unit << 9, unit}.
+  // A warp of that kernel walks a contiguous range of this table as ONE continuous cp.async stream.
+  int stage_blocks = 0;
+  int64_t n_stages = 0;
+  DeviceBuffer<int4> stages;            // [n_stages]
+  DeviceBuffer<int32_t> unit_stage_ptr; // [n_chunks + 1] first stage of each unit
+  std::vector<int32_t> h_unit_stage_ptr;
 };
 constexpr int SPMV_CHUNK = 48;   // slots per mat-vec work unit (one warp); multiple of 4
 
@@ -64,8 +72,9 @@ struct PatternKeyHook {
   virtual int64_t extra_keys(const uint64_t* list_key, int64_t n_lists, int64_t n_cam, DeviceBuffer<uint64_t>& out,
                              cudaStream_t stream) = 0;
 };
+// stage_blocks > 0: also build the stage table (slots per stage of the caller's mat-vec kernel)
 void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t stream, KernelTimers& kt,
-                         PatternKeyHook* hook = nullptr);
+                         PatternKeyHook* hook = nullptr, int stage_blocks = 0);
 // number of distinct valid strictly-upper keys (i < j) in `keys` (device, n entries; sorts a copy)
 int64_t count_unique_upper_keys(const uint64_t* keys, int64_t n, int64_t n_cam, cudaStream_t stream);
 // Two 48-bit order-independent hashes of the upper BSR pattern (row pointers and columns): equal

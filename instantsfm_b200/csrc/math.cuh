@@ -187,16 +187,36 @@ template <typename T> ISFM_HD void transform_point(const T* cam7, const T* X, T 
   y[2] = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + cam7[2];
 }
 
-// residual only: proj - obs  (ReprojNonBatched.forward, bundle_adjustment.py:59-64)
-template <int MODEL, typename T>
-ISFM_HD void ba_residual(const T* cam, const T* pp, const T* X, const T* obs, T r[2]) {
-  T R[9], y[3];
+// residual only: proj - obs  (ReprojNonBatched.forward, bundle_adjustment.py:59-64), in the
+// arithmetic of S.
+template <int MODEL, typename S>
+ISFM_HD void ba_residual_in(const S* cam, const S* pp, const S* X, const S* obs, S r[2]) {
+  S R[9], y[3];
   transform_point(cam, X, R, y);
-  T iz = T(1) / y[2];
-  T u0 = y[0] * iz, u1 = y[1] * iz, o0, o1;
-  distort<MODEL, T>(u0, u1, cam + 7, o0, o1);
+  S iz = S(1) / y[2];
+  S u0 = y[0] * iz, u1 = y[1] * iz, o0, o1;
+  distort<MODEL, S>(u0, u1, cam + 7, o0, o1);
   r[0] = o0 + pp[0] - obs[0];
   r[1] = o1 + pp[1] - obs[1];
+}
+
+// The residual is ALWAYS evaluated in double, also in the fp32 build: proj ~ 1e3 px against
+// residuals of ~0.5 px means that fp32 arithmetic leaves ~1e-4 RELATIVE noise on every residual,
+// i.e. on the gradient J^T r -- which moves weakly constrained points by several 1e-4 of their
+// norm and is the difference between meeting and missing the 1e-4 parity bar on poses / points.
+// ~80 double operations per observation next to ~800 fp32 ones for the Jacobian blocks; the
+// parameters themselves stay fp32 (the minimiser is sought on the fp32 grid, evaluated exactly).
+template <int MODEL, typename T>
+ISFM_HD void ba_residual(const T* cam, const T* pp, const T* X, const T* obs, T r[2]) {
+  constexpr int CW = 7 + ModelTraits<MODEL>::NI;
+  double c[CW], p2[2], x[3], o[2], rd[2];
+#pragma unroll
+  for (int i = 0; i < CW; ++i) c[i] = (double)cam[i];
+  p2[0] = (double)pp[0]; p2[1] = (double)pp[1];
+  x[0] = (double)X[0]; x[1] = (double)X[1]; x[2] = (double)X[2];
+  o[0] = (double)obs[0]; o[1] = (double)obs[1];
+  ba_residual_in<MODEL, double>(c, p2, x, o, rd);
+  r[0] = (T)rd[0]; r[1] = (T)rd[1];
 }
 
 // residual + Jacobian blocks (unweighted).  Jc[2][D] with D = 6 + NI: columns
@@ -217,8 +237,12 @@ ISFM_HD void ba_linearize(const T* cam, const T* pp, const T* X, const T* obs, T
   for (int i = 0; i < NI; ++i) k[i] = S::seed(cam[7 + i], 2 + i);
   S o0, o1;
   distort<MODEL, S>(S::seed(u0, 0), S::seed(u1, 1), k, o0, o1);
-  r[0] = o0.v + pp[0] - obs[0];
-  r[1] = o1.v + pp[1] - obs[1];
+  if (sizeof(T) == 8) {
+    r[0] = o0.v + pp[0] - obs[0];
+    r[1] = o1.v + pp[1] - obs[1];
+  } else {
+    ba_residual<MODEL, T>(cam, pp, X, obs, r);   // double arithmetic (see above); the blocks stay in T
+  }
   // Jy = dproj/du * du/dy,  du/dy = (1/z) [1 0 -u0; 0 1 -u1]
   T Jy[6];
   Jy[0] = o0.d[0] * iz; Jy[1] = o0.d[1] * iz; Jy[2] = -(o0.d[0] * u0 + o0.d[1] * u1) * iz;

@@ -641,18 +641,29 @@ struct BlockPCG {
       pcg_init_state_kernel<D><<<1, 256, 0, s>>>(n_cam, max_iter, part_a.get(), part_b.get(), state.get()); }
     const double tol2 = tol * tol;
     // ---- persistent path: the whole solve in one cooperative kernel (single rank or peer exchange) ----
-    if (persist_grid > 0 && (!multi || peer) && !kt.enabled_fine()) {
+    if (persist_grid > 0 && (!multi || peer) && !kt.enabled_fine() && sp.stage_blocks == SpmvCfg<T, D>::WB) {
       PcgArgs<T> a;
       memset(&a, 0, sizeof a);
       a.n_cam = n_cam; a.unit_lo = (int)unit_lo; a.unit_hi = (int)unit_hi; a.max_iter = max_iter;
       a.unit_row = sp.chunk_row.get(); a.unit_beg = sp.chunk_beg.get(); a.urow_ptr = sp.urow_ptr.get(); a.ucol = sp.ucol.get();
       a.tpos = sp.tpos.get(); a.dep_beg = dep_beg; a.dep_end = dep_end; a.chunk_ptr = sp.chunk_ptr.get();
+      a.stages = sp.stages.get();
+      a.stage_lo = sp.h_unit_stage_ptr[(size_t)unit_lo]; a.stage_hi = sp.h_unit_stage_ptr[(size_t)unit_hi];
       a.E = E; a.Hd = Hd; a.Minv = Minv;
       a.x = x.get(); a.r = r.get(); a.z = z.get(); a.p = p.get(); a.pp = pp.get(); a.q = q.get(); a.y = y.get(); a.yup = yup.get(); a.C = C.get();
       a.part_pq = part_pq.get(); a.part_a = part_a.get(); a.part_b = part_b.get();
       a.st = state.get(); a.tol2 = tol2;
+      // warps per row-pair group of the combine phase: cheapest of {1, 2, 4} by rounds x (L2 round trips of a thread + sync)
       const int64_t avg_dep = sp.n_off / std::max(n_cam, 1);
-      a.wpr = avg_dep < 192 ? 1 : (avg_dep < 512 ? 2 : 4);
+      {
+        double best = 1e300;
+        for (int wpr : {1, 2, 4}) {
+          const int gpc = PersistCfg<T, D>::NW / wpr, G = 32 * wpr / D;
+          const int64_t rounds = div_up((n_cam + 1) / 2, (int64_t)persist_grid * gpc);
+          const double cost = (double)rounds * (1.5 + 0.7 * std::ceil(2.0 * (double)avg_dep / std::max(G, 1) / 16.0));
+          if (cost < best) { best = cost; a.wpr = wpr; }
+        }
+      }
       if (const char* e = getenv("ISFM_PCG_WPR")) a.wpr = std::max(1, std::min(4, atoi(e)));
       if (a.wpr == 3) a.wpr = 2;
       a.cams_per_cta = div_up(n_cam, persist_grid);

@@ -33,7 +33,8 @@ template <typename T, int D> struct PersistCfg {
   static constexpr int DP = (D + S::VE - 1) / S::VE * S::VE;
   static constexpr int NCH = DP / S::VE;                              // 16-byte chunks per padded row
   static constexpr int POFF = S::NLD * 32 * S::VE;                    // offset of the p_j area inside a stage buffer
-  static constexpr int STG = POFF + S::WB * DP;                       // elements per stage buffer
+  static constexpr int PIOFF = POFF + S::WB * DP;                     // offset of p_i (the stage's own row)
+  static constexpr int STG = PIOFF + DP;                              // elements per stage buffer
   static constexpr size_t PER_WARP = 2 * (size_t)STG * sizeof(T);
   static constexpr int NW_RAW = (int)((size_t)222 * 1024 / PER_WARP);
   static constexpr int NW = NW_RAW >= 24 ? 24 : (NW_RAW >= 16 ? 16 : (NW_RAW >= 12 ? 12 : 8));
@@ -47,6 +48,8 @@ template <typename T>
 struct PcgArgs {
   int n_cam, unit_lo, unit_hi, max_iter;
   const int32_t *unit_row, *unit_beg, *urow_ptr, *ucol, *tpos, *dep_beg, *dep_end, *chunk_ptr;
+  const int4* stages;          // SchurPattern::stages
+  int stage_lo, stage_hi;      // stages of the units [unit_lo, unit_hi)
   const T *E, *Hd, *Minv;
   T *x, *r, *z, *p, *pp, *q, *y, *yup, *C;   // pp: p padded to rows of PersistCfg::DP elements
   double *part_pq, *part_a, *part_b;   // [gridDim.x] per-CTA partials of p.q, r.z, r.r
@@ -124,37 +127,36 @@ __device__ __forceinline__ void sum_partials2(const double* __restrict__ pa, con
   __syncthreads();
 }
 
-// One mat-vec work unit (<= SPMV_CHUNK consecutive slots of one upper row) by one warp; see
-// pcg_spmv_upper_kernel.  `unit` is a global unit id.
+// Mat-vec phase of one warp: a contiguous range [g0, g1) of the stage table, walked as ONE
+// continuous cp.async stream (stage g + 1 is in flight while stage g is multiplied; the per-stage
+// descriptors are fetched three, the column / deposit indices two stages ahead).  Unit and row
+// changes happen inside the stream -- the stage's own p_i travels with it into shared memory, the
+// row partial is folded and stored when a stage is flagged last-of-unit -- so a warp never drains
+// its pipeline between work units (the stand-alone kernel, one unit per warp, does).
 template <typename T, int D>
-__device__ __forceinline__ void spmv_unit(T* buf, int lane, int unit, const PcgArgs<T>& a, uint64_t pol_stream, uint64_t pol_keep, bool hint) {
+__device__ __forceinline__ void spmv_stream(T* buf, int lane, int g0, int g1, const PcgArgs<T>& a, uint64_t pol_stream,
+                                            uint64_t pol_keep, bool hint) {
   typedef SpmvCfg<T, D> Cfg;
   typedef PersistCfg<T, D> PC;
-  constexpr int GPW = Cfg::GPW, WB = Cfg::WB, DD = D * D, VE = Cfg::VE, NLD = Cfg::NLD, STG = PC::STG, DP = PC::DP;
+  constexpr int GPW = Cfg::GPW, DD = D * D, VE = Cfg::VE, NLD = Cfg::NLD, STG = PC::STG, DP = PC::DP;
+  if (g0 >= g1) return;
   const int bl = lane / D, r = lane % D;
-  const int row = __ldg(a.unit_row + unit);
-  const int beg = __ldg(a.unit_beg + unit), end = min(beg + SPMV_CHUNK, __ldg(a.urow_ptr + row + 1));
-  const int ns = (end - beg + WB - 1) / WB;
-  T pi[D];
-#pragma unroll
-  for (int c = 0; c < D; ++c) pi[c] = __ldcg(a.p + (size_t)row * D + c);
-  auto load_idx = [&](int k, int* jj, int* tp) {
-    const int base = beg + k * WB;
-    const int nb = min(WB, end - base);
+  auto meta = [&](int g) -> int4 { return g < g1 ? __ldg(a.stages + g) : make_int4(0, 0, 0, 0); };
+  auto load_idx = [&](const int4& m, int* jj, int* tp) {
+    const int nb = m.z & 0xff;
 #pragma unroll
     for (int pass = 0; pass < Cfg::PASSES; ++pass) {
       const int b = pass * GPW + bl;
-      const bool on = k < ns && bl < GPW && b < nb;
-      jj[pass] = on ? __ldg(a.ucol + base + b) : -1;
-      tp[pass] = on ? __ldg(a.tpos + base + b) : -1;
+      const bool on = bl < GPW && b < nb;
+      jj[pass] = on ? __ldg(a.ucol + m.y + b) : -1;
+      tp[pass] = on ? __ldg(a.tpos + m.y + b) : -1;
     }
   };
-  auto issue = [&](int k, const int* jj) {
-    const int base = beg + k * WB;
-    const int nb = min(WB, end - base);
+  auto issue = [&](int g, const int4& m, const int* jj) {
+    const int nb = m.z & 0xff;
     const int last = nb * DD / VE - 1;   // indices past the end re-copy the last vector
-    const T* src = a.E + (size_t)base * DD;
-    T* dst = buf + (size_t)(k & 1) * STG;
+    const T* src = a.E + (size_t)m.y * DD;
+    T* dst = buf + (size_t)((g - g0) & 1) * STG;
     if (hint) {
 #pragma unroll
       for (int q = 0; q < NLD; ++q) cp_async16_hint(dst + (size_t)(lane + 32 * q) * VE, src + (size_t)min(lane + 32 * q, last) * VE, pol_stream);
@@ -165,18 +167,22 @@ __device__ __forceinline__ void spmv_unit(T* buf, int lane, int unit, const PcgA
 #pragma unroll
     for (int pass = 0; pass < Cfg::PASSES; ++pass)
       if (jj[pass] >= 0 && r < PC::NCH) cp_async16(dst + PC::POFF + (pass * GPW + bl) * DP + r * VE, a.pp + (size_t)jj[pass] * DP + r * VE);
+    if (lane < PC::NCH) cp_async16(dst + PC::PIOFF + lane * VE, a.pp + (size_t)m.x * DP + lane * VE);
     cp_async_commit();
   };
+  int4 m0 = meta(g0), m1 = meta(g0 + 1), m2 = meta(g0 + 2);
   int j0[Cfg::PASSES], t0[Cfg::PASSES], j1[Cfg::PASSES], t1[Cfg::PASSES], j2[Cfg::PASSES], t2[Cfg::PASSES];
-  load_idx(0, j0, t0);
-  load_idx(1, j1, t1);
-  issue(0, j0);
+  load_idx(m0, j0, t0);
+  load_idx(m1, j1, t1);
+  issue(g0, m0, j0);
   T acc = T(0);
-  for (int k = 0; k < ns; ++k) {
-    load_idx(k + 2, j2, t2);
-    if (k + 1 < ns) { issue(k + 1, j1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+  for (int g = g0; g < g1; ++g) {
+    const int4 m3 = meta(g + 3);
+    load_idx(m2, j2, t2);
+    if (g + 1 < g1) { issue(g + 1, m1, j1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncwarp();
-    const T* S = buf + (size_t)(k & 1) * STG;
+    const T* S = buf + (size_t)((g - g0) & 1) * STG;
+    const T* pi = S + PC::PIOFF;
 #pragma unroll
     for (int pass = 0; pass < Cfg::PASSES; ++pass) {
       if (j0[pass] >= 0) {
@@ -188,16 +194,20 @@ __device__ __forceinline__ void spmv_unit(T* buf, int lane, int unit, const PcgA
         if (t0[pass] >= 0) st_global_hint(a.C + (size_t)t0[pass] * D + r, t, pol_keep);
       }
     }
+    if (m0.z & (1 << 9)) {   // last stage of its unit: fold the GPW block lanes onto lanes 0..D-1, store the unit's row partial
+#pragma unroll
+      for (int k = 1; k < GPW; ++k) {
+        T o = __shfl_sync(0xffffffffu, acc, (lane + k * D) & 31);
+        if (lane < D) acc += o;
+      }
+      if (lane < D) st_global_hint(a.yup + (size_t)m0.w * D + lane, acc, pol_keep);
+      acc = T(0);
+    }
     __syncwarp();
 #pragma unroll
     for (int pass = 0; pass < Cfg::PASSES; ++pass) { j0[pass] = j1[pass]; t0[pass] = t1[pass]; j1[pass] = j2[pass]; t1[pass] = t2[pass]; }
+    m0 = m1; m1 = m2; m2 = m3;
   }
-#pragma unroll
-  for (int k = 1; k < GPW; ++k) {
-    T o = __shfl_sync(0xffffffffu, acc, (lane + k * D) & 31);
-    if (lane < D) acc += o;
-  }
-  if (lane < D) st_global_hint(a.yup + (size_t)unit * D + lane, acc, pol_keep);
 }
 
 // true when camera row `row` lies in the circular range [lo, lo + len) of an n-row system
@@ -231,10 +241,13 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
     if (prof) { const unsigned long long t = global_ns(); a.phase_ns[ph] += t - t_prev; t_prev = t; }
   };
 
-  // mat-vec units of this warp: a contiguous share of [unit_lo, unit_hi)
-  const int n_units = a.unit_hi - a.unit_lo;
+  // mat-vec stages of this warp: an equal share of [stage_lo, stage_hi), moved to unit boundaries
+  // (a unit's row partial is produced by exactly one warp)
+  const int n_stages = a.stage_hi - a.stage_lo;
   const long long wg = (long long)blockIdx.x * NW + w, wtot = (long long)nblk * NW;
-  const int wu0 = a.unit_lo + (int)((wg * n_units) / wtot), wu1 = a.unit_lo + (int)(((wg + 1) * n_units) / wtot);
+  int wg0 = a.stage_lo + (int)((wg * n_stages) / wtot), wg1 = a.stage_lo + (int)(((wg + 1) * n_stages) / wtot);
+  while (wg0 < a.stage_hi && !(__ldg(a.stages + wg0).z & (1 << 8))) ++wg0;
+  while (wg1 < a.stage_hi && !(__ldg(a.stages + wg1).z & (1 << 8))) ++wg1;
   T* wbuf = smem + (size_t)w * 2 * PC::STG;
 
   // combine phase geometry: a group of `wpr` warps sums one pair of rows (b, n - 1 - b)
@@ -243,7 +256,7 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
   const int gg = gt / D, gc = gt % D;
   const int n_pairs = (n + 1) / 2;
   const long long gtot = (long long)nblk * gpc;
-  constexpr int MLP = 8;
+  constexpr int MLP = 16;
 
   // cameras of the update / direction phases: an even share, or -- two-level -- whole clusters
   constexpr int CPB = NT / D;
@@ -277,7 +290,7 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
     const int parity = (int)((seq + 1u) & 1u);
     if (!first) {
     // ---------------- P1: mat-vec ----------------
-    for (int u = wu0; u < wu1; ++u) spmv_unit<T, D>(wbuf, lane, u, a, pol_stream, pol_keep, !a.keep_in_l2);
+    spmv_stream<T, D>(wbuf, lane, wg0, wg1, a, pol_stream, pol_keep, !a.keep_in_l2);
     if (!grid_barrier<false>(st, epoch)) return;
     lap(PH_SPMV);
 

@@ -11,7 +11,7 @@ system) instead of full-system Jacobi PCG (1e-5).
 import numpy as np
 
 from ..engine import BAEngine
-from ..geometry import matrices_to_pose7, pose7_to_matrices, transform_points
+from ..geometry import matrices_to_pose7, pose7_to_matrices, quat_to_mat as quat_rows_to_matrices
 from ._common import concat_features, device_index, flatten_observations, should_stop
 
 # CameraModelId.value -> principal-point indices inside Camera.params (scene/defs.py:115-140).
@@ -86,12 +86,27 @@ class TorchBA:
         table, offsets = concat_features(images, "features")
         points_2d = table[offsets[image_id] + feature_id].reshape(-1, 2)
 
-        # cheirality, evaluated once before the solve (:102-107)
-        y = transform_points(camera_params[image_id, :7], points_3d[point_idx])
-        valid = y[:, 2] > 0.1
+        # cheirality, evaluated once before the solve (:102-107): only the depth y.z = R[2,:] X + t_z is
+        # needed, with ONE rotation matrix per image instead of one per observation
+        if image_id.size:
+            R = quat_rows_to_matrices(camera_params[:, 3:7])
+            z = np.einsum("nj,nj->n", R[image_id, 2, :], points_3d[point_idx]) + camera_params[image_id, 2]
+            valid = z > 0.1
+        else:
+            valid = np.zeros(0, bool)
         points_2d, image_id, point_idx = points_2d[valid], image_id[valid], point_idx[valid]
-        unique_cameras, cam_inv = np.unique(image_id, return_inverse=True)             # torch.unique(sorted=True)
-        unique_points, pt_inv = np.unique(point_idx, return_inverse=True)
+        # torch.unique(sorted=True, return_inverse=True) (:108-109) without a sort: images through a
+        # presence table, points through the run boundaries of the (non-decreasing) point index
+        present = np.zeros(len(images), dtype=bool)
+        present[image_id] = True
+        unique_cameras = np.flatnonzero(present)
+        cam_inv = (np.cumsum(present) - 1)[image_id]
+        if point_idx.size and np.all(point_idx[1:] >= point_idx[:-1]):
+            new_run = np.concatenate([[True], point_idx[1:] != point_idx[:-1]])
+            unique_points = point_idx[new_run]
+            pt_inv = np.cumsum(new_run) - 1
+        else:
+            unique_points, pt_inv = np.unique(point_idx, return_inverse=True)
         return {"track_keys": track_keys, "unique_cameras": unique_cameras, "unique_points": unique_points,
                 "remaining": remaining, "pp_indices": pp_indices,
                 "camera_params": camera_params[unique_cameras], "camera_pps": camera_pps[unique_cameras],
