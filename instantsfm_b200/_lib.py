@@ -5,7 +5,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libisfm_b200.so")
+# ISFM_LIB_PATH: an alternative build of the same library (kernel-variant A/B runs); never a fallback
+LIB_PATH = os.environ.get("ISFM_LIB_PATH") or os.path.join(_HERE, "lib", "libisfm_b200.so")
 N_TIMERS = 16
 
 

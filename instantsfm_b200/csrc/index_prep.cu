@@ -189,6 +189,18 @@ __global__ void list_len_key_kernel(const int64_t* __restrict__ list_off, int64_
   id[t] = (int32_t)t;
 }
 
+// stage table: flag (bit 10) the stages whose columns are consecutive
+__global__ void stage_contiguity_kernel(int4* stages, int64_t n_stages, const int32_t* __restrict__ ucol) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= n_stages) return;
+  int4 m = stages[g];
+  const int nb = m.z & 0xff;
+  bool contig = nb > 0;
+  const int j0 = nb > 0 ? ucol[m.y] : 0;
+  for (int b = 1; b < nb && contig; ++b) contig = ucol[m.y + b] == j0 + b;
+  if (contig) { m.z |= 1 << 10; stages[g] = m; }
+}
+
 int bits_for(uint64_t max_value) {
   int b = 1;
   while (b < 64 && (max_value >> b) != 0) ++b;
@@ -424,6 +436,8 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
       ISFM_CUDA(cudaMemcpyAsync(sp.stages.get(), stg.data(), stg.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
       ISFM_CUDA(cudaMemcpyAsync(sp.unit_stage_ptr.get(), sp.h_unit_stage_ptr.data(), sp.h_unit_stage_ptr.size() * sizeof(int32_t),
                                 cudaMemcpyHostToDevice, s));
+      if (sp.n_stages > 0)
+        stage_contiguity_kernel<<<div_up(sp.n_stages, TPB), TPB, 0, s>>>(sp.stages.get(), sp.n_stages, sp.ucol.get());
     }
     ISFM_CUDA(cudaStreamSynchronize(s));
   }

@@ -219,11 +219,11 @@ ISFM_HD void ba_residual(const T* cam, const T* pp, const T* X, const T* obs, T 
   r[0] = (T)rd[0]; r[1] = (T)rd[1];
 }
 
-// residual + Jacobian blocks (unweighted).  Jc[2][D] with D = 6 + NI: columns
-// [d tau (3), d phi (3), intrinsics] for the left perturbation X <- Exp(delta) X; Jp[2][3].
+// residual + Jacobian blocks (unweighted), in the arithmetic of T.  Jc[2][D] with D = 6 + NI:
+// columns [d tau (3), d phi (3), intrinsics] for the left perturbation X <- Exp(delta) X; Jp[2][3].
 template <int MODEL, typename T>
-ISFM_HD void ba_linearize(const T* cam, const T* pp, const T* X, const T* obs, T r[2],
-                          T* Jc /* 2*D */, T Jp[6]) {
+ISFM_HD void ba_linearize_in(const T* cam, const T* pp, const T* X, const T* obs, T r[2],
+                             T* Jc /* 2*D */, T Jp[6]) {
   constexpr int NI = ModelTraits<MODEL>::NI;
   constexpr int D = 6 + NI;
   constexpr int ND = 2 + NI;
@@ -237,12 +237,8 @@ ISFM_HD void ba_linearize(const T* cam, const T* pp, const T* X, const T* obs, T
   for (int i = 0; i < NI; ++i) k[i] = S::seed(cam[7 + i], 2 + i);
   S o0, o1;
   distort<MODEL, S>(S::seed(u0, 0), S::seed(u1, 1), k, o0, o1);
-  if (sizeof(T) == 8) {
-    r[0] = o0.v + pp[0] - obs[0];
-    r[1] = o1.v + pp[1] - obs[1];
-  } else {
-    ba_residual<MODEL, T>(cam, pp, X, obs, r);   // double arithmetic (see above); the blocks stay in T
-  }
+  r[0] = o0.v + pp[0] - obs[0];
+  r[1] = o1.v + pp[1] - obs[1];
   // Jy = dproj/du * du/dy,  du/dy = (1/z) [1 0 -u0; 0 1 -u1]
   T Jy[6];
   Jy[0] = o0.d[0] * iz; Jy[1] = o0.d[1] * iz; Jy[2] = -(o0.d[0] * u0 + o0.d[1] * u1) * iz;
@@ -261,6 +257,37 @@ ISFM_HD void ba_linearize(const T* cam, const T* pp, const T* X, const T* obs, T
     Jp[3 * row + 0] = j[0] * R[0] + j[1] * R[3] + j[2] * R[6];   // Jy R
     Jp[3 * row + 1] = j[0] * R[1] + j[1] * R[4] + j[2] * R[7];
     Jp[3 * row + 2] = j[0] * R[2] + j[1] * R[5] + j[2] * R[8];
+  }
+}
+
+// The linearisation is ALWAYS evaluated in double, also in the fp32 build (the blocks are then
+// stored as fp32).  Two measured reasons (C1, 12 LM steps against the fp64 oracle): (i) proj ~ 1e3
+// px against residuals of ~0.5 px leaves ~1e-4 relative noise on every fp32 residual; (ii) the
+// rotation columns -Jy [y]x are differences of products ~1e3 and carry ~1e-6 relative error in
+// fp32.  Either one perturbs the gradient J^T r by an amount that the softest modes of the
+// reduced system (lambda ~ 1e-4 .. 1e-6 of the diagonal) amplify into ~1e-4 relative errors of
+// rotations and weakly constrained points -- the difference between missing and meeting the 1e-4
+// parity bar.  ~10^3 double operations per observation, once per LM step.
+template <int MODEL, typename T>
+ISFM_HD void ba_linearize(const T* cam, const T* pp, const T* X, const T* obs, T r[2],
+                          T* Jc /* 2*D */, T Jp[6]) {
+  if (sizeof(T) == 8) {
+    ba_linearize_in<MODEL, T>(cam, pp, X, obs, r, Jc, Jp);
+  } else {
+    constexpr int NI = ModelTraits<MODEL>::NI;
+    constexpr int D = 6 + NI, CW = 7 + NI;
+    double c[CW], p2[2], x[3], o[2], rd[2], jc[2 * D], jp[6];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) c[i] = (double)cam[i];
+    p2[0] = (double)pp[0]; p2[1] = (double)pp[1];
+    x[0] = (double)X[0]; x[1] = (double)X[1]; x[2] = (double)X[2];
+    o[0] = (double)obs[0]; o[1] = (double)obs[1];
+    ba_linearize_in<MODEL, double>(c, p2, x, o, rd, jc, jp);
+    r[0] = (T)rd[0]; r[1] = (T)rd[1];
+#pragma unroll
+    for (int i = 0; i < 2 * D; ++i) Jc[i] = (T)jc[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Jp[i] = (T)jp[i];
   }
 }
 

@@ -653,19 +653,6 @@ struct BlockPCG {
       a.x = x.get(); a.r = r.get(); a.z = z.get(); a.p = p.get(); a.pp = pp.get(); a.q = q.get(); a.y = y.get(); a.yup = yup.get(); a.C = C.get();
       a.part_pq = part_pq.get(); a.part_a = part_a.get(); a.part_b = part_b.get();
       a.st = state.get(); a.tol2 = tol2;
-      // warps per row-pair group of the combine phase: cheapest of {1, 2, 4} by rounds x (L2 round trips of a thread + sync)
-      const int64_t avg_dep = sp.n_off / std::max(n_cam, 1);
-      {
-        double best = 1e300;
-        for (int wpr : {1, 2, 4}) {
-          const int gpc = PersistCfg<T, D>::NW / wpr, G = 32 * wpr / D;
-          const int64_t rounds = div_up((n_cam + 1) / 2, (int64_t)persist_grid * gpc);
-          const double cost = (double)rounds * (1.5 + 0.7 * std::ceil(2.0 * (double)avg_dep / std::max(G, 1) / 16.0));
-          if (cost < best) { best = cost; a.wpr = wpr; }
-        }
-      }
-      if (const char* e = getenv("ISFM_PCG_WPR")) a.wpr = std::max(1, std::min(4, atoi(e)));
-      if (a.wpr == 3) a.wpr = 2;
       a.cams_per_cta = div_up(n_cam, persist_grid);
       const int64_t my_slots = n_units > 0 ? (int64_t)std::min<int64_t>((int64_t)n_units * SPMV_CHUNK, sp.nnzu) : 0;
       a.keep_in_l2 = (size_t)my_slots * D * D * sizeof(T) <= ((size_t)72 << 20) && !getenv("ISFM_NO_L2_KEEP");

@@ -55,7 +55,6 @@ struct PcgArgs {
   double *part_pq, *part_a, *part_b;   // [gridDim.x] per-CTA partials of p.q, r.z, r.r
   PcgState* st;
   double tol2;
-  int wpr;            // warps per row group in the combine phase (1, 2, 4 or 8)
   int cams_per_cta;   // cameras of the update / direction phases owned by one CTA (whole clusters when coarse)
   int keep_in_l2;     // this rank's slice of E fits the L2: stream it without the evict_first hint
   // multi-rank exchange of y over peer memory (comm.cuh); row_lo / row_len: circular range of the
@@ -142,13 +141,17 @@ __device__ __forceinline__ void spmv_stream(T* buf, int lane, int g0, int g1, co
   if (g0 >= g1) return;
   const int bl = lane / D, r = lane % D;
   auto meta = [&](int g) -> int4 { return g < g1 ? __ldg(a.stages + g) : make_int4(0, 0, 0, 0); };
+  // m.z bit 10: the stage's columns are consecutive (dense rows, banded street rows): column =
+  // first column + block index, no index loads, and the p_j rows form ONE contiguous piece of pp
   auto load_idx = [&](const int4& m, int* jj, int* tp) {
     const int nb = m.z & 0xff;
+    const bool contig = (m.z & (1 << 10)) != 0;
+    const int jfirst = (contig && nb > 0) ? __ldg(a.ucol + m.y) : 0;
 #pragma unroll
     for (int pass = 0; pass < Cfg::PASSES; ++pass) {
       const int b = pass * GPW + bl;
       const bool on = bl < GPW && b < nb;
-      jj[pass] = on ? __ldg(a.ucol + m.y + b) : -1;
+      jj[pass] = on ? (contig ? jfirst + b : __ldg(a.ucol + m.y + b)) : -1;
       tp[pass] = on ? __ldg(a.tpos + m.y + b) : -1;
     }
   };
@@ -164,9 +167,17 @@ __device__ __forceinline__ void spmv_stream(T* buf, int lane, int g0, int g1, co
 #pragma unroll
       for (int q = 0; q < NLD; ++q) cp_async16(dst + (size_t)(lane + 32 * q) * VE, src + (size_t)min(lane + 32 * q, last) * VE);
     }
+    if (m.z & (1 << 10)) {
+      // consecutive columns: nb padded rows of pp in one run -- coalesced 16-byte copies (a few
+      // 128-byte lines) instead of nb scattered ones (one L2 transaction each)
+      const int jfirst = __shfl_sync(0xffffffffu, jj[0], 0);   // lane 0 owns block 0 of pass 0
+      const T* psrc = a.pp + (size_t)jfirst * DP;
+      for (int c = lane; c < nb * PC::NCH; c += 32) cp_async16(dst + PC::POFF + c * VE, psrc + c * VE);
+    } else {
 #pragma unroll
-    for (int pass = 0; pass < Cfg::PASSES; ++pass)
-      if (jj[pass] >= 0 && r < PC::NCH) cp_async16(dst + PC::POFF + (pass * GPW + bl) * DP + r * VE, a.pp + (size_t)jj[pass] * DP + r * VE);
+      for (int pass = 0; pass < Cfg::PASSES; ++pass)
+        if (jj[pass] >= 0 && r < PC::NCH) cp_async16(dst + PC::POFF + (pass * GPW + bl) * DP + r * VE, a.pp + (size_t)jj[pass] * DP + r * VE);
+    }
     if (lane < PC::NCH) cp_async16(dst + PC::PIOFF + lane * VE, a.pp + (size_t)m.x * DP + lane * VE);
     cp_async_commit();
   };
@@ -250,12 +261,16 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
   while (wg1 < a.stage_hi && !(__ldg(a.stages + wg1).z & (1 << 8))) ++wg1;
   T* wbuf = smem + (size_t)w * 2 * PC::STG;
 
-  // combine phase geometry: a group of `wpr` warps sums one pair of rows (b, n - 1 - b)
-  const int wpr = a.wpr, gthreads = 32 * wpr, G = gthreads / D;
+  // combine phase geometry: the row pairs (b, n - 1 - b) -- equal work on a dense system -- are dealt
+  // to the CTAs in contiguous shares; a CTA with m pairs forms groups of NW / m warps (all its
+  // threads work whether it owns 1 pair or 100), one pair per group and round
+  const int n_pairs = (n + 1) / 2;
+  const int pair0 = (int)(((long long)blockIdx.x * n_pairs) / nblk), pair1 = (int)(((long long)(blockIdx.x + 1) * n_pairs) / nblk);
+  const int m_pairs = pair1 - pair0;
+  const int wpr = m_pairs >= NW ? 1 : NW / max(m_pairs, 1);
+  const int gthreads = 32 * wpr, G = gthreads / D;
   const int grp = w / wpr, gpc = NW / wpr, gt = tid - grp * gthreads;   // group in CTA, groups per CTA, thread in group
   const int gg = gt / D, gc = gt % D;
-  const int n_pairs = (n + 1) / 2;
-  const long long gtot = (long long)nblk * gpc;
   constexpr int MLP = 16;
 
   // cameras of the update / direction phases: an even share, or -- two-level -- whole clusters
@@ -297,11 +312,11 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
     // ---------------- P2: combine ----------------
     {
       int round = 0;
-      for (long long item0 = 0; item0 < n_pairs; item0 += gtot, ++round) {
-        const long long item = item0 + (long long)blockIdx.x * gpc + grp;
+      for (int item0 = pair0; item0 < pair1; item0 += gpc, ++round) {
+        const int item = item0 + grp;
         T* sh = smem + (size_t)(round & 1) * (NW * 32 * 2) + (size_t)grp * (gthreads * 2);   // [half][G][D] per group
         int rows[2] = {-1, -1};
-        if (item < n_pairs && grp < gpc) {
+        if (item < pair1 && grp < gpc) {
           rows[0] = (int)item;
           rows[1] = n - 1 - (int)item;
           if (rows[1] <= rows[0]) rows[1] = -1;   // middle row of an odd system: once
