@@ -862,7 +862,7 @@ struct FusedTmaCfg {
 };
 
 #ifndef ISFM_FUSED_TMA_MINB
-#define ISFM_FUSED_TMA_MINB 5
+#define ISFM_FUSED_TMA_MINB 4
 #endif
 template <int MODEL>
 __global__ void __launch_bounds__(FUSED_TPB, ISFM_FUSED_TMA_MINB * (256 / FUSED_TPB))

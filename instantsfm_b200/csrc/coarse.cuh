@@ -98,45 +98,50 @@ __global__ void coarse_modes_kernel(CoarseGeom g, int cw, const T* __restrict__ 
   }
 }
 
-// ---- per trial: G = P^T E P (dense [ncp][ncp], fp64), one CTA per coarse block (I <= J) ----
-// A group of 8 lanes (7 working) owns one member block at a time; lane k forms column k of
-// X = P_i^T B P_j and keeps 7 fp64 accumulators.  The groups' sums are added in group order.
+// ---- per trial: G = P^T E P (dense [ncp][ncp], fp64) ----
+// CTA (k, c): chunk c of the member blocks of the k-th non-empty coarse block (I <= J).  A group of
+// 8 lanes (7 working) owns one member block at a time; lane k forms column k of X = P_i^T B P_j
+// (fp32 products of fp32 data) and keeps 7 fp64 accumulators.  The groups' sums are added in
+// group order into the chunk's own partial matrix; coarse_reduce_parts_kernel adds the chunks in
+// chunk order: deterministic, no atomics.
 constexpr int GAL_TPB = 128;
+constexpr int GAL_SPLIT = 8;
 template <typename T, int D>
 __global__ void __launch_bounds__(GAL_TPB)
-coarse_galerkin_kernel(CoarseGeom g, const int32_t* __restrict__ coff, const int32_t* __restrict__ cslot,
+coarse_galerkin_kernel(CoarseGeom g, const int2* __restrict__ cblocks, const int32_t* __restrict__ coff, const int32_t* __restrict__ cslot,
                        const int32_t* __restrict__ row_of, const int32_t* __restrict__ ucol, const T* __restrict__ E,
-                       const T* __restrict__ Pm, double* __restrict__ G) {
-  const int I = blockIdx.x / g.ncl, J = blockIdx.x % g.ncl;
-  if (I > J) return;
+                       const T* __restrict__ Pm, double* __restrict__ Gparts) {
+  const int2 ij = cblocks[blockIdx.x];
+  const int I = ij.x, J = ij.y, chunk = blockIdx.y;
   constexpr int NG = GAL_TPB / 8;
   __shared__ double part[NG][2][CM * CM];   // [group][off-diagonal members | diagonal members][r * CM + k]
   const int grp = threadIdx.x >> 3, k = threadIdx.x & 7;
   double acc[CM], accd[CM];
 #pragma unroll
   for (int r = 0; r < CM; ++r) { acc[r] = 0.0; accd[r] = 0.0; }
-  const int beg = coff[I * g.ncl + J], end = coff[I * g.ncl + J + 1];
+  const int b0 = coff[I * g.ncl + J], b1 = coff[I * g.ncl + J + 1];
+  const int beg = b0 + (int)(((long long)(b1 - b0) * chunk) / GAL_SPLIT), end = b0 + (int)(((long long)(b1 - b0) * (chunk + 1)) / GAL_SPLIT);
   if (k < CM) {
     for (int m = beg + grp; m < end; m += NG) {
       const int e = cslot[m], i = row_of[e], j = ucol[e];
       const T* __restrict__ B = E + (size_t)e * (D * D);
       const T* __restrict__ Pi = Pm + (size_t)i * (6 * CM);
       const T* __restrict__ Pj = Pm + (size_t)j * (6 * CM);
-      double t[6];
+      float t[6];
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
-        double s = 0.0;
+        float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) s += (double)B[r * D + c] * (double)Pj[c * CM + k];
+        for (int c = 0; c < 6; ++c) s += (float)B[r * D + c] * (float)Pj[c * CM + k];
         t[r] = s;
       }
       const bool dg = i == j;
 #pragma unroll
       for (int r = 0; r < CM; ++r) {
-        double s = 0.0;
+        float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) s += (double)Pi[c * CM + r] * t[c];
-        if (dg) accd[r] += s; else acc[r] += s;
+        for (int c = 0; c < 6; ++c) s += (float)Pi[c * CM + r] * t[c];
+        if (dg) accd[r] += (double)s; else acc[r] += (double)s;
       }
     }
 #pragma unroll
@@ -147,6 +152,7 @@ coarse_galerkin_kernel(CoarseGeom g, const int32_t* __restrict__ coff, const int
     const int r = threadIdx.x / CM, c = threadIdx.x % CM;
     double x = 0.0, xt = 0.0, xd = 0.0;
     for (int q = 0; q < NG; ++q) { x += part[q][0][r * CM + c]; xt += part[q][0][c * CM + r]; xd += part[q][1][r * CM + c]; }
+    double* G = Gparts + (size_t)chunk * g.ncp * g.ncp;
     if (I == J) {
       G[(size_t)(I * CM + r) * g.ncp + J * CM + c] = x + xt + xd;   // pairs (i, j) and (j, i) of one cluster, diagonal blocks once
     } else {
@@ -154,6 +160,14 @@ coarse_galerkin_kernel(CoarseGeom g, const int32_t* __restrict__ coff, const int
       G[(size_t)(J * CM + c) * g.ncp + I * CM + r] = x + xd;        // mirrored coarse block
     }
   }
+}
+static __global__ void coarse_reduce_parts_kernel(size_t n, const double* __restrict__ parts, double* __restrict__ G) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = 0.0;
+#pragma unroll
+  for (int c = 0; c < GAL_SPLIT; ++c) v += parts[(size_t)c * n + i];
+  G[i] = v;
 }
 
 // A = P^T Hd P - G  (Hd: the damped diagonal blocks S_ii; added once, after the all-reduce of G);
@@ -257,7 +271,9 @@ struct CoarseLevel {
   bool enabled = false;
   CoarseGeom g;
   DeviceBuffer<int32_t> coff, cslot, row_of;
-  DeviceBuffer<double> c0, G, A, ROW, COL, PINV, rc;
+  DeviceBuffer<int2> cblocks;   // non-empty coarse blocks (I <= J)
+  int n_cblocks = 0;
+  DeviceBuffer<double> c0, G, Gparts, A, ROW, COL, PINV, rc;
   DeviceBuffer<T> Pm, Ainv;
   DeviceBuffer<int> fail;
 
@@ -297,8 +313,21 @@ struct CoarseLevel {
     coff.alloc(nk + 1);
     coarse_offsets_kernel<<<div_up(nk + 1, 256), 256, 0, s>>>(keys_s.get(), nnzu, coff.get(), nk);
     ISFM_CUDA(cudaGetLastError());
-    ISFM_CUDA(cudaStreamSynchronize(s));   // temporaries go out of scope
+    {
+      std::vector<int32_t> h_off((size_t)nk + 1);
+      ISFM_CUDA(cudaMemcpyAsync(h_off.data(), coff.get(), h_off.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      ISFM_CUDA(cudaStreamSynchronize(s));   // temporaries go out of scope
+      std::vector<int2> nz;
+      for (int I = 0; I < g.ncl; ++I)
+        for (int J = I; J < g.ncl; ++J)
+          if (h_off[(size_t)I * g.ncl + J + 1] > h_off[(size_t)I * g.ncl + J]) nz.push_back(make_int2(I, J));
+      n_cblocks = (int)nz.size();
+      cblocks.alloc(std::max<size_t>(nz.size(), 1));
+      if (!nz.empty()) ISFM_CUDA(cudaMemcpyAsync(cblocks.get(), nz.data(), nz.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+      ISFM_CUDA(cudaStreamSynchronize(s));
+    }
     const size_t nn = (size_t)g.ncp * g.ncp;
+    Gparts.alloc(nn * GAL_SPLIT);
     c0.alloc((size_t)g.ncl * 3); G.alloc(nn); A.alloc(nn); ROW.alloc((size_t)GJ_B * g.ncp); COL.alloc((size_t)g.ncp * GJ_B);
     PINV.alloc(GJ_B * GJ_B); rc.alloc(g.ncp); Pm.alloc((size_t)n_cam * 6 * CM); Ainv.alloc(nn); fail.alloc(1);
     enabled = true;
@@ -316,8 +345,12 @@ struct CoarseLevel {
   void factor(const T* E, const T* Hd, const SchurPattern& sp, isfm_comm* comm, cudaStream_t s, KernelTimers& kt) {
     if (!enabled) return;
     { TimerScope ts(kt, T_COARSE);
-      ISFM_CUDA(cudaMemsetAsync(G.get(), 0, (size_t)g.ncp * g.ncp * sizeof(double), s));
-      coarse_galerkin_kernel<T, D><<<g.ncl * g.ncl, GAL_TPB, 0, s>>>(g, coff.get(), cslot.get(), row_of.get(), sp.ucol.get(), E, Pm.get(), G.get()); }
+      const size_t nn = (size_t)g.ncp * g.ncp;
+      ISFM_CUDA(cudaMemsetAsync(Gparts.get(), 0, nn * GAL_SPLIT * sizeof(double), s));
+      if (n_cblocks > 0)
+        coarse_galerkin_kernel<T, D><<<dim3(n_cblocks, GAL_SPLIT), GAL_TPB, 0, s>>>(g, cblocks.get(), coff.get(), cslot.get(), row_of.get(),
+                                                                                  sp.ucol.get(), E, Pm.get(), Gparts.get());
+      coarse_reduce_parts_kernel<<<div_up((int64_t)nn, 256), 256, 0, s>>>(nn, Gparts.get(), G.get()); }
     if (comm_world(comm) > 1) {
       TimerScope ts(kt, T_COMM);
       comm_allreduce_sum(comm, G.get(), (size_t)g.ncp * g.ncp, true, s);

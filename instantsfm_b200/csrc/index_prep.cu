@@ -436,7 +436,7 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
       ISFM_CUDA(cudaMemcpyAsync(sp.stages.get(), stg.data(), stg.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
       ISFM_CUDA(cudaMemcpyAsync(sp.unit_stage_ptr.get(), sp.h_unit_stage_ptr.data(), sp.h_unit_stage_ptr.size() * sizeof(int32_t),
                                 cudaMemcpyHostToDevice, s));
-      if (sp.n_stages > 0)
+      if (sp.n_stages > 0 && !getenv("ISFM_PCG_NO_CONTIG"))
         stage_contiguity_kernel<<<div_up(sp.n_stages, TPB), TPB, 0, s>>>(sp.stages.get(), sp.n_stages, sp.ucol.get());
     }
     ISFM_CUDA(cudaStreamSynchronize(s));

@@ -535,6 +535,16 @@ struct BlockPCG {
   DeviceBuffer<double> part_pq, part_a, part_b;
   // persistent kernel (pcg_persistent.cuh): grid size (0 = unavailable), accumulated phase times
   int persist_grid = 0;
+  // Stage stream of the persistent kernel: the stage table of the pattern re-ordered so that warp w
+  // of the grid owns the CONTIGUOUS range [warp_stage_ptr[w], warp_stage_ptr[w + 1]) holding the
+  // units w, w + W, w + 2 W, ... (W warps in the grid).  All warps therefore advance through the
+  // matrix together, as a window of W units (~55 MB) that slides over it -- the DRAM / TLB
+  // locality of a grid of short-lived CTAs launched in order -- instead of W far-apart streams.
+  DeviceBuffer<int4> stream;
+  DeviceBuffer<int32_t> warp_stage_ptr;
+  int64_t stream_lo = -1, stream_hi = -1;
+  int stream_grid = 0;
+  const void* stream_src = nullptr;
   double phase_ms[8] = {0};
   int64_t persist_solves = 0;
   // two-level preconditioner and sparse exchange ranges, set by the owner before solve()
@@ -577,6 +587,7 @@ struct BlockPCG {
     own_valid = false;
     coarse = CoarseRef{};
     ring_valid = false;
+    stream_lo = stream_hi = -1;
     // persistent solve kernel: one CTA per SM, if the device can co-schedule them
     persist_grid = 0;
     if (!getenv("ISFM_NO_PERSISTENT")) {
@@ -595,6 +606,37 @@ struct BlockPCG {
                                    (int)SpmvCfg<T, D>::SMEM));
     if (!h_state) ISFM_CUDA(cudaMallocHost(&h_state, sizeof(PcgState)));
     if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+  }
+
+  // (re)builds the stage stream for the units [unit_lo, unit_hi) and the current grid; no-op when unchanged
+  void build_stream(const SchurPattern& sp, int64_t unit_lo, int64_t unit_hi, cudaStream_t s) {
+    if (stream_lo == unit_lo && stream_hi == unit_hi && stream_grid == persist_grid && stream_src == (const void*)sp.stages.get()) return;
+    const int W = persist_grid * PersistCfg<T, D>::NW;
+    const bool interleave = !getenv("ISFM_PCG_BLOCKED_ORDER");   // A/B: contiguous unit ranges per warp instead
+    std::vector<int4> h_all((size_t)std::max<int64_t>(sp.n_stages, 1));
+    ISFM_CUDA(cudaMemcpyAsync(h_all.data(), sp.stages.get(), (size_t)sp.n_stages * sizeof(int4), cudaMemcpyDeviceToHost, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));
+    std::vector<int4> out;
+    std::vector<int32_t> ptr((size_t)W + 1, 0);
+    const int64_t n_units = unit_hi - unit_lo;
+    out.reserve((size_t)(sp.h_unit_stage_ptr[(size_t)unit_hi] - sp.h_unit_stage_ptr[(size_t)unit_lo]) + 1);
+    for (int w = 0; w < W; ++w) {
+      ptr[(size_t)w] = (int32_t)out.size();
+      if (interleave) {
+        for (int64_t u = unit_lo + w; u < unit_hi; u += W)
+          for (int32_t g = sp.h_unit_stage_ptr[(size_t)u]; g < sp.h_unit_stage_ptr[(size_t)u + 1]; ++g) out.push_back(h_all[(size_t)g]);
+      } else {
+        const int64_t u0 = unit_lo + (int64_t)w * n_units / W, u1 = unit_lo + (int64_t)(w + 1) * n_units / W;
+        for (int64_t u = u0; u < u1; ++u)
+          for (int32_t g = sp.h_unit_stage_ptr[(size_t)u]; g < sp.h_unit_stage_ptr[(size_t)u + 1]; ++g) out.push_back(h_all[(size_t)g]);
+      }
+    }
+    ptr[(size_t)W] = (int32_t)out.size();
+    stream.alloc(std::max<size_t>(out.size(), 1)); warp_stage_ptr.alloc(ptr.size());
+    if (!out.empty()) ISFM_CUDA(cudaMemcpyAsync(stream.get(), out.data(), out.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+    ISFM_CUDA(cudaMemcpyAsync(warp_stage_ptr.get(), ptr.data(), ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    ISFM_CUDA(cudaStreamSynchronize(s));   // the host vectors go out of scope
+    stream_lo = unit_lo; stream_hi = unit_hi; stream_grid = persist_grid; stream_src = (const void*)sp.stages.get();
   }
 
   // split mat-vec set-up: restrict the combine kernel to the deposits of the upper slots [slot_lo, slot_hi)
@@ -647,8 +689,9 @@ struct BlockPCG {
       a.n_cam = n_cam; a.unit_lo = (int)unit_lo; a.unit_hi = (int)unit_hi; a.max_iter = max_iter;
       a.unit_row = sp.chunk_row.get(); a.unit_beg = sp.chunk_beg.get(); a.urow_ptr = sp.urow_ptr.get(); a.ucol = sp.ucol.get();
       a.tpos = sp.tpos.get(); a.dep_beg = dep_beg; a.dep_end = dep_end; a.chunk_ptr = sp.chunk_ptr.get();
-      a.stages = sp.stages.get();
-      a.stage_lo = sp.h_unit_stage_ptr[(size_t)unit_lo]; a.stage_hi = sp.h_unit_stage_ptr[(size_t)unit_hi];
+      build_stream(sp, unit_lo, unit_hi, s);
+      a.stages = stream.get();
+      a.warp_stage_ptr = warp_stage_ptr.get();
       a.E = E; a.Hd = Hd; a.Minv = Minv;
       a.x = x.get(); a.r = r.get(); a.z = z.get(); a.p = p.get(); a.pp = pp.get(); a.q = q.get(); a.y = y.get(); a.yup = yup.get(); a.C = C.get();
       a.part_pq = part_pq.get(); a.part_a = part_a.get(); a.part_b = part_b.get();

@@ -48,8 +48,9 @@ template <typename T>
 struct PcgArgs {
   int n_cam, unit_lo, unit_hi, max_iter;
   const int32_t *unit_row, *unit_beg, *urow_ptr, *ucol, *tpos, *dep_beg, *dep_end, *chunk_ptr;
-  const int4* stages;          // SchurPattern::stages
-  int stage_lo, stage_hi;      // stages of the units [unit_lo, unit_hi)
+  const int4* stages;          // this solve's stage stream (BlockPCG::stream): the stages of the units
+                               // [unit_lo, unit_hi) dealt to the warps of the grid
+  const int32_t* warp_stage_ptr;   // [grid * NW + 1] stage range of every warp
   const T *E, *Hd, *Minv;
   T *x, *r, *z, *p, *pp, *q, *y, *yup, *C;   // pp: p padded to rows of PersistCfg::DP elements
   double *part_pq, *part_a, *part_b;   // [gridDim.x] per-CTA partials of p.q, r.z, r.r
@@ -252,13 +253,9 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
     if (prof) { const unsigned long long t = global_ns(); a.phase_ns[ph] += t - t_prev; t_prev = t; }
   };
 
-  // mat-vec stages of this warp: an equal share of [stage_lo, stage_hi), moved to unit boundaries
-  // (a unit's row partial is produced by exactly one warp)
-  const int n_stages = a.stage_hi - a.stage_lo;
-  const long long wg = (long long)blockIdx.x * NW + w, wtot = (long long)nblk * NW;
-  int wg0 = a.stage_lo + (int)((wg * n_stages) / wtot), wg1 = a.stage_lo + (int)(((wg + 1) * n_stages) / wtot);
-  while (wg0 < a.stage_hi && !(__ldg(a.stages + wg0).z & (1 << 8))) ++wg0;
-  while (wg1 < a.stage_hi && !(__ldg(a.stages + wg1).z & (1 << 8))) ++wg1;
+  // mat-vec stages of this warp (whole units: a unit's row partial is produced by exactly one warp)
+  const int wg = blockIdx.x * NW + w;
+  const int wg0 = __ldg(a.warp_stage_ptr + wg), wg1 = __ldg(a.warp_stage_ptr + wg + 1);
   T* wbuf = smem + (size_t)w * 2 * PC::STG;
 
   // combine phase geometry: the row pairs (b, n - 1 - b) -- equal work on a dense system -- are dealt
