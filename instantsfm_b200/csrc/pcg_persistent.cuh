@@ -142,17 +142,19 @@ __device__ __forceinline__ void spmv_stream(T* buf, int lane, int g0, int g1, co
   if (g0 >= g1) return;
   const int bl = lane / D, r = lane % D;
   auto meta = [&](int g) -> int4 { return g < g1 ? __ldg(a.stages + g) : make_int4(0, 0, 0, 0); };
-  // m.z bit 10: the stage's columns are consecutive (dense rows, banded street rows): column =
-  // first column + block index, no index loads, and the p_j rows form ONE contiguous piece of pp
+  // m.z bit 10: the stage's columns are consecutive (dense rows, banded street rows): no column
+  // loads, and the p_j rows form ONE contiguous piece of pp.  Loaded values are only STORED here
+  // (consumed one iteration later): no load-to-use stall in the stream.
   auto load_idx = [&](const int4& m, int* jj, int* tp) {
     const int nb = m.z & 0xff;
     const bool contig = (m.z & (1 << 10)) != 0;
-    const int jfirst = (contig && nb > 0) ? __ldg(a.ucol + m.y) : 0;
 #pragma unroll
     for (int pass = 0; pass < Cfg::PASSES; ++pass) {
       const int b = pass * GPW + bl;
       const bool on = bl < GPW && b < nb;
-      jj[pass] = on ? (contig ? jfirst + b : __ldg(a.ucol + m.y + b)) : -1;
+      // contiguous stage: every lane keeps the stage's FIRST column in jj[0] (jj[1..] unused)
+      if (pass == 0) jj[0] = contig ? (nb > 0 ? __ldg(a.ucol + m.y) : -1) : (on ? __ldg(a.ucol + m.y + b) : -1);
+      else jj[pass] = (!contig && on) ? __ldg(a.ucol + m.y + b) : -1;
       tp[pass] = on ? __ldg(a.tpos + m.y + b) : -1;
     }
   };
@@ -171,8 +173,7 @@ __device__ __forceinline__ void spmv_stream(T* buf, int lane, int g0, int g1, co
     if (m.z & (1 << 10)) {
       // consecutive columns: nb padded rows of pp in one run -- coalesced 16-byte copies (a few
       // 128-byte lines) instead of nb scattered ones (one L2 transaction each)
-      const int jfirst = __shfl_sync(0xffffffffu, jj[0], 0);   // lane 0 owns block 0 of pass 0
-      const T* psrc = a.pp + (size_t)jfirst * DP;
+      const T* psrc = a.pp + (size_t)jj[0] * DP;
       for (int c = lane; c < nb * PC::NCH; c += 32) cp_async16(dst + PC::POFF + c * VE, psrc + c * VE);
     } else {
 #pragma unroll
@@ -188,16 +189,21 @@ __device__ __forceinline__ void spmv_stream(T* buf, int lane, int g0, int g1, co
   load_idx(m1, j1, t1);
   issue(g0, m0, j0);
   T acc = T(0);
+  T pi[D];
   for (int g = g0; g < g1; ++g) {
-    const int4 m3 = meta(g + 3);
+    const int4 m3 = meta(g + 3);   // descriptor three stages ahead: consumed (load_idx) in the NEXT iteration
     load_idx(m2, j2, t2);
     if (g + 1 < g1) { issue(g + 1, m1, j1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncwarp();
     const T* S = buf + (size_t)((g - g0) & 1) * STG;
-    const T* pi = S + PC::PIOFF;
+    if (m0.z & (1 << 8)) {   // first stage of a unit: a new row, its p_i moves from the stage buffer into registers
+#pragma unroll
+      for (int c = 0; c < D; ++c) pi[c] = S[PC::PIOFF + c];
+    }
+    const int nb0 = m0.z & 0xff;
 #pragma unroll
     for (int pass = 0; pass < Cfg::PASSES; ++pass) {
-      if (j0[pass] >= 0) {
+      if (bl < GPW && pass * GPW + bl < nb0) {
         const T* B = S + (pass * GPW + bl) * DD;
         const T* pj = S + PC::POFF + (pass * GPW + bl) * DP;
         T t = T(0);
