@@ -53,7 +53,7 @@ def emit(line):
 METRIC = "ba_lm_observations_per_sec"
 UNIT = "obs/s"
 CPU_SAMPLE_SCALE = 0.02   # cpu_baseline: config with points/observations scaled by this factor
-C5_STEPS, C5_WARMUP = 5, 2   # fixed so that every rank count repeats the run of profiles/r2_c5_n1.json
+C5_STEPS, C5_WARMUP = 10, 2   # fixed so that every rank count repeats the run of profiles/r2_c5_n1.json
 # dram__bytes_read.sum + dram__bytes_write.sum per launch on config C3 (1 GPU, full size), from the
 # `ncu --set full` captures summarised under profiles/ (ncu cannot run inside the bench).  pcg_solve: per PCG iteration.
 NCU_TRAFFIC_C3 = {"pcg_solve": 535.1e6, "schur_offdiag": 2887.5e6, "linearize": 788.6e6, "camera_blocks": 664.7e6,

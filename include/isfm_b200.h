@@ -59,9 +59,11 @@ typedef struct isfm_step_stats {
   int32_t rejects;
   int32_t pcg_iters;    /* total PCG iterations over all trials                          */
   int32_t accepted;     /* 1 if the final trial was kept                                 */
-  int32_t pcg_status;   /* last trial's PCG: 1 converged, 0 hit pcg_max_iter, 2 breakdown
-                           (non-positive curvature / non-finite: x holds the last good
-                           iterate; bae prints and breaks, bundle_adjustment.py:132)      */
+  int32_t pcg_status;   /* last trial's PCG: 1 converged (true residual b - S x verified
+                           below pcg_tol), 0 hit pcg_max_iter, 2 breakdown (non-positive
+                           curvature / non-finite: x holds the last good iterate; bae
+                           prints and breaks, bundle_adjustment.py:132), 4 the true
+                           residual stagnated above pcg_tol (floating-point floor)        */
   int32_t reserved;
 } isfm_step_stats;
 

@@ -653,8 +653,9 @@ struct BlockPCG {
     if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
   }
 
-  // Solves S x = b.  Returns iterations; result in x.  status: 1 converged, 0 hit max_iter,
-  // 2 breakdown.
+  // Solves S x = b.  Returns iterations; result in x.  status: 1 converged (persistent kernel: the
+  // TRUE residual b - S x, recomputed after the recursive one converged, is below the tolerance),
+  // 0 hit max_iter, 2 breakdown, 4 the true residual stagnated above the tolerance (fp32 floor).
   // unit_lo / unit_hi: the mat-vec work units this rank multiplies (all of them unless the ranks
   // share one block pattern and the summed E has been reduce-scattered by unit ranges; the
   // partials and deposits of the other units are zero, see BASolver::setup_matvec_split)
@@ -692,7 +693,8 @@ struct BlockPCG {
       build_stream(sp, unit_lo, unit_hi, s);
       a.stages = stream.get();
       a.warp_stage_ptr = warp_stage_ptr.get();
-      a.E = E; a.Hd = Hd; a.Minv = Minv;
+      a.E = E; a.Hd = Hd; a.Minv = Minv; a.b = b;
+      a.verify = getenv("ISFM_PCG_NO_VERIFY") ? 0 : 1;
       a.x = x.get(); a.r = r.get(); a.z = z.get(); a.p = p.get(); a.pp = pp.get(); a.q = q.get(); a.y = y.get(); a.yup = yup.get(); a.C = C.get();
       a.part_pq = part_pq.get(); a.part_a = part_a.get(); a.part_b = part_b.get();
       a.st = state.get(); a.tol2 = tol2;

@@ -51,7 +51,8 @@ struct PcgArgs {
   const int4* stages;          // this solve's stage stream (BlockPCG::stream): the stages of the units
                                // [unit_lo, unit_hi) dealt to the warps of the grid
   const int32_t* warp_stage_ptr;   // [grid * NW + 1] stage range of every warp
-  const T *E, *Hd, *Minv;
+  const T *E, *Hd, *Minv, *b;
+  int verify;                  // re-compute the TRUE residual b - S x when the recursive one converged (see kernel)
   T *x, *r, *z, *p, *pp, *q, *y, *yup, *C;   // pp: p padded to rows of PersistCfg::DP elements
   double *part_pq, *part_a, *part_b;   // [gridDim.x] per-CTA partials of p.q, r.z, r.r
   PcgState* st;
@@ -295,7 +296,15 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
   double rr = bb;
   // two-level: the initial z = M^-1 r needs the coarse correction too: one pass of the update /
   // direction phases with alpha = beta = 0 (q is zeroed by the host) before the first mat-vec
-  bool first = coarse;
+  // Pass kinds.  ITER: a PCG iteration.  INIT (two-level only): update / direction phases alone,
+  // alpha = beta = 0.  VERIFY: the recursive residual says "converged" -- in fp32 it keeps
+  // shrinking after the true residual has stagnated -- so the true residual r = b - S x is
+  // recomputed with one more mat-vec (p := x); if it is above the tolerance the solve goes on from
+  // it (restart: p = z, at most two times), else it ends.  The reported residual is a true one.
+  enum { ITER = 0, INIT = 1, VERIFY = 2 };
+  int mode = coarse ? INIT : ITER;
+  int restarts = 0;
+  bool first = mode == INIT;
   if (!first) {   // padded copy of the initial direction (pcg_init_kernel wrote p)
     for (int c0 = cam0; c0 < cam1; c0 += CPB) {
       const int cam = c0 + ucam;
@@ -306,7 +315,7 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
   while (true) {
     double pq_acc = 0.0;
     const int parity = (int)((seq + 1u) & 1u);
-    if (!first) {
+    if (mode != INIT) {
     // ---------------- P1: mat-vec ----------------
     spmv_stream<T, D>(wbuf, lane, wg0, wg1, a, pol_stream, pol_keep, !a.keep_in_l2);
     if (!grid_barrier<false>(st, epoch)) return;
@@ -428,16 +437,17 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
     if (tid == 0) a.part_pq[blockIdx.x] = pq_acc;
     if (!grid_barrier<false>(st, epoch)) return;
     lap(a.peer ? PH_EXCHANGE : PH_COMBINE);
-    }   // !first
+    }   // mode != INIT
 
     // ---------------- P3: update ----------------
     T alpha = T(0);
-    if (!first) {
+    if (mode == ITER) {
       double pq, dummy;
       sum_partials2(a.part_pq, nullptr, nblk, pq, dummy);
       if (!(pq > 0.0) || !isfinite(pq)) { done = 2; break; }   // breakdown: x keeps the last good iterate
       alpha = (T)(rho / pq);
     }
+    const bool verify_pass = mode == VERIFY;
     double rz_acc = 0.0, rr_acc = 0.0;
     double* cw = reinterpret_cast<double*>(pcg_smem);                 // [CPB][8] coarse contributions of one pass
     double* rc_loc = cw + (size_t)CPB * 8;                            // [ncl_cta][8]
@@ -450,13 +460,18 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
       const bool on = ucam < CPB && cam < cam1;
       T rv[D];
       if (on) {
+        if (verify_pass) {   // true residual: q holds S x
 #pragma unroll
-        for (int c = 0; c < D; ++c) { const size_t o = (size_t)cam * D + c; rv[c] = __ldcg(a.r + o) - alpha * __ldcg(a.q + o); }
+          for (int c = 0; c < D; ++c) { const size_t o = (size_t)cam * D + c; rv[c] = __ldg(a.b + o) - __ldcg(a.q + o); }
+        } else {
+#pragma unroll
+          for (int c = 0; c < D; ++c) { const size_t o = (size_t)cam * D + c; rv[c] = __ldcg(a.r + o) - alpha * __ldcg(a.q + o); }
+        }
       }
       __syncthreads();   // every thread of a camera has read the old r before anyone overwrites it
       if (on) {
         const size_t o = (size_t)cam * D + uk;
-        a.x[o] += alpha * __ldcg(a.p + o);
+        if (!verify_pass) a.x[o] += alpha * __ldcg(a.p + o);
         a.r[o] = rv[uk];
         const T* __restrict__ m = a.Minv + (size_t)cam * (D * D) + uk * D;
         T zz = T(0);
@@ -543,15 +558,39 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
     double rho_new;
     sum_partials2(a.part_a, a.part_b, nblk, rho_new, rr);
     T beta = T(0);
-    if (!first) {
+    bool to_verify = false;
+    if (mode == ITER) {
       ++it;
       if (!(isfinite(rho_new) && isfinite(rr))) { done = 2; break; }
-      if (rr < a.tol2 * bb) { done = 1; break; }
-      if (it >= a.max_iter) break;
+      if (rr < a.tol2 * bb) {
+        if (!a.verify) { done = 1; break; }
+        to_verify = true;               // p := x below, then one mat-vec for the true residual
+      } else if (it >= a.max_iter) break;
       beta = (T)(rho_new / rho);
+    } else if (mode == VERIFY) {
+      ++it;   // a verification pass costs one mat-vec: counted as an iteration
+      if (!(isfinite(rho_new) && isfinite(rr))) { done = 2; break; }
+      // rr is the TRUE squared residual now (a small slack: the two residuals differ by rounding)
+      if (rr < 2.25 * a.tol2 * bb || restarts >= 2 || it >= a.max_iter) { done = rr < 2.25 * a.tol2 * bb ? 1 : 4; break; }
+      ++restarts;                        // go on from the true residual: p = z
     } else if (!isfinite(rho_new)) { done = 2; break; }
     first = false;
+    mode = to_verify ? VERIFY : ITER;
     rho = rho_new;
+    if (to_verify) {
+      for (int c0 = cam0; c0 < cam1; c0 += CPB) {
+        const int cam = c0 + ucam;
+        if (ucam < CPB && cam < cam1) {
+          const size_t o = (size_t)cam * D + uk;
+          const T xv = a.x[o];
+          a.p[o] = xv;
+          a.pp[(size_t)cam * PC::DP + uk] = xv;
+        }
+      }
+      if (!grid_barrier<false>(st, epoch)) return;
+      lap(PH_DIRECTION);
+      continue;
+    }
     for (int c0 = cam0; c0 < cam1; c0 += CPB) {
       const int cam = c0 + ucam;
       if (ucam < CPB && cam < cam1) {
