@@ -59,10 +59,11 @@ static __global__ void coarse_offsets_kernel(const uint32_t* __restrict__ sorted
 // ---- per LM step: the prolongation blocks P_i (6 x 7) from the current poses ----
 template <typename T>
 __global__ void coarse_centroid_kernel(CoarseGeom g, int cw, const T* __restrict__ cam, double* __restrict__ c0) {
-  const int cl = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per cluster; lanes stride over its cameras, fixed shuffle tree: deterministic
+  const int cl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (cl >= g.ncl) return;
   double s[3] = {0, 0, 0};
-  for (int i = g.begin(cl); i < g.end(cl); ++i) {
+  for (int i = g.begin(cl) + lane; i < g.end(cl); i += 32) {
     const T* c = cam + (size_t)i * cw;
     double R[9];
     const double q[4] = {(double)c[3], (double)c[4], (double)c[5], (double)c[6]};
@@ -70,8 +71,10 @@ __global__ void coarse_centroid_kernel(CoarseGeom g, int cw, const T* __restrict
     // centre = -R^T t
     for (int k = 0; k < 3; ++k) s[k] -= R[0 * 3 + k] * (double)c[0] + R[1 * 3 + k] * (double)c[1] + R[2 * 3 + k] * (double)c[2];
   }
+  for (int k = 0; k < 3; ++k)
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
   const double inv = 1.0 / (double)(g.end(cl) - g.begin(cl));
-  for (int k = 0; k < 3; ++k) c0[cl * 3 + k] = s[k] * inv;
+  if (lane < 3) c0[cl * 3 + lane] = (lane == 0 ? s[0] : (lane == 1 ? s[1] : s[2])) * inv;
 }
 template <typename T>
 __global__ void coarse_modes_kernel(CoarseGeom g, int cw, const T* __restrict__ cam, const double* __restrict__ c0, T* __restrict__ Pm) {
@@ -172,16 +175,20 @@ static __global__ void coarse_reduce_parts_kernel(size_t n, const double* __rest
 
 // A = P^T Hd P - G  (Hd: the damped diagonal blocks S_ii; added once, after the all-reduce of G);
 // padding rows / columns: identity.  One CTA per coarse row block.
+constexpr int ASM_PARTS = 8;
 template <typename T, int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 coarse_assemble_kernel(CoarseGeom g, const T* __restrict__ Hd, const T* __restrict__ Pm, const double* __restrict__ G, double* __restrict__ A) {
+  __shared__ double Hp[ASM_PARTS][CM * CM];
   __shared__ double H[CM * CM];
   const int I = blockIdx.x;
   if (I < g.ncl) {
-    if (threadIdx.x < CM * CM) {
-      const int r = threadIdx.x / CM, c = threadIdx.x % CM;
+    // H_I = sum_{i in I} P_i^T Hd_i P_i: part p takes the cameras begin + p, begin + p + 8, ...; parts added in order
+    const int part = threadIdx.x / (CM * CM), e = threadIdx.x % (CM * CM);
+    if (part < ASM_PARTS) {
+      const int r = e / CM, c = e % CM;
       double s = 0.0;
-      for (int i = g.begin(I); i < g.end(I); ++i) {
+      for (int i = g.begin(I) + part; i < g.end(I); i += ASM_PARTS) {
         const T* __restrict__ h = Hd + (size_t)i * (D * D);
         const T* __restrict__ P = Pm + (size_t)i * (6 * CM);
         for (int a = 0; a < 6; ++a) {
@@ -190,6 +197,12 @@ coarse_assemble_kernel(CoarseGeom g, const T* __restrict__ Hd, const T* __restri
           s += (double)P[a * CM + r] * t;
         }
       }
+      Hp[part][e] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < CM * CM) {
+      double s = 0.0;
+      for (int q = 0; q < ASM_PARTS; ++q) s += Hp[q][threadIdx.x];
       H[threadIdx.x] = s;
     }
     __syncthreads();
@@ -227,15 +240,14 @@ gj_panel_kernel(int n, int kb, const double* __restrict__ A, double* __restrict_
   __syncthreads();
   // Gauss-Jordan on [M | Inv]
   for (int p = 0; p < GJ_B; ++p) {
+    // read phase (old values) / write phase: two barriers per pivot
     const double piv = M[p][p];
     if (!(piv > 0.0) && threadIdx.x == 0) *fail = 1;
     const double ip = 1.0 / piv;
+    const double mp = M[p][tx] * ip, vp = Inv[p][tx] * ip, f = M[ty][p];
     __syncthreads();
-    if (ty == p) { M[p][tx] *= ip; Inv[p][tx] *= ip; }
-    __syncthreads();
-    const double f = M[ty][p];
-    __syncthreads();
-    if (ty != p) { M[ty][tx] -= f * M[p][tx]; Inv[ty][tx] -= f * Inv[p][tx]; }
+    if (ty == p) { M[p][tx] = mp; Inv[p][tx] = vp; }
+    else { M[ty][tx] -= f * mp; Inv[ty][tx] -= f * vp; }
     __syncthreads();
   }
   double s = 0.0;
@@ -244,21 +256,60 @@ gj_panel_kernel(int n, int kb, const double* __restrict__ A, double* __restrict_
   ROW[(size_t)ty * n + J * GJ_B + tx] = s;
   if (J == K) PINV[ty * GJ_B + tx] = Inv[ty][tx];
 }
-static __global__ void __launch_bounds__(GJ_B * GJ_B)
+// 64 x 64 tile per CTA (2 x 2 pivot-sized blocks), 256 threads, a 4 x 4 micro-tile each; n is a multiple of 32, so
+// edge tiles are guarded per 32-block.
+constexpr int GJ_T = 64;
+static __global__ void __launch_bounds__(256)
 gj_update_kernel(int n, int kb, double* __restrict__ A, const double* __restrict__ ROW, const double* __restrict__ COL,
                  const double* __restrict__ PINV) {
-  __shared__ double Cs[GJ_B][GJ_B + 1], Rs[GJ_B][GJ_B + 1];
-  const int tx = threadIdx.x % GJ_B, ty = threadIdx.x / GJ_B, I = blockIdx.y, J = blockIdx.x, K = kb;
-  double* dst = A + (size_t)(I * GJ_B + ty) * n + J * GJ_B + tx;
-  if (I == K && J == K) { *dst = PINV[ty * GJ_B + tx]; return; }
-  if (I == K) { *dst = ROW[(size_t)ty * n + J * GJ_B + tx]; return; }
-  Cs[ty][tx] = COL[(size_t)(I * GJ_B + ty) * GJ_B + tx];
-  Rs[ty][tx] = J == K ? PINV[ty * GJ_B + tx] : ROW[(size_t)ty * n + J * GJ_B + tx];
+  __shared__ double Cs[GJ_T][GJ_B + 1], Rs[GJ_B][GJ_T + 1];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int i0 = blockIdx.y * GJ_T, j0 = blockIdx.x * GJ_T, K0 = kb * GJ_B;
+  // stage the column panel rows [i0, i0 + 64) and the row panel columns [j0, j0 + 64); inside the pivot
+  // block column the "row panel" is Pinv (A[I,K] <- -COL[I] Pinv), inside the pivot block row nothing is multiplied
+  for (int e = threadIdx.x; e < GJ_T * GJ_B; e += 256) {
+    const int r = e / GJ_B, c = e % GJ_B;
+    Cs[r][c] = i0 + r < n ? COL[(size_t)(i0 + r) * GJ_B + c] : 0.0;
+  }
+  for (int e = threadIdx.x; e < GJ_B * GJ_T; e += 256) {
+    const int r = e / GJ_T, c = e % GJ_T, col = j0 + c;
+    double v = 0.0;
+    if (col < n) v = (col >= K0 && col < K0 + GJ_B) ? PINV[r * GJ_B + (col - K0)] : ROW[(size_t)r * n + col];
+    Rs[r][c] = v;
+  }
   __syncthreads();
-  double s = 0.0;
-#pragma unroll 8
-  for (int c = 0; c < GJ_B; ++c) s += Cs[ty][c] * Rs[c][tx];
-  *dst = J == K ? -s : *dst - s;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 4
+  for (int c = 0; c < GJ_B; ++c) {
+    double cv[4], rv[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) cv[a] = Cs[ty * 4 + a][c];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) rv[b] = Rs[c][tx * 4 + b];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] += cv[a] * rv[b];
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int row = i0 + ty * 4 + a;
+    if (row >= n) continue;
+    const bool prow = row >= K0 && row < K0 + GJ_B;   // pivot block row
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int col = j0 + tx * 4 + b;
+      if (col >= n) continue;
+      const bool pcol = col >= K0 && col < K0 + GJ_B;
+      double* dst = A + (size_t)row * n + col;
+      if (prow) *dst = pcol ? PINV[(row - K0) * GJ_B + (col - K0)] : ROW[(size_t)(row - K0) * n + col];
+      else *dst = pcol ? -acc[a][b] : *dst - acc[a][b];
+    }
+  }
 }
 template <typename T>
 __global__ void coarse_store_kernel(size_t n, const double* __restrict__ A, T* __restrict__ out) {
@@ -288,11 +339,11 @@ struct CoarseLevel {
     const bool sparse_chain = n_cam >= 512 && density < 0.15;
     if (!(env ? atoi(env) != 0 : sparse_chain) || n_cam < 8) return;
     // cluster size: a quarter of the mean upper row length (~ the co-visibility window), at most
-    // ISFM_COARSE_MAX_CLUSTERS clusters (default 160: the dense inverse of the 7 * clusters coarse
+    // ISFM_COARSE_MAX_CLUSTERS clusters (default 148: the dense inverse of the 7 * clusters coarse
     // matrix is replicated on every rank and costs O(clusters^3) per trial)
     int cs = (int)std::max<int64_t>(4, n_off_global / std::max<int64_t>(n_cam, 1) / 4);
     if (const char* e = getenv("ISFM_COARSE_CS")) cs = std::max(2, atoi(e));
-    int max_cl = 160;
+    int max_cl = 148;   // <= SMs of a B200: one cluster per CTA in the update / coarse phases of the persistent kernel
     if (const char* e = getenv("ISFM_COARSE_MAX_CLUSTERS")) max_cl = std::max(1, atoi(e));
     cs = std::max<int>(cs, (int)((n_cam + max_cl - 1) / max_cl));
     cs = (int)std::min<int64_t>(cs, std::max<int64_t>(n_cam / 2, 2));
@@ -337,7 +388,7 @@ struct CoarseLevel {
   void update_modes(const T* cam, int cw, cudaStream_t s, KernelTimers& kt) {
     if (!enabled) return;
     TimerScope ts(kt, T_MISC);
-    coarse_centroid_kernel<T><<<div_up(g.ncl, 128), 128, 0, s>>>(g, cw, cam, c0.get());
+    coarse_centroid_kernel<T><<<div_up(g.ncl, 4), 128, 0, s>>>(g, cw, cam, c0.get());
     coarse_modes_kernel<T><<<div_up(g.n_cam, 128), 128, 0, s>>>(g, cw, cam, c0.get(), Pm.get());
   }
 
@@ -356,12 +407,12 @@ struct CoarseLevel {
       comm_allreduce_sum(comm, G.get(), (size_t)g.ncp * g.ncp, true, s);
     }
     TimerScope ts(kt, T_COARSE);
-    coarse_assemble_kernel<T, D><<<g.ncl + 1, 128, 0, s>>>(g, Hd, Pm.get(), G.get(), A.get());
+    coarse_assemble_kernel<T, D><<<g.ncl + 1, 512, 0, s>>>(g, Hd, Pm.get(), G.get(), A.get());
     ISFM_CUDA(cudaMemsetAsync(fail.get(), 0, sizeof(int), s));
     const int nb = g.ncp / GJ_B;
     for (int k = 0; k < nb; ++k) {
       gj_panel_kernel<<<nb, GJ_B * GJ_B, 0, s>>>(g.ncp, k, A.get(), ROW.get(), COL.get(), PINV.get(), fail.get());
-      gj_update_kernel<<<dim3(nb, nb), GJ_B * GJ_B, 0, s>>>(g.ncp, k, A.get(), ROW.get(), COL.get(), PINV.get());
+      gj_update_kernel<<<dim3(div_up(g.ncp, GJ_T), div_up(g.ncp, GJ_T)), 256, 0, s>>>(g.ncp, k, A.get(), ROW.get(), COL.get(), PINV.get());
     }
     coarse_store_kernel<T><<<div_up((int64_t)g.ncp * g.ncp, 256), 256, 0, s>>>((size_t)g.ncp * g.ncp, A.get(), Ainv.get());
     ISFM_CUDA(cudaGetLastError());

@@ -58,7 +58,10 @@ struct SchurPattern {
   DeviceBuffer<int32_t> unit_stage_ptr; // [n_chunks + 1] first stage of each unit
   std::vector<int32_t> h_unit_stage_ptr;
 };
-constexpr int SPMV_CHUNK = 48;   // slots per mat-vec work unit (one warp); multiple of 4
+#ifndef ISFM_SPMV_CHUNK
+#define ISFM_SPMV_CHUNK 48
+#endif
+constexpr int SPMV_CHUNK = ISFM_SPMV_CHUNK;   // slots per mat-vec work unit; multiple of 4
 
 // cam_idx / pt_idx: device int32 [n_obs] in the caller's order.
 void build_obs_index(ObsIndex& ix, int64_t n_cam, int64_t n_pt, int64_t n_obs, const int32_t* cam_idx,
