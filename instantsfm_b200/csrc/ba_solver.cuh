@@ -76,6 +76,8 @@ struct BASolver : BASolverBase {
   double* h_scalars = nullptr;  // pinned [4]
   BlockPCG<T, D> pcg;
   CoarseLevel<T, D> coarse;   // two-level preconditioner (chain-like camera graphs), see coarse.cuh
+  int coarse_age = -1, coarse_period = 3, iters_at_factor = -1;   // LM steps since the coarse inverse was built; rebuild period
+  bool coarse_refresh = false;
   int cur = 0;
   bool have_loss = false;
   double loss = 0.0;
@@ -106,6 +108,7 @@ struct BASolver : BASolverBase {
     ISFM_CUDA(cudaMallocHost(&h_scalars, 4 * sizeof(double)));
     if (const char* e = getenv("ISFM_MIN_DAMPING")) min_damping = atof(e);
     debug = getenv("ISFM_DEBUG") != nullptr;
+    if (const char* e = getenv("ISFM_COARSE_PERIOD")) coarse_period = std::max(1, atoi(e));
     no_tile_backsub = getenv("ISFM_NO_TILE_BACKSUB") != nullptr;
   }
   ~BASolver() override {
@@ -163,7 +166,7 @@ struct BASolver : BASolverBase {
     scalars.alloc(4); fail.alloc(1); fail.zero(s); red_stage.alloc(3 * RED_SLICES);
     if (desc.optimize_poses) {
       UnionKeys hook(this);
-      build_schur_pattern(sp, ix, s, timers, comm_world(comm) > 1 ? &hook : nullptr, SpmvCfg<T, D>::WB);
+      build_schur_pattern(sp, ix, s, timers, comm_world(comm) > 1 ? &hook : nullptr, SpmvCfg<T, D>::WB, persistent_grid_warps<T, D>());
       mark("build_schur_pattern");
       HCC_GC.alloc((size_t)nc * (D * D + D)); HD.alloc((size_t)nc * D * D);
       E.alloc((size_t)sp.nnzu * D * D); E.zero(s);   // padding slots stay zero
@@ -179,6 +182,7 @@ struct BASolver : BASolverBase {
     }
     ISFM_CUDA(cudaStreamSynchronize(s));
     cur = 0; have_loss = false; has_problem = true;
+    coarse_age = -1; coarse_refresh = false; iters_at_factor = -1;
     tr.init(desc.tr_radius, desc.tr_max, desc.tr_up, desc.tr_down);
   }
 
@@ -217,6 +221,7 @@ struct BASolver : BASolverBase {
       const bool overlap = (double)sum_cnt >= 1.5 * (double)std::max<int64_t>(n_union, 1);
       if (!(env ? atoi(env) != 0 : overlap)) { out.release(); return 0; }
       self->union_pattern = true;
+      matvec_share = world;   // the summed matrix will be split across the ranks
       return max_cnt * world;
     }
   };
@@ -526,12 +531,24 @@ struct BASolver : BASolverBase {
     { TimerScope ts(timers, T_PRECOND);
       precond_kernel<T, D><<<div_up(n_cam, 64), 64, 0, s>>>((int)n_cam, HME.get(), mu, HD.get(), MINV.get(), bvec.get(),
                                                             fail.get()); }
-    coarse.factor(E.get(), HD.get(), sp, comm, s, timers);   // no-op unless the two-level preconditioner is on
+    // Two-level preconditioner: the coarse inverse is LAGGED -- rebuilt on the first trial of every
+    // `coarse_period`-th LM step, or as soon as a solve needed 30 % more iterations than the one right
+    // after the last rebuild.  A stale coarse level only slows PCG down, it never changes the system.
+    // Same decisions on every rank (iteration counts are identical across ranks).
+    if (coarse.enabled && (coarse_age < 0 || coarse_age >= coarse_period || coarse_refresh)) {
+      coarse.factor(E.get(), HD.get(), sp, comm, s, timers);
+      coarse_age = 0; coarse_refresh = false; iters_at_factor = -1;
+    }
     int max_iter = desc.pcg_max_iter > 0 ? desc.pcg_max_iter : (int)std::min<int64_t>(10 * n_cam * D, 5000);
     // split mat-vec: the kernel indexes blocks by their global slot, E_own starts at this rank's first slot
     const T* Emat = split_matvec ? E_own.get() - split_off[comm_rank(comm)] : E.get();
-    return pcg.solve(sp, Emat, HD.get(), MINV.get(),
-                     bvec.get(), desc.pcg_tol, max_iter, comm, s, timers, pcg_status, unit_lo, unit_hi);
+    const int iters = pcg.solve(sp, Emat, HD.get(), MINV.get(),
+                                bvec.get(), desc.pcg_tol, max_iter, comm, s, timers, pcg_status, unit_lo, unit_hi);
+    if (coarse.enabled) {
+      if (iters_at_factor < 0) iters_at_factor = iters;
+      else if (iters > iters_at_factor + iters_at_factor * 3 / 10 + 4) coarse_refresh = true;
+    }
+    return iters;
   }
 
   void step(double* loss_out, isfm_step_stats* st) override {
@@ -554,7 +571,11 @@ struct BASolver : BASolverBase {
     isfm_step_stats stats;
     memset(&stats, 0, sizeof stats);
     stats.loss_before = last;
-    if (desc.optimize_poses) coarse.update_modes(cam[cur].get(), CW, s, timers);   // cluster modes at the current poses
+    if (desc.optimize_poses && coarse.enabled) {
+      if (coarse_age >= 0) ++coarse_age;
+      if (coarse_age < 0 || coarse_age >= coarse_period || coarse_refresh)
+        coarse.update_modes(cam[cur].get(), CW, s, timers);   // cluster modes at the current poses (only when the inverse is rebuilt)
+    }
     double mu = 1.0;
     bool built = false;
     int rejects = 0;

@@ -372,7 +372,7 @@ struct GPSolver : GPSolverBase {
     rays.alloc((size_t)no * 3);
     { TimerScope ts(timers, T_INDEX_PREP);
       gather_rows_kernel<T><<<div_up(no * 3, GP_TPB), GP_TPB, 0, s>>>(no, 3, rays_raw.get(), ix.obs_perm.get(), rays.get()); }
-    build_schur_pattern(sp, ix, s, timers, nullptr, SpmvCfg<T, 3>::WB);
+    build_schur_pattern(sp, ix, s, timers, nullptr, SpmvCfg<T, 3>::WB, persistent_grid_warps<T, 3>());
     A.alloc((size_t)no); JV.alloc((size_t)no * 3); RT.alloc((size_t)no * 3); QW.alloc((size_t)no * 15);
     HINV.alloc((size_t)np * 6); GX.alloc((size_t)np * 3); TP.alloc((size_t)np * 3);
     ACC.alloc((size_t)nc * GP_CAM_ACC); ACCSUM.alloc((size_t)nc * GP_CAM_ACC);

@@ -266,7 +266,7 @@ int64_t count_unique_upper_keys(const uint64_t* keys, int64_t n, int64_t n_cam, 
   return (int64_t)c;
 }
 
-void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, KernelTimers& kt, PatternKeyHook* hook, int stage_blocks) {
+void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, KernelTimers& kt, PatternKeyHook* hook, int stage_blocks, int grid_warps) {
   TimerScope ts(kt, T_INDEX_PREP);
   const int64_t n = ix.n_obs, n_cam = ix.n_cam;
   const int g = div_up(n, TPB);
@@ -405,9 +405,15 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
     sp.n_blocks = sp.nnzu;
     sp.nnzu = nnzp;
     up = upp;
+    int unit = SPMV_CHUNK;
+    if (grid_warps > 0 && !getenv("ISFM_FIXED_UNITS")) {
+      const int64_t slots_per_warp = nnzp / ((int64_t)grid_warps * std::max(hook ? hook->matvec_share : 1, 1));
+      while (unit > 12 && slots_per_warp / unit < 8) unit /= 2;
+    }
+    sp.unit_slots = unit;
     for (int64_t i = 0; i < n_cam; ++i) {
       cptr[i] = (int32_t)crow.size();
-      for (int32_t b = up[i]; b < up[i + 1]; b += SPMV_CHUNK) { crow.push_back((int32_t)i); cbeg.push_back(b); }
+      for (int32_t b = up[i]; b < up[i + 1]; b += unit) { crow.push_back((int32_t)i); cbeg.push_back(b); }
     }
     cptr[n_cam] = (int32_t)crow.size();
     sp.n_chunks = (int64_t)crow.size();
@@ -421,9 +427,9 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
     std::vector<int4> stg;
     sp.h_unit_stage_ptr.assign(crow.size() + 1, 0);
     if (stage_blocks > 0) {
-      stg.reserve(crow.size() * ((SPMV_CHUNK + stage_blocks - 1) / stage_blocks));
+      stg.reserve(crow.size() * ((unit + stage_blocks - 1) / stage_blocks));
       for (size_t u = 0; u < crow.size(); ++u) {
-        const int32_t row = crow[u], beg = cbeg[u], end = std::min<int32_t>(beg + SPMV_CHUNK, up[row + 1]);
+        const int32_t row = crow[u], beg = cbeg[u], end = std::min<int32_t>(beg + unit, up[row + 1]);
         sp.h_unit_stage_ptr[u] = (int32_t)stg.size();
         for (int32_t b = beg; b < end; b += stage_blocks) {
           const int32_t nb = std::min<int32_t>(stage_blocks, end - b);

@@ -8,6 +8,11 @@
 
 namespace isfm {
 
+#ifndef ISFM_SPMV_CHUNK
+#define ISFM_SPMV_CHUNK 48
+#endif
+constexpr int SPMV_CHUNK = ISFM_SPMV_CHUNK;   // largest mat-vec work unit in slots; multiple of 4
+
 struct ObsIndex {
   int64_t n_cam = 0, n_pt = 0, n_obs = 0;
   // point-major order ("sorted position" a = 0..n_obs-1)
@@ -49,6 +54,7 @@ struct SchurPattern {
   DeviceBuffer<int32_t> chunk_beg;   // [n_chunks] first upper slot of the chunk
   DeviceBuffer<int32_t> chunk_ptr;   // [n_cam + 1] first chunk of each row
   std::vector<int32_t> h_chunk_beg;  // host copy of chunk_beg (splitting the units across ranks)
+  int unit_slots = SPMV_CHUNK;       // slots per mat-vec work unit of THIS pattern (<= SPMV_CHUNK, see build_schur_pattern)
   // Stage table of the persistent PCG kernel: every unit cut into stages of <= stage_blocks slots,
   // in unit order; one int4 per stage = {row, first slot, slots | first-of-unit << 8 | last-of-unit << 9, unit}.
   // A warp of that kernel walks a contiguous range of this table as ONE continuous cp.async stream.
@@ -58,10 +64,6 @@ struct SchurPattern {
   DeviceBuffer<int32_t> unit_stage_ptr; // [n_chunks + 1] first stage of each unit
   std::vector<int32_t> h_unit_stage_ptr;
 };
-#ifndef ISFM_SPMV_CHUNK
-#define ISFM_SPMV_CHUNK 48
-#endif
-constexpr int SPMV_CHUNK = ISFM_SPMV_CHUNK;   // slots per mat-vec work unit; multiple of 4
 
 // cam_idx / pt_idx: device int32 [n_obs] in the caller's order.
 void build_obs_index(ObsIndex& ix, int64_t n_cam, int64_t n_pt, int64_t n_obs, const int32_t* cam_idx,
@@ -72,12 +74,16 @@ void build_obs_index(ObsIndex& ix, int64_t n_cam, int64_t n_pt, int64_t n_obs, c
 // that every rank builds the UNION pattern (zero blocks where it has no pairs).
 struct PatternKeyHook {
   virtual ~PatternKeyHook() {}
+  int matvec_share = 1;   // set by extra_keys: ranks that will share the mat-vec of this pattern (union pattern: world)
   virtual int64_t extra_keys(const uint64_t* list_key, int64_t n_lists, int64_t n_cam, DeviceBuffer<uint64_t>& out,
                              cudaStream_t stream) = 0;
 };
-// stage_blocks > 0: also build the stage table (slots per stage of the caller's mat-vec kernel)
+// stage_blocks > 0: also build the stage table (slots per stage of the caller's mat-vec kernel).
+// grid_warps > 0 (warps of the persistent PCG grid): the work unit shrinks from SPMV_CHUNK to 24 or
+// 12 slots until every warp has >= 8 units per mat-vec -- small per-rank shares (8-way strong
+// scaling) are then balanced at stage granularity instead of losing 20 % to the last unit.
 void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t stream, KernelTimers& kt,
-                         PatternKeyHook* hook = nullptr, int stage_blocks = 0);
+                         PatternKeyHook* hook = nullptr, int stage_blocks = 0, int grid_warps = 0);
 // number of distinct valid strictly-upper keys (i < j) in `keys` (device, n entries; sorts a copy)
 int64_t count_unique_upper_keys(const uint64_t* keys, int64_t n, int64_t n_cam, cudaStream_t stream);
 // Two 48-bit order-independent hashes of the upper BSR pattern (row pointers and columns): equal

@@ -85,7 +85,7 @@ template <typename T, int D> struct SpmvCfg {
 // a per-warp double buffer: stage k+1 is in flight while stage k is multiplied.
 template <typename T, int D>
 __global__ void __launch_bounds__(PCG_TPB)
-pcg_spmv_upper_kernel(int n_units, const int32_t* __restrict__ unit_row, const int32_t* __restrict__ unit_beg,
+pcg_spmv_upper_kernel(int n_units, int unit_slots, const int32_t* __restrict__ unit_row, const int32_t* __restrict__ unit_beg,
                       const int32_t* __restrict__ urow_ptr, const int32_t* __restrict__ ucol,
                       const int32_t* __restrict__ tpos, const T* __restrict__ EU, const T* __restrict__ p,
                       T* __restrict__ yup_part, T* __restrict__ C, const PcgState* __restrict__ st) {
@@ -99,7 +99,7 @@ pcg_spmv_upper_kernel(int n_units, const int32_t* __restrict__ unit_row, const i
   T* buf = reinterpret_cast<T*>(spmv_smem) + (size_t)w * 2 * STG;
   const int bl = lane / D, r = lane % D;
   const int row = unit_row[unit];
-  const int beg = unit_beg[unit], end = min(beg + SPMV_CHUNK, urow_ptr[row + 1]);
+  const int beg = unit_beg[unit], end = min(beg + unit_slots, urow_ptr[row + 1]);
   const int ns = (end - beg + WB - 1) / WB;
   T pi[D];
 #pragma unroll
@@ -513,6 +513,17 @@ pcg_direction_kernel(int n_cam, int n_part, double tol2, const double* __restric
 #include "pcg_persistent.cuh"
 namespace isfm {
 
+// warps of the persistent PCG grid on the current device (0: that kernel will not be used)
+template <typename T, int D>
+inline int persistent_grid_warps() {
+  if (getenv("ISFM_NO_PERSISTENT")) return 0;
+  int dev = 0, coop = 0, n_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  return coop ? n_sm * PersistCfg<T, D>::NW : 0;
+}
+
 // deposit positions written by the upper slots [slot_lo, slot_hi): min / max per destination row
 static __global__ void own_deposit_range_kernel(int slot_lo, int slot_hi, const int32_t* __restrict__ ucol,
                                                 const int32_t* __restrict__ tpos, int32_t* beg, int32_t* end) {
@@ -703,7 +714,7 @@ struct BlockPCG {
       a.part_pq = part_pq.get(); a.part_a = part_a.get(); a.part_b = part_b.get();
       a.st = state.get(); a.tol2 = tol2;
       a.cams_per_cta = div_up(n_cam, persist_grid);
-      const int64_t my_slots = n_units > 0 ? (int64_t)std::min<int64_t>((int64_t)n_units * SPMV_CHUNK, sp.nnzu) : 0;
+      const int64_t my_slots = n_units > 0 ? (int64_t)std::min<int64_t>((int64_t)n_units * sp.unit_slots, sp.nnzu) : 0;
       a.keep_in_l2 = (size_t)my_slots * D * D * sizeof(T) <= ((size_t)72 << 20) && !getenv("ISFM_NO_L2_KEEP");
       a.peer = peer ? 1 : 0;
       a.push_grid = big_push ? 1 : 0;
@@ -736,7 +747,7 @@ struct BlockPCG {
       if (n_units > 0) {
         TimerScope ts(kt, T_PCG_SPMV);
         pcg_spmv_upper_kernel<T, D><<<div_up(n_units, SpmvCfg<T, D>::NW), PCG_TPB, SpmvCfg<T, D>::SMEM, s>>>(
-            n_units, sp.chunk_row.get() + unit_lo, sp.chunk_beg.get() + unit_lo, sp.urow_ptr.get(), sp.ucol.get(), sp.tpos.get(), E,
+            n_units, sp.unit_slots, sp.chunk_row.get() + unit_lo, sp.chunk_beg.get() + unit_lo, sp.urow_ptr.get(), sp.ucol.get(), sp.tpos.get(), E,
             p.get(), yup.get() + (size_t)unit_lo * D, C.get(), state.get()); }
       if (!multi) {
         TimerScope ts(kt, T_PCG_VEC);

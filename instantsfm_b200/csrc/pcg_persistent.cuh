@@ -268,7 +268,10 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
   // combine phase geometry: the row pairs (b, n - 1 - b) -- equal work on a dense system -- are dealt
   // to the CTAs in contiguous shares; a CTA with m pairs forms groups of NW / m warps (all its
   // threads work whether it owns 1 pair or 100), one pair per group and round
-  const int n_pairs = (n + 1) / 2;
+  // (multi-rank, local pattern: only the rows of this rank's ring carry anything -- the items are then
+  // those rows, one per group, so that ALL CTAs share them)
+  const bool ring_items = a.peer && a.row_len[me] < n;
+  const int n_pairs = ring_items ? a.row_len[me] : (n + 1) / 2;
   const int pair0 = (int)(((long long)blockIdx.x * n_pairs) / nblk), pair1 = (int)(((long long)(blockIdx.x + 1) * n_pairs) / nblk);
   const int m_pairs = pair1 - pair0;
   const int wpr = m_pairs >= NW ? 1 : NW / max(m_pairs, 1);
@@ -329,14 +332,15 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
         T* sh = smem + (size_t)(round & 1) * (NW * 32 * 2) + (size_t)grp * (gthreads * 2);   // [half][G][D] per group
         int rows[2] = {-1, -1};
         if (item < pair1 && grp < gpc) {
-          rows[0] = (int)item;
-          rows[1] = n - 1 - (int)item;
-          if (rows[1] <= rows[0]) rows[1] = -1;   // middle row of an odd system: once
+          if (ring_items) {
+            rows[0] = a.row_lo[me] + item;
+            if (rows[0] >= n) rows[0] -= n;
+          } else {
+            rows[0] = (int)item;
+            rows[1] = n - 1 - (int)item;
+            if (rows[1] <= rows[0]) rows[1] = -1;   // middle row of an odd system: once
+          }
         }
-        if (a.peer)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            if (rows[h] >= 0 && !in_ring(rows[h], a.row_lo[me], a.row_len[me], n)) rows[h] = -1;   // rows this rank never touches
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int row = rows[h];
