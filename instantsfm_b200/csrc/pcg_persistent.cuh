@@ -271,7 +271,7 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
   // (multi-rank, local pattern: only the rows of this rank's ring carry anything -- the items are then
   // those rows, one per group, so that ALL CTAs share them)
   const bool ring_items = a.peer && a.row_len[me] < n;
-  const int n_pairs = ring_items ? a.row_len[me] : (n + 1) / 2;
+  const int n_pairs = ring_items ? (a.row_len[me] + 1) / 2 : (n + 1) / 2;
   const int pair0 = (int)(((long long)blockIdx.x * n_pairs) / nblk), pair1 = (int)(((long long)(blockIdx.x + 1) * n_pairs) / nblk);
   const int m_pairs = pair1 - pair0;
   const int wpr = m_pairs >= NW ? 1 : NW / max(m_pairs, 1);
@@ -332,9 +332,11 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
         T* sh = smem + (size_t)(round & 1) * (NW * 32 * 2) + (size_t)grp * (gthreads * 2);   // [half][G][D] per group
         int rows[2] = {-1, -1};
         if (item < pair1 && grp < gpc) {
-          if (ring_items) {
-            rows[0] = a.row_lo[me] + item;
+          if (ring_items) {   // two consecutive rows of the ring
+            rows[0] = a.row_lo[me] + 2 * item;
+            rows[1] = 2 * item + 1 < a.row_len[me] ? rows[0] + 1 : -1;
             if (rows[0] >= n) rows[0] -= n;
+            if (rows[1] >= n) rows[1] -= n;
           } else {
             rows[0] = (int)item;
             rows[1] = n - 1 - (int)item;
