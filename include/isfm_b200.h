@@ -292,6 +292,35 @@ int isfm_reprojection_test(int32_t model_id, int64_t n_obs, int64_t n_cam, int64
                            double max_error, double min_depth, uint8_t* pass_out,
                            double* err_out, void* stream);
 
+/* ------------------------------------------------------------------------------------ */
+/* pixel-space camera maps of the scene layer, fp64 like the   */
+/* reference's numpy, ALL eleven camera models of scene/defs.py:101-113.                   */
+/* cam_table [n_cam, ISFM_CAMERA_ROW] doubles per camera, the attributes Camera.set_params */
+/* (scene/defs.py:177-237) derives from `params`:                                          */
+/*   [0] model id, [1] fx, [2] fy, [3] cx, [4] cy, [5..10] k[0..5], [11] p0, [12] p1,      */
+/*   [13] omega, [14] sx0, [15] sx1   (unused entries 0)                                   */
+/* ------------------------------------------------------------------------------------ */
+#define ISFM_CAMERA_ROW 16
+/* FilterTracksByReprojection, instantsfm/processors/track_filter.py:68-114 (called by
+ * filter_points, track_retriangulation.py:200-204): per observation
+ *   p = world2cam[image] [X; 1];  e = || Camera.cam2img(p) - feature ||   (defs.py:371-412)
+ *   valid_out = (p.z > 1e-10) && (e < max_error);   err_out (may be NULL) = e.
+ * world2cam [n_img,4,4], image_cam int32 [n_img] (Image.cam_id), xyz [n_trk,3], features
+ * [n_obs,2] = Image.features[feature_id] of every observation, image_ids / track_idx as in
+ * isfm_filter_observations.                                                               */
+int isfm_filter_reprojection(int64_t n_obs, int64_t n_img, int64_t n_trk, int64_t n_cam,
+                             const double* world2cam, const int32_t* image_cam,
+                             const double* cam_table, const double* xyz, const double* features,
+                             const int32_t* image_ids, const int32_t* track_idx, double max_error,
+                             uint8_t* valid_out, double* err_out, void* stream);
+/* UndistortImages, instantsfm/processors/image_undistortion.py:3-9 (global_mapper.py:98,116,
+ * 121,142): features [n_feat,2] pixels, cam_idx int32 [n_feat] = camera of the feature's image;
+ * features_undist_out [n_feat,3] = [Camera.img2cam(xy), 1] / norm (defs.py:315-369; the
+ * distorted models restate cv2.undistortPoints: 5 fixed-point iterations).                 */
+int isfm_undistort_features(int64_t n_feat, int64_t n_cam, const double* cam_table,
+                            const double* features, const int32_t* cam_idx,
+                            double* features_undist_out, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -85,6 +85,9 @@ SIGNATURES = {
                                        c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "isfm_filter_triangulation_angle": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                                 c_void_p, c_void_p]),
+    "isfm_filter_reprojection": (c_int, [c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
+    "isfm_undistort_features": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

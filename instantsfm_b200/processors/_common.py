@@ -48,3 +48,44 @@ def flatten_observations(tracks, track_ids):
     obs = np.concatenate(obs_list, axis=0).astype(np.int64)
     which = np.repeat(np.arange(len(track_ids), dtype=np.int64), lengths)
     return obs[:, 0], obs[:, 1], which
+
+
+CAMERA_ROW = 16   # ISFM_CAMERA_ROW, include/isfm_b200.h
+# model value -> (focal idx, pp idx, k idx (up to 6), p idx, omega idx, sx idx) into Camera.params:
+# the attributes Camera.set_params derives (scene/defs.py:177-237)
+_PARAM_LAYOUT = {
+    0: ([0, 0], [1, 2], [], [], None, []),
+    1: ([0, 1], [2, 3], [], [], None, []),
+    2: ([0, 0], [1, 2], [3], [], None, []),
+    3: ([0, 0], [1, 2], [3, 4], [], None, []),
+    4: ([0, 1], [2, 3], [4, 5], [6, 7], None, []),
+    5: ([0, 1], [2, 3], [4, 5, 6, 7], [], None, []),
+    6: ([0, 1], [2, 3], [4, 5, 8, 9, 10, 11], [6, 7], None, []),
+    7: ([0, 1], [2, 3], [], [], 4, []),
+    8: ([0, 0], [1, 2], [3], [], None, []),
+    9: ([0, 0], [1, 2], [3, 4], [], None, []),
+    10: ([0, 1], [2, 3], [4, 5, 8, 9], [6, 7], None, [10, 11]),
+}
+
+
+def camera_table(cameras):
+    """[n_cam, CAMERA_ROW] fp64 table of the scene-layer camera maps (isfm_filter_reprojection,
+    isfm_undistort_features): model id, focal lengths, principal point, k[0..5], p, omega, sx."""
+    table = np.zeros((len(cameras), CAMERA_ROW), dtype=np.float64)
+    for i, cam in enumerate(cameras):
+        model = cam.model_id.value if hasattr(cam.model_id, "value") else int(cam.model_id)
+        if model not in _PARAM_LAYOUT:
+            raise NotImplementedError
+        f, pp, k, p, omega, sx = _PARAM_LAYOUT[model]
+        prm = np.asarray(cam.params, dtype=np.float64)
+        table[i, 0] = model
+        table[i, 1:3] = prm[f]
+        table[i, 3:5] = prm[pp]
+        table[i, 5:5 + len(k)] = prm[k]
+        if p:
+            table[i, 11:13] = prm[p]
+        if omega is not None:
+            table[i, 13] = prm[omega]
+        if sx:
+            table[i, 14:16] = prm[sx]
+    return table

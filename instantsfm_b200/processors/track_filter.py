@@ -17,7 +17,7 @@ There is no CPU path: without the CUDA library / a GPU these functions raise.
 import numpy as np
 
 from .. import _lib
-from ._common import concat_features, flatten_observations
+from ._common import camera_table, concat_features, flatten_observations
 
 EPSILON = 1e-10
 _ANGLE, _REPROJ_NORM = 0, 1
@@ -50,6 +50,25 @@ def _observation_mask(mode, images, tracks, threshold):
     return keys, lengths, valid.astype(bool)
 
 
+def _apply_mask_with_lookahead_counter(tracks, keys, lengths, valid):
+    """Drop the rejected observations in place; the counter reproduces the reference's loop
+    (track_filter.py:57-62 and :107-112), which advances ``count`` BEFORE testing
+    ``np.all(valid_mask[count:count + obs_count])`` -- i.e. it looks at the NEXT window."""
+    starts = np.concatenate([[0], np.cumsum(lengths)])
+    invalid_prefix = np.concatenate([[0], np.cumsum(~valid)])
+    n = valid.size
+    counter = 0
+    for i, k in enumerate(keys):
+        lo, hi = int(starts[i]), int(starts[i + 1])
+        if invalid_prefix[hi] != invalid_prefix[lo]:
+            track = tracks[k]
+            track.observations = np.asarray(track.observations)[valid[lo:hi]]
+        w_lo, w_hi = min(hi, n), min(hi + (hi - lo), n)
+        if invalid_prefix[w_hi] != invalid_prefix[w_lo]:
+            counter += 1
+    return counter
+
+
 def FilterTracksByAngle(cameras, images, tracks, max_angle_error):
     """track_filter.py:5-24."""
     thres = np.cos(np.deg2rad(max_angle_error))
@@ -69,19 +88,32 @@ def FilterTracksByAngle(cameras, images, tracks, max_angle_error):
 def FilterTracksByReprojectionNormalized(cameras, images, tracks, max_reprojection_error):
     """track_filter.py:26-66."""
     keys, lengths, valid = _observation_mask(_REPROJ_NORM, images, tracks, max_reprojection_error)
-    starts = np.concatenate([[0], np.cumsum(lengths)])
-    invalid_prefix = np.concatenate([[0], np.cumsum(~valid)])
-    n = valid.size
-    counter = 0
-    for i, k in enumerate(keys):
-        lo, hi = int(starts[i]), int(starts[i + 1])
-        if invalid_prefix[hi] != invalid_prefix[lo]:
-            track = tracks[k]
-            track.observations = np.asarray(track.observations)[valid[lo:hi]]
-        # the reference's counter looks at the NEXT window of the mask (:59-62)
-        w_lo, w_hi = min(hi, n), min(hi + (hi - lo), n)
-        if invalid_prefix[w_hi] != invalid_prefix[w_lo]:
-            counter += 1
+    counter = _apply_mask_with_lookahead_counter(tracks, keys, lengths, valid)
+    print(f'Filtered {counter} / {len(tracks)} tracks by reprojection error')
+    return counter
+
+
+def FilterTracksByReprojection(cameras, images, tracks, max_reprojection_error):
+    """track_filter.py:68-114 (pixel space, through Camera.cam2img; called by filter_points,
+    track_retriangulation.py:200-204).  All eleven camera models, one model per camera.  The
+    returned counter has the same look-ahead quirk as FilterTracksByReprojectionNormalized
+    (:109-112)."""
+    keys, image_id, feature_id, which, lengths = _flatten(images, tracks)
+    n_obs = int(image_id.size)
+    valid = np.zeros(n_obs, dtype=np.uint8)
+    if n_obs:
+        table, offsets = concat_features(images, "features")
+        feats = np.ascontiguousarray(table[offsets[image_id] + feature_id].reshape(-1, 2), dtype=np.float64)
+        world2cam = np.ascontiguousarray(np.stack([np.asarray(img.world2cam, dtype=np.float64) for img in images], 0))
+        image_cam = np.ascontiguousarray([img.cam_id for img in images], dtype=np.int32)
+        cams = camera_table(cameras)
+        xyz = np.ascontiguousarray(np.stack([np.asarray(tracks[k].xyz, dtype=np.float64) for k in keys], 0))
+        ids = np.ascontiguousarray(image_id, dtype=np.int32)
+        tix = np.ascontiguousarray(which, dtype=np.int32)
+        _lib.check(_lib.load().isfm_filter_reprojection(n_obs, len(images), len(keys), len(cameras), _ptr(world2cam), _ptr(image_cam),
+                                                        _ptr(cams), _ptr(xyz), _ptr(feats), _ptr(ids), _ptr(tix),
+                                                        float(max_reprojection_error), _ptr(valid), None, None))
+    counter = _apply_mask_with_lookahead_counter(tracks, keys, lengths, valid.astype(bool))
     print(f'Filtered {counter} / {len(tracks)} tracks by reprojection error')
     return counter
 

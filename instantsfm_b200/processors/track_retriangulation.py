@@ -5,17 +5,19 @@ reprojection test (:81-91) runs as a CUDA kernel in fp64 (include/isfm_b200.h:
 isfm_reprojection_test) with the camera models of the BA path; the per-observation Python loops
 that gather the candidates (:50-57) are one fancy index.
 
-``RetriangulateTracks`` (:215-259) only sequences this function, points-only ``TorchBA.Solve``
-(``optimize_poses=False``) and the track filters, so a maintainer keeps the reference's loop and
-imports the pieces from this package.  ``merge_tracks`` is unused by the reference (:209-211) and
-not provided.  There is no CPU path.
+``filter_points`` (:200-204) and ``RetriangulateTracks`` (:215-259) sequence this function,
+points-only ``TorchBA.Solve`` (``optimize_poses=False``) and the track filters
+(``FilterTracksByReprojection`` in pixel space + ``FilterTracksTriangulationAngle``), all of which
+run through the C ABI.  ``merge_tracks`` is unused by the reference (:209-211: "not used in the
+pipeline") and not provided.  There is no CPU path.
 """
 import numpy as np
 
 from .. import _lib
 from ..geometry import matrices_to_pose7
 from ._common import concat_features
-from .bundle_adjustment import _PP, _model_value
+from .bundle_adjustment import _PP, TorchBA, _model_value
+from .track_filter import FilterTracksByReprojection, FilterTracksTriangulationAngle
 
 EPSILON = 1e-7   # track_retriangulation.py:16
 
@@ -78,3 +80,32 @@ def complete_and_merge_tracks(cameras, images, tracks, tracks_orig, TRIANGULATOR
     num_completed_observations = complete_tracks(cameras, images, tracks, tracks_orig, TRIANGULATOR_OPTIONS)
     print('Number of completed observations:', num_completed_observations)
     return num_completed_observations
+
+
+def filter_points(cameras, images, tracks, TRIANGULATOR_OPTIONS):
+    """track_retriangulation.py:200-204."""
+    num_filtered = FilterTracksByReprojection(cameras, images, tracks, TRIANGULATOR_OPTIONS['filter_max_reproj_error'])
+    num_filtered += FilterTracksTriangulationAngle(cameras, images, tracks, TRIANGULATOR_OPTIONS['filter_min_tri_angle'])
+    return num_filtered
+
+
+def RetriangulateTracks(cameras, images, tracks, tracks_orig, TRIANGULATOR_OPTIONS, BUNDLE_ADJUSTER_OPTIONS, ba_factory=TorchBA):
+    """track_retriangulation.py:215-259: complete the tracks, then up to ``ba_global_max_refinements``
+    rounds of points-only BA -> complete -> filter, until fewer than
+    ``ba_global_max_refinement_change`` of the tracks changed.  Image registration flags are saved
+    and restored around the loop like the reference does (:217,257-258).  ``ba_factory`` (default:
+    this package's TorchBA) builds the solver of each round."""
+    image_registered = [image.is_registered for image in images]
+    complete_and_merge_tracks(cameras, images, tracks, tracks_orig, TRIANGULATOR_OPTIONS)
+    rounds = TRIANGULATOR_OPTIONS['ba_global_max_refinements']
+    for i in range(rounds):
+        print(f'Running bundle adjustment iteration {i+1} / {rounds}')
+        options = dict(BUNDLE_ADJUSTER_OPTIONS)
+        options['optimize_poses'] = False
+        ba_factory().Solve(cameras, images, tracks, options)
+        changed = abs(complete_and_merge_tracks(cameras, images, tracks, tracks_orig, TRIANGULATOR_OPTIONS))
+        changed += filter_points(cameras, images, tracks, TRIANGULATOR_OPTIONS)
+        if changed / len(tracks) < TRIANGULATOR_OPTIONS['ba_global_max_refinement_change']:
+            break
+    for image, flag in zip(images, image_registered):
+        image.is_registered = flag

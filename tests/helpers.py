@@ -64,3 +64,73 @@ def normal_blocks(pb, mu, delta=1.0):
     E, e = schur_contribution(pb, Hpp, gp, Hcp, mu)
     S, rhs = assemble_reduced_system(Hcc, gc, E, e, mu)
     return Hpp, gp, Hcc, gc, S, rhs
+
+
+# ---------------------------------------------------------------------------------------------
+# pixel-space scenes for the scene-layer camera maps (FilterTracksByReprojection, UndistortImages)
+# ---------------------------------------------------------------------------------------------
+PIXEL_MODEL_PARAMS = {   # plausible intrinsics per CameraModelId.value (scene/defs.py:177-237 layouts)
+    0: [1000.0, 640.0, 480.0],
+    1: [1010.0, 990.0, 640.0, 480.0],
+    2: [1000.0, 640.0, 480.0, -0.08],
+    3: [1000.0, 640.0, 480.0, -0.08, 0.015],
+    4: [1010.0, 990.0, 640.0, 480.0, -0.07, 0.02, 1e-3, -8e-4],
+    5: [1010.0, 990.0, 640.0, 480.0, -0.03, 0.01, -2e-3, 5e-4],
+    6: [1010.0, 990.0, 640.0, 480.0, -0.07, 0.02, 1e-3, -8e-4, 3e-3, 0.01, -4e-3, 1e-3],
+    7: [1010.0, 990.0, 640.0, 480.0, 0.35],
+    8: [1000.0, 640.0, 480.0, -0.03],
+    9: [1000.0, 640.0, 480.0, -0.03, 0.008],
+    10: [1010.0, 990.0, 640.0, 480.0, -0.03, 0.01, 1e-3, -8e-4, -2e-3, 5e-4, 2e-3, -1e-3],
+}
+
+
+def make_pixel_scene(models=(3,), n_img=12, n_trk=200, mean_len=4.0, seed=0, outlier_frac=0.15, behind_frac=0.05, noise_px=0.4):
+    """Seeded scene with PIXEL features: one camera per entry of ``models`` (images cycle through
+    them), poses on a ring looking inwards, tracks whose features are the oracle's cam2img of the
+    point plus noise; gross outliers, points behind a camera, a single-view and an empty track.
+    Every image also carries unreferenced random features so that UndistortImages covers the frame.
+    Returns (cameras, images, tracks) of instantsfm_b200.scene.defs types."""
+    from instantsfm_b200.scene.defs import Camera, CameraModelId, Image, Track
+    from oracle.camera_ops import Intrinsics, cam2img
+    rng = np.random.default_rng(seed)
+    cameras = []
+    for ci, m in enumerate(models):
+        p = np.array(PIXEL_MODEL_PARAMS[m]) * (1.0 + 0.01 * rng.normal(size=len(PIXEL_MODEL_PARAMS[m])))
+        cameras.append(Camera(id=ci, model_id=CameraModelId(m), width=1280, height=960, params=[float(x) for x in p]))
+    intr = [Intrinsics(c.model_id.value, c.params) for c in cameras]
+    images = []
+    for i in range(n_img):
+        ang = 2 * np.pi * i / n_img
+        c = np.array([12 * np.cos(ang), 12 * np.sin(ang), rng.normal(0, 0.5)])
+        z = -c / np.linalg.norm(c) + rng.normal(0, 0.05, 3)
+        z /= np.linalg.norm(z)
+        x = np.cross([0, 0, 1.0], z); x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        R = np.stack([x, y, z], 0)
+        w2c = np.eye(4); w2c[:3, :3] = R; w2c[:3, 3] = -R @ c
+        images.append(Image(id=i, cam_id=i % len(cameras), is_registered=True, world2cam=w2c))
+    feats = [[rng.uniform([0, 0], [1280, 960]) for _ in range(5)] for _ in range(n_img)]
+    tracks = {}
+    for t in range(n_trk):
+        X = rng.normal(0, 2.0, 3)
+        k = 0 if t == 7 else (1 if t % 23 == 0 else min(n_img, 2 + rng.geometric(1.0 / max(mean_len - 1.0, 1.0))))
+        ids = rng.choice(n_img, size=k, replace=False)
+        if k and rng.random() < behind_frac:
+            c = images[ids[0]].center()
+            X = c + (c - X) * 0.5
+        obs = []
+        for i in ids:
+            p = images[i].world2cam[:3, :3] @ X + images[i].world2cam[:3, 3]
+            with np.errstate(all="ignore"):
+                px = cam2img(intr[images[i].cam_id], p[None])[0]
+            if not np.all(np.isfinite(px)):
+                px = np.array([640.0, 480.0])
+            px = px + rng.normal(0, noise_px, 2)
+            if rng.random() < outlier_frac:
+                px = px + rng.normal(0, 25.0, 2)
+            obs.append((int(i), len(feats[i])))
+            feats[i].append(px)
+        tracks[500 + 7 * t] = Track(id=500 + 7 * t, xyz=X, observations=np.array(obs, dtype=np.int64).reshape(-1, 2))
+    for i, img in enumerate(images):
+        img.features = np.array(feats[i]).reshape(-1, 2)
+    return cameras, images, tracks

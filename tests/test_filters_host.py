@@ -18,7 +18,11 @@ from instantsfm_b200.synthetic import ba_arrays_to_scene, make_ba_problem, make_
 from oracle import retriangulation as orc_rt
 from oracle.camera_models import reproject
 from oracle.lie import rotate_quat
+from tests.golden.make_camera_ops_golden import FILTER_CASES, UNDISTORT_CASES
 from tests.golden.make_track_filter_golden import CASES
+from tests.helpers import make_pixel_scene
+from tests.test_camera_ops_host import GOLDEN as CAMOPS_GOLDEN
+from tests.test_camera_ops_host import check_filter_golden
 from tests.test_track_filter_host import check_against_golden
 
 EPS = 1e-10
@@ -73,6 +77,44 @@ class FakeLib:
         _arr(out, (n_obs,), np.uint8)[:] = ((e <= max_err) & (z > min_depth)).numpy()
         return 0
 
+    def isfm_filter_reprojection(self, n_obs, n_img, n_trk, n_cam, w2c, image_cam, cams, xyz, feat, ids, tix, thr, out, err, stream):
+        from oracle.camera_ops import Intrinsics, cam2img
+        rows = _arr(cams, (n_cam, 16), np.float64)
+        intr = []
+        for r in rows:   # rebuild Camera.params-independent intrinsics straight from the table row
+            c = Intrinsics.__new__(Intrinsics)
+            c.model, c.f, c.c, c.k, c.p, c.omega, c.sx = int(r[0]), list(r[1:3]), list(r[3:5]), list(r[5:11]), list(r[11:13]), float(r[13]), list(r[14:16])
+            intr.append(c)
+        ids_ = _arr(ids, (n_obs,), np.int32)
+        M = _arr(w2c, (n_img, 4, 4), np.float64)[ids_]
+        X = _arr(xyz, (n_trk, 3), np.float64)[_arr(tix, (n_obs,), np.int32)]
+        f = _arr(feat, (n_obs, 2), np.float64)
+        ic = _arr(image_cam, (n_img,), np.int32)[ids_]
+        p = np.stack([((M[:, r, 0] * X[:, 0] + M[:, r, 1] * X[:, 1]) + M[:, r, 2] * X[:, 2]) + M[:, r, 3] for r in range(3)], 1)
+        keep = np.zeros(n_obs, bool)
+        with np.errstate(all="ignore"):
+            for a in range(n_obs):
+                e = np.linalg.norm(cam2img(intr[ic[a]], p[a:a + 1])[0] - f[a])
+                keep[a] = (p[a, 2] > EPS) and (e < thr)
+        _arr(out, (n_obs,), np.uint8)[:] = keep
+        return 0
+
+    def isfm_undistort_features(self, n_feat, n_cam, cams, feat, cam_idx, out, stream):
+        from oracle.camera_ops import Intrinsics, img2cam
+        rows = _arr(cams, (n_cam, 16), np.float64)
+        f = _arr(feat, (n_feat, 2), np.float64)
+        ci = _arr(cam_idx, (n_feat,), np.int32)
+        o = _arr(out, (n_feat, 3), np.float64)
+        for a in range(n_feat):
+            r = rows[ci[a]]
+            c = Intrinsics.__new__(Intrinsics)
+            c.model, c.f, c.c, c.k, c.p, c.omega, c.sx = int(r[0]), list(r[1:3]), list(r[3:5]), list(r[5:11]), list(r[11:13]), float(r[13]), list(r[14:16])
+            with np.errstate(all="ignore"):
+                uv = img2cam(c, f[a:a + 1])[0]
+                b = np.array([uv[0], uv[1], 1.0])
+                o[a] = b / np.linalg.norm(b)
+        return 0
+
     def isfm_last_error(self):
         return b""
 
@@ -111,3 +153,69 @@ def test_complete_tracks_host_logic_matches_oracle(model_id, fake_lib):
     assert nx == ny and nx > 0
     for tid in x:
         assert np.array_equal(np.asarray(x[tid].observations), np.asarray(y[tid].observations))
+
+
+@pytest.mark.parametrize("case", FILTER_CASES, ids=[c[0] for c in FILTER_CASES])
+def test_filter_reprojection_host_logic_matches_reference_golden(case, fake_lib):
+    """FilterTracksByReprojection drop-in: flattening, camera table, mask bookkeeping, counter quirk."""
+    name, thr, kw = case
+    cameras, images, tracks = make_pixel_scene(**kw)
+    tracks = copy.deepcopy(tracks)
+    with redirect_stdout(io.StringIO()):
+        ret = tf.FilterTracksByReprojection(cameras, images, tracks, thr)
+    check_filter_golden(name, tracks, ret)
+
+
+@pytest.mark.parametrize("case", UNDISTORT_CASES, ids=[c[0] for c in UNDISTORT_CASES])
+def test_undistort_images_host_logic_matches_reference_golden(case, fake_lib, monkeypatch):
+    from instantsfm_b200.processors import image_undistortion as iu
+    name, kw = case
+    cameras, images, _ = make_pixel_scene(**kw)
+    iu.UndistortImages(cameras, images)
+    assert [im.features_undist.shape[0] for im in images] == list(CAMOPS_GOLDEN[name + "/n_feat"])
+    got = np.concatenate([im.features_undist for im in images], 0)
+    want = CAMOPS_GOLDEN[name + "/bearings"]
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.nanmax(np.abs(got - want)) <= 1e-12
+    # one image through undistort_process gives the same rows
+    one = copy.deepcopy(images[3])
+    iu.undistort_process(one, cameras[one.cam_id])
+    assert np.array_equal(one.features_undist, images[3].features_undist, equal_nan=True)
+
+
+def test_camera_table_matches_oracle_rows():
+    from instantsfm_b200.processors._common import camera_table
+    from oracle.camera_ops import Intrinsics
+    cameras, _, _ = make_pixel_scene(models=tuple(range(11)), n_img=11, n_trk=5, seed=2)
+    t = camera_table(cameras)
+    for cam, row in zip(cameras, t):
+        assert np.array_equal(row, Intrinsics(cam.model_id.value, cam.params).row())
+
+
+def test_retriangulate_tracks_sequences_the_reference_loop(fake_lib):
+    """RetriangulateTracks (track_retriangulation.py:215-259) with a recording BA stand-in: points-only
+    options, complete -> BA -> complete -> filter rounds, early exit on a small change, flags restored."""
+    a = make_ba_problem(10, 300, 1500, seed=71, model_id=3)
+    cameras, images, full = ba_arrays_to_scene(a)
+    tracks_orig = {tid: t.observations.copy() for tid, t in full.items()}
+    tracks = {tid: copy.deepcopy(t) for k, (tid, t) in enumerate(full.items()) if k % 5}
+    for t in tracks.values():
+        t.observations = t.observations[:-1] if len(t.observations) > 2 else t.observations
+    images[2].is_registered = False
+    calls = []
+
+    class RecordingBA:
+        def Solve(self, cams, imgs, trks, options):
+            calls.append(dict(options))
+            assert trks is tracks
+
+    topts = {'complete_max_reproj_error': 60.0, 'filter_max_reproj_error': 80.0, 'filter_min_tri_angle': 0.1,
+             'ba_global_max_refinements': 4, 'ba_global_max_refinement_change': 0.0005}
+    bopts = {'optimize_poses': True, 'max_num_iterations': 7}
+    with redirect_stdout(io.StringIO()):
+        tr.RetriangulateTracks(cameras, images, tracks, tracks_orig, topts, bopts, ba_factory=RecordingBA)
+    # the stand-in BA moves nothing, so the second completion changes nothing and the loose filter little -> early exit
+    assert 1 <= len(calls) <= 4 and all(c['optimize_poses'] is False and c['max_num_iterations'] == 7 for c in calls)
+    assert bopts['optimize_poses'] is True                      # caller's dict untouched (:248-249 copies it)
+    assert images[2].is_registered is False and images[1].is_registered is True
+    assert len(tracks) > 200 and sum(len(t.observations) for t in tracks.values()) > 1000
