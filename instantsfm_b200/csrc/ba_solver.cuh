@@ -76,6 +76,7 @@ struct BASolver : BASolverBase {
   double* h_scalars = nullptr;  // pinned [4]
   BlockPCG<T, D> pcg;
   CoarseLevel<T, D> coarse;   // two-level preconditioner (chain-like camera graphs), see coarse.cuh
+  int coarse_fallbacks = 0;   // solves repeated with block-Jacobi alone (see run_schur_and_pcg)
   int coarse_age = -1, coarse_period = 3, iters_at_factor = -1;   // LM steps since the coarse inverse was built; rebuild period
   bool coarse_refresh = false;
   int cur = 0;
@@ -98,7 +99,13 @@ struct BASolver : BASolverBase {
   DeviceBuffer<T> E_own;                      // sum over ranks of this rank's range of E
   bool union_pattern = false;                 // the block pattern is the union over ranks (zero blocks where no local pairs)
   bool debug = false, no_tile_backsub = false;   // environment switches, read once at creation
-  double min_damping = 0.0;   // floor on the LM damping used to build the systems (see DESIGN.md, fp32 conditioning)
+  // Floor on the LM damping used to build the systems (DESIGN.md, fp32 conditioning).  The reduced
+  // system S = damp(Hcc) - E is stored in T: along the seven gauge directions of the scene only the
+  // damping term is left of it, and below ~16 eps_T that term is smaller than the rounding noise of
+  // the stored blocks -- S turns numerically indefinite (PCG breakdown, rejected trials; measured at
+  // C3: 67 rejected trials and a diverged cost within 25 LM steps without the floor, none with it).
+  // The trust region itself (radius, reported damping) is not touched.
+  double min_damping = sizeof(T) == 4 ? 1e-6 : 0.0;
 
   explicit BASolver(const isfm_ba_desc& d) : desc(d) {
     s = static_cast<cudaStream_t>(d.stream);   // never the legacy default stream: isfm_ba_create substitutes an own stream
@@ -542,12 +549,24 @@ struct BASolver : BASolverBase {
     int max_iter = desc.pcg_max_iter > 0 ? desc.pcg_max_iter : (int)std::min<int64_t>(10 * n_cam * D, 5000);
     // split mat-vec: the kernel indexes blocks by their global slot, E_own starts at this rank's first slot
     const T* Emat = split_matvec ? E_own.get() - split_off[comm_rank(comm)] : E.get();
-    const int iters = pcg.solve(sp, Emat, HD.get(), MINV.get(),
-                                bvec.get(), desc.pcg_tol, max_iter, comm, s, timers, pcg_status, unit_lo, unit_hi);
+    int status = 0;
+    int iters = pcg.solve(sp, Emat, HD.get(), MINV.get(), bvec.get(), desc.pcg_tol, max_iter, comm, s, timers, &status, unit_lo, unit_hi);
     if (coarse.enabled) {
-      if (iters_at_factor < 0) iters_at_factor = iters;
+      if (status == 2 || status == 0) {
+        // Safety net: breakdown (r.z <= 0: the coarse inverse lost positive definiteness) or no
+        // convergence with the two-level preconditioner -- solve this system again with block-Jacobi
+        // alone (the kernel ignores the coarse level while its `fail` flag is set) and rebuild the
+        // coarse inverse before the next solve.  Same decision on every rank.
+        const int one = 1;
+        ISFM_CUDA(cudaMemcpyAsync(coarse.fail.get(), &one, sizeof(int), cudaMemcpyHostToDevice, s));
+        ISFM_CUDA(cudaStreamSynchronize(s));
+        coarse_fallbacks++;
+        iters += pcg.solve(sp, Emat, HD.get(), MINV.get(), bvec.get(), desc.pcg_tol, max_iter, comm, s, timers, &status, unit_lo, unit_hi);
+        coarse_refresh = true;
+      } else if (iters_at_factor < 0) iters_at_factor = iters;
       else if (iters > iters_at_factor + iters_at_factor * 3 / 10 + 4) coarse_refresh = true;
     }
+    if (pcg_status) *pcg_status = status;
     return iters;
   }
 

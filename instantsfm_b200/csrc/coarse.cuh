@@ -175,10 +175,17 @@ static __global__ void coarse_reduce_parts_kernel(size_t n, const double* __rest
 
 // A = P^T Hd P - G  (Hd: the damped diagonal blocks S_ii; added once, after the all-reduce of G);
 // padding rows / columns: identity.  One CTA per coarse row block.
+// Ridge: along the seven gauge directions of the whole scene P^T (Hcc - E) P vanishes and only the
+// damping term is left, while G carries the rounding noise of the stored E (eps_T relative): with a
+// late-LM damping of 1e-8 the computed A would be indefinite there.  `ridge` * diag(P^T Hd P) is
+// added to the diagonal (ridge_eps * eps_T): the coarse level then treats those modes as slightly more damped
+// than they are, the preconditioner stays positive definite.  Default 4 eps_T: with the fp32 damping floor of
+// 16 eps_T (ba_solver.cuh) the damping term itself dominates the noise; the ridge is a second line of defence.
 constexpr int ASM_PARTS = 8;
 template <typename T, int D>
 __global__ void __launch_bounds__(512)
-coarse_assemble_kernel(CoarseGeom g, const T* __restrict__ Hd, const T* __restrict__ Pm, const double* __restrict__ G, double* __restrict__ A) {
+coarse_assemble_kernel(CoarseGeom g, const T* __restrict__ Hd, const T* __restrict__ Pm, const double* __restrict__ G, double* __restrict__ A,
+                       double ridge) {
   __shared__ double Hp[ASM_PARTS][CM * CM];
   __shared__ double H[CM * CM];
   const int I = blockIdx.x;
@@ -210,7 +217,7 @@ coarse_assemble_kernel(CoarseGeom g, const T* __restrict__ Hd, const T* __restri
       const int r = idx / g.ncp, col = idx % g.ncp;
       const size_t o = (size_t)(I * CM + r) * g.ncp + col;
       double v = col < g.ncl * CM ? -G[o] : 0.0;
-      if (col / CM == I && col < g.ncl * CM) v += H[r * CM + col % CM];
+      if (col / CM == I && col < g.ncl * CM) v += H[r * CM + col % CM] * (col % CM == r ? 1.0 + ridge : 1.0);
       A[o] = v;
     }
   } else {
@@ -311,12 +318,6 @@ gj_update_kernel(int n, int kb, double* __restrict__ A, const double* __restrict
     }
   }
 }
-template <typename T>
-__global__ void coarse_store_kernel(size_t n, const double* __restrict__ A, T* __restrict__ out) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (T)A[i];
-}
-
 template <typename T, int D>
 struct CoarseLevel {
   bool enabled = false;
@@ -325,23 +326,28 @@ struct CoarseLevel {
   DeviceBuffer<int2> cblocks;   // non-empty coarse blocks (I <= J)
   int n_cblocks = 0;
   DeviceBuffer<double> c0, G, Gparts, A, ROW, COL, PINV, rc;
-  DeviceBuffer<T> Pm, Ainv;
+  DeviceBuffer<T> Pm;
+  DeviceBuffer<double> Ainv;   // fp64: the inverse of a coarse matrix of condition 1e8 rounded to fp32 is no longer positive definite
   DeviceBuffer<int> fail;
+  double ridge_eps = 4.0;   // ridge on the coarse diagonal in units of eps_T (see coarse_assemble_kernel)
 
   // decides whether the coarse level pays (sparse, chain-like camera graph) and builds the slot lists
   // n_off_global: strictly-upper blocks of the whole reduced system (all ranks)
   void setup(const SchurPattern& sp, int64_t n_off_global, int64_t n_cam, cudaStream_t s, KernelTimers& kt) {
     enabled = false;
     if (D < CM) return;
+    if (const char* e = getenv("ISFM_COARSE_RIDGE")) ridge_eps = atof(e);
     const char* env = getenv("ISFM_TWO_LEVEL");   // "0": never, "1": always, unset: by sparsity
     if (env && atoi(env) == 0) return;
-    const double density = (double)n_off_global / std::max(1.0, 0.5 * (double)n_cam * (double)(n_cam - 1));
-    const bool sparse_chain = n_cam >= 512 && density < 0.15;
-    if (!(env ? atoi(env) != 0 : sparse_chain) || n_cam < 8) return;
+    // Default: every system of at least 32 cameras.  On chain-like camera graphs (street scenes) the
+    // coarse level removes the bending modes block-Jacobi needs thousands of iterations for; on dense
+    // BAL-like systems it removes the weakly damped global modes (measured at C3: 31 -> 11 PCG
+    // iterations per LM step for 0.3 ms of coarse set-up per trial).
+    if (!(env ? atoi(env) != 0 : n_cam >= 32) || n_cam < 8) return;
     // cluster size: a quarter of the mean upper row length (~ the co-visibility window), at most
     // ISFM_COARSE_MAX_CLUSTERS clusters (default 148: the dense inverse of the 7 * clusters coarse
     // matrix is replicated on every rank and costs O(clusters^3) per trial)
-    int cs = (int)std::max<int64_t>(4, n_off_global / std::max<int64_t>(n_cam, 1) / 4);
+    int cs = (int)std::max<int64_t>(4, std::min<int64_t>(n_off_global / std::max<int64_t>(n_cam, 1) / 4, n_cam / 16));
     if (const char* e = getenv("ISFM_COARSE_CS")) cs = std::max(2, atoi(e));
     int max_cl = 148;   // <= SMs of a B200: one cluster per CTA in the update / coarse phases of the persistent kernel
     if (const char* e = getenv("ISFM_COARSE_MAX_CLUSTERS")) max_cl = std::max(1, atoi(e));
@@ -407,14 +413,15 @@ struct CoarseLevel {
       comm_allreduce_sum(comm, G.get(), (size_t)g.ncp * g.ncp, true, s);
     }
     TimerScope ts(kt, T_COARSE);
-    coarse_assemble_kernel<T, D><<<g.ncl + 1, 512, 0, s>>>(g, Hd, Pm.get(), G.get(), A.get());
+    coarse_assemble_kernel<T, D><<<g.ncl + 1, 512, 0, s>>>(g, Hd, Pm.get(), G.get(), A.get(),
+                                                          ridge_eps * (sizeof(T) == 4 ? 5.96e-8 : 1.11e-16));
     ISFM_CUDA(cudaMemsetAsync(fail.get(), 0, sizeof(int), s));
     const int nb = g.ncp / GJ_B;
     for (int k = 0; k < nb; ++k) {
       gj_panel_kernel<<<nb, GJ_B * GJ_B, 0, s>>>(g.ncp, k, A.get(), ROW.get(), COL.get(), PINV.get(), fail.get());
       gj_update_kernel<<<dim3(div_up(g.ncp, GJ_T), div_up(g.ncp, GJ_T)), 256, 0, s>>>(g.ncp, k, A.get(), ROW.get(), COL.get(), PINV.get());
     }
-    coarse_store_kernel<T><<<div_up((int64_t)g.ncp * g.ncp, 256), 256, 0, s>>>((size_t)g.ncp * g.ncp, A.get(), Ainv.get());
+    ISFM_CUDA(cudaMemcpyAsync(Ainv.get(), A.get(), (size_t)g.ncp * g.ncp * sizeof(double), cudaMemcpyDeviceToDevice, s));
     ISFM_CUDA(cudaGetLastError());
   }
 };

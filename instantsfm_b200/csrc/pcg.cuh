@@ -559,10 +559,11 @@ struct BlockPCG {
   double phase_ms[8] = {0};
   int64_t persist_solves = 0;
   // two-level preconditioner and sparse exchange ranges, set by the owner before solve()
-  struct CoarseRef { int enabled = 0, cs = 0, ncl = 0, ncp = 0; const T* Pm = nullptr; const T* Ainv = nullptr; double* rc = nullptr; const int* fail = nullptr; } coarse;
+  struct CoarseRef { int enabled = 0, cs = 0, ncl = 0, ncp = 0; const T* Pm = nullptr; const double* Ainv = nullptr; double* rc = nullptr; int* fail = nullptr; } coarse;
   int row_lo[ISFM_MAX_PEERS] = {0}, row_len[ISFM_MAX_PEERS] = {0};
   bool ring_valid = false;
   DeviceBuffer<PcgState> state;
+  DeviceBuffer<double> rc_parts;   // persistent kernel, two-level: [grid][maxov][8]
   PcgState* h_state = nullptr;  // pinned
   // The whole iteration loop of a single-rank solve is ONE graph launch: a conditional WHILE node
   // whose body holds the kernels of one iteration; the last kernel sets the loop condition on the
@@ -725,8 +726,12 @@ struct BlockPCG {
         if (!push_env) a.push_grid = (size_t)row_len[comm_rank(comm)] * D * sizeof(T) > ((size_t)128 << 10);
       }
       a.coarse = coarse.enabled; a.cs = coarse.cs; a.ncl = coarse.ncl; a.ncp = coarse.ncp;
-      a.kcl = coarse.enabled ? div_up(coarse.ncl, persist_grid) : 0;
-      a.Pm = coarse.Pm; a.Ainv = coarse.Ainv; a.rc = coarse.rc; a.coarse_fail = coarse.fail;
+      a.maxov = 0;
+      if (coarse.enabled) {   // most clusters a CTA's camera share can overlap; its partial coarse residuals live in rc_parts
+        a.maxov = (a.cams_per_cta + coarse.cs - 2) / coarse.cs + 1;
+        rc_parts.alloc((size_t)persist_grid * a.maxov * 8);
+      }
+      a.Pm = coarse.Pm; a.Ainv = coarse.Ainv; a.rc = rc_parts.get(); a.coarse_fail = coarse.fail;
       a.phase_ns = &state.get()->phase_ns[0];
       if (coarse.enabled) ISFM_CUDA(cudaMemsetAsync(q.get(), 0, (size_t)n_cam * D * sizeof(T), s));   // alpha = 0 pass reads q
       { TimerScope ts(kt, T_PCG_SPMV);

@@ -20,6 +20,7 @@
 // removes the rigid "bending" modes of long camera chains that make block-Jacobi PCG need
 // thousands of iterations on city-scale street scenes.
 #pragma once
+#include <type_traits>
 
 namespace isfm {
 
@@ -35,9 +36,14 @@ template <typename T, int D> struct PersistCfg {
   static constexpr int POFF = S::NLD * 32 * S::VE;                    // offset of the p_j area inside a stage buffer
   static constexpr int PIOFF = POFF + S::WB * DP;                     // offset of p_i (the stage's own row)
   static constexpr int STG = PIOFF + DP;                              // elements per stage buffer
-  static constexpr size_t PER_WARP = 2 * (size_t)STG * sizeof(T);
+  // Ring depth and warps per CTA: 16 warps with a 3-stage ring where that fits (two stages in flight
+  // per warp while one is multiplied, and 512 threads leave ptxas 128 registers -- at 24 warps the
+  // 80-register cap made it re-materialise every address inside the stream loop), else a 2-stage ring.
+  static constexpr int NW3 = (int)((size_t)222 * 1024 / (3 * (size_t)STG * sizeof(T)));
+  static constexpr int NST = NW3 >= 16 ? 3 : 2;
+  static constexpr size_t PER_WARP = NST * (size_t)STG * sizeof(T);
   static constexpr int NW_RAW = (int)((size_t)222 * 1024 / PER_WARP);
-  static constexpr int NW = NW_RAW >= 24 ? 24 : (NW_RAW >= 16 ? 16 : (NW_RAW >= 12 ? 12 : 8));
+  static constexpr int NW = NW_RAW >= 16 ? 16 : (NW_RAW >= 12 ? 12 : 8);
   static constexpr int NT = NW * 32;
   static constexpr size_t SMEM = (size_t)NW * PER_WARP;
 };
@@ -65,11 +71,11 @@ struct PcgArgs {
   PeerExchange px;
   int row_lo[ISFM_MAX_PEERS], row_len[ISFM_MAX_PEERS];
   // two-level preconditioner (coarse.cuh)
-  int coarse, cs, ncl, ncp, kcl;   // cluster size (cameras; the last cluster also takes the remainder), clusters,
-                                   // padded coarse dimension, clusters per CTA
+  int coarse, cs, ncl, ncp, maxov;   // cluster size (cameras; the last cluster also takes the remainder), clusters,
+                                     // padded coarse dimension, most clusters one CTA's camera share overlaps
   const T* Pm;                // [n_cam][6][PCG_MODES]
-  const T* Ainv;              // [ncp][ncp]
-  double* rc;                 // [ncp]
+  const double* Ainv;         // [ncp][ncp]
+  double* rc;                 // [gridDim.x][maxov][8]: per-CTA partial coarse residuals P^T r of the clusters its cameras overlap
   const int* coarse_fail;     // set by the dense inverse when Ac was not positive definite: block-Jacobi only
   unsigned long long* phase_ns;   // [PH_N] accumulated by CTA 0 (may be NULL)
 };
@@ -128,95 +134,148 @@ __device__ __forceinline__ void sum_partials2(const double* __restrict__ pa, con
   __syncthreads();
 }
 
+// 16-byte shared-memory load of VE consecutive elements (LDS.128)
+__device__ __forceinline__ void lds16(const float* p, float* out) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+__device__ __forceinline__ void lds16(const double* p, double* out) {
+  const double2 v = *reinterpret_cast<const double2*>(p);
+  out[0] = v.x; out[1] = v.y;
+}
+
 // Mat-vec phase of one warp: a contiguous range [g0, g1) of the stage table, walked as ONE
 // continuous cp.async stream (stage g + 1 is in flight while stage g is multiplied; the per-stage
 // descriptors are fetched three, the column / deposit indices two stages ahead).  Unit and row
 // changes happen inside the stream -- the stage's own p_i travels with it into shared memory, the
 // row partial is folded and stored when a stage is flagged last-of-unit -- so a warp never drains
 // its pipeline between work units (the stand-alone kernel, one unit per warp, does).
-template <typename T, int D>
+//
+// Instruction diet (the loop is issue / latency bound, not bandwidth bound: ncu, profiles/):
+//  * the column and deposit indices of a stage are ONE coalesced load each (lane k holds block k's)
+//    and reach the lane that needs them by shuffle -- no per-pass predicated index loads;
+//  * lanes beyond GPW * D shadow the last block lane (same loads, same arithmetic, no stores), full
+//    stages run a branch-free body, only a row's last stage takes the predicated one;
+//  * every shared-memory address is one per-lane base + an immediate; p_j rows are read with 16-byte
+//    loads from their padded rows.
+template <typename T, int D, bool HINT>
 __device__ __forceinline__ void spmv_stream(T* buf, int lane, int g0, int g1, const PcgArgs<T>& a, uint64_t pol_stream,
-                                            uint64_t pol_keep, bool hint) {
+                                            uint64_t pol_keep) {
   typedef SpmvCfg<T, D> Cfg;
   typedef PersistCfg<T, D> PC;
-  constexpr int GPW = Cfg::GPW, DD = D * D, VE = Cfg::VE, NLD = Cfg::NLD, STG = PC::STG, DP = PC::DP;
+  constexpr int GPW = Cfg::GPW, WB = Cfg::WB, PASSES = Cfg::PASSES, DD = D * D, VE = Cfg::VE, NLD = Cfg::NLD, STG = PC::STG, DP = PC::DP,
+                NCH = PC::NCH;
+  constexpr int NIDX = (WB + 31) / 32;             // index registers per lane (WB > 32 only for the 3x3 blocks of GP)
+  constexpr int NPC = (WB * NCH + 31) / 32;        // p_j chunk copies per lane and stage
+  constexpr unsigned FULL = 0xffffffffu;
   if (g0 >= g1) return;
-  const int bl = lane / D, r = lane % D;
+  const int bl_raw = lane / D, r = lane % D;
+  const bool lane_on = bl_raw < GPW;
+  const int bl = lane_on ? bl_raw : GPW - 1;
+  const int o_row = bl * DD + r * D, o_col = bl * DD + r, o_pj = PC::POFF + bl * DP;
   auto meta = [&](int g) -> int4 { return g < g1 ? __ldg(a.stages + g) : make_int4(0, 0, 0, 0); };
-  // m.z bit 10: the stage's columns are consecutive (dense rows, banded street rows): no column
-  // loads, and the p_j rows form ONE contiguous piece of pp.  Loaded values are only STORED here
-  // (consumed one iteration later): no load-to-use stall in the stream.
-  auto load_idx = [&](const int4& m, int* jj, int* tp) {
+  // lane k (+ 32 i) holds the column / deposit position of the stage's block k (+ 32 i)
+  auto load_idx = [&](const int4& m, int* col, int* tp) {
     const int nb = m.z & 0xff;
-    const bool contig = (m.z & (1 << 10)) != 0;
 #pragma unroll
-    for (int pass = 0; pass < Cfg::PASSES; ++pass) {
-      const int b = pass * GPW + bl;
-      const bool on = bl < GPW && b < nb;
-      // contiguous stage: every lane keeps the stage's FIRST column in jj[0] (jj[1..] unused)
-      if (pass == 0) jj[0] = contig ? (nb > 0 ? __ldg(a.ucol + m.y) : -1) : (on ? __ldg(a.ucol + m.y + b) : -1);
-      else jj[pass] = (!contig && on) ? __ldg(a.ucol + m.y + b) : -1;
-      tp[pass] = on ? __ldg(a.tpos + m.y + b) : -1;
+    for (int i = 0; i < NIDX; ++i) {
+      const int k = lane + 32 * i;
+      const bool on = k < nb;
+      col[i] = on ? __ldg(a.ucol + m.y + k) : 0;
+      tp[i] = on ? __ldg(a.tpos + m.y + k) : -1;
     }
   };
-  auto issue = [&](int g, const int4& m, const int* jj) {
-    const int nb = m.z & 0xff;
-    const int last = nb * DD / VE - 1;   // indices past the end re-copy the last vector
-    const T* src = a.E + (size_t)m.y * DD;
-    T* dst = buf + (size_t)((g - g0) & 1) * STG;
-    if (hint) {
+  auto pick = [&](const int* v, int blk) -> int {   // v of block blk, from the lane that holds it
+    int x = __shfl_sync(FULL, v[0], blk & 31);
 #pragma unroll
-      for (int q = 0; q < NLD; ++q) cp_async16_hint(dst + (size_t)(lane + 32 * q) * VE, src + (size_t)min(lane + 32 * q, last) * VE, pol_stream);
-    } else {
-#pragma unroll
-      for (int q = 0; q < NLD; ++q) cp_async16(dst + (size_t)(lane + 32 * q) * VE, src + (size_t)min(lane + 32 * q, last) * VE);
-    }
-    if (m.z & (1 << 10)) {
-      // consecutive columns: nb padded rows of pp in one run -- coalesced 16-byte copies (a few
-      // 128-byte lines) instead of nb scattered ones (one L2 transaction each)
-      const T* psrc = a.pp + (size_t)jj[0] * DP;
-      for (int c = lane; c < nb * PC::NCH; c += 32) cp_async16(dst + PC::POFF + c * VE, psrc + c * VE);
-    } else {
-#pragma unroll
-      for (int pass = 0; pass < Cfg::PASSES; ++pass)
-        if (jj[pass] >= 0 && r < PC::NCH) cp_async16(dst + PC::POFF + (pass * GPW + bl) * DP + r * VE, a.pp + (size_t)jj[pass] * DP + r * VE);
-    }
-    if (lane < PC::NCH) cp_async16(dst + PC::PIOFF + lane * VE, a.pp + (size_t)m.x * DP + lane * VE);
-    cp_async_commit();
+    for (int i = 1; i < NIDX; ++i) { const int y = __shfl_sync(FULL, v[i], blk & 31); if (blk >= 32 * i) x = y; }
+    return x;
   };
-  int4 m0 = meta(g0), m1 = meta(g0 + 1), m2 = meta(g0 + 2);
-  int j0[Cfg::PASSES], t0[Cfg::PASSES], j1[Cfg::PASSES], t1[Cfg::PASSES], j2[Cfg::PASSES], t2[Cfg::PASSES];
-  load_idx(m0, j0, t0);
-  load_idx(m1, j1, t1);
-  issue(g0, m0, j0);
-  T acc = T(0);
-  T pi[D];
-  for (int g = g0; g < g1; ++g) {
-    const int4 m3 = meta(g + 3);   // descriptor three stages ahead: consumed (load_idx) in the NEXT iteration
-    load_idx(m2, j2, t2);
-    if (g + 1 < g1) { issue(g + 1, m1, j1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncwarp();
-    const T* S = buf + (size_t)((g - g0) & 1) * STG;
-    if (m0.z & (1 << 8)) {   // first stage of a unit: a new row, its p_i moves from the stage buffer into registers
+  auto issue = [&](T* dst, const int4& m, const int* col) {
+    const int nb = m.z & 0xff;
+    const int nv = nb * DD / VE;                   // rows are padded to multiples of 4 slots: exact
+    const T* src = a.E + (size_t)m.y * DD + (size_t)lane * VE;
+    T* d = dst + lane * VE;
 #pragma unroll
-      for (int c = 0; c < D; ++c) pi[c] = S[PC::PIOFF + c];
-    }
-    const int nb0 = m0.z & 0xff;
-#pragma unroll
-    for (int pass = 0; pass < Cfg::PASSES; ++pass) {
-      if (bl < GPW && pass * GPW + bl < nb0) {
-        const T* B = S + (pass * GPW + bl) * DD;
-        const T* pj = S + PC::POFF + (pass * GPW + bl) * DP;
-        T t = T(0);
-#pragma unroll
-        for (int c = 0; c < D; ++c) { acc += B[r * D + c] * pj[c]; t += B[c * D + r] * pi[c]; }
-        if (t0[pass] >= 0) st_global_hint(a.C + (size_t)t0[pass] * D + r, t, pol_keep);
+    for (int q = 0; q < NLD; ++q) {
+      if (lane + 32 * q < nv) {
+        if (HINT) cp_async16_hint(d + q * 32 * VE, src + q * 32 * VE, pol_stream);
+        else cp_async16(d + q * 32 * VE, src + q * 32 * VE);
       }
     }
+    // p_j: chunk c of the stage = 16-byte piece (c % NCH) of the padded row of block c / NCH's column;
+    // consecutive columns (dense rows, banded street rows) make these a few full 128-byte lines
+#pragma unroll
+    for (int k = 0; k < NPC; ++k) {
+      const int c = lane + 32 * k, blk = c / NCH, ch = c - blk * NCH;
+      const int j = pick(col, blk);
+      if (c < nb * NCH) cp_async16(dst + PC::POFF + c * VE, a.pp + (size_t)j * DP + ch * VE);
+    }
+    if (lane < NCH) cp_async16(dst + PC::PIOFF + lane * VE, a.pp + (size_t)m.x * DP + lane * VE);
+    cp_async_commit();
+  };
+  // ring of NST stage buffers: stages g + 1 .. g + NST - 1 are in flight while stage g is multiplied;
+  // descriptors are fetched NST + 1, indices NST stages ahead
+  constexpr int NST = PC::NST;
+  int4 m0 = meta(g0), m1 = meta(g0 + 1), m2 = meta(g0 + 2), m3 = NST == 3 ? meta(g0 + 3) : make_int4(0, 0, 0, 0);
+  int c0[NIDX], t0[NIDX], c1[NIDX], t1[NIDX], c2[NIDX], t2[NIDX], c3[NIDX], t3[NIDX];
+  load_idx(m0, c0, t0);
+  load_idx(m1, c1, t1);
+  issue(buf, m0, c0);
+  if (NST == 3) {
+    load_idx(m2, c2, t2);
+    if (g0 + 1 < g1) issue(buf + STG, m1, c1);
+  }
+  T acc = T(0);
+  T pi[D];
+  int par = 0, nxt = NST - 1;   // ring slots of the stage being multiplied / being issued
+  for (int g = g0; g < g1; ++g) {
+    const int4 mn = meta(g + NST + 1);   // consumed (load_idx) in the NEXT iteration
+    if (NST == 3) {
+      load_idx(m3, c3, t3);
+      if (g + 2 < g1) { issue(buf + nxt * STG, m2, c2); cp_async_wait<2>(); }
+      else if (g + 1 < g1) cp_async_wait<1>();
+      else cp_async_wait<0>();
+    } else {
+      load_idx(m2, c2, t2);
+      if (g + 1 < g1) { issue(buf + nxt * STG, m1, c1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    }
+    __syncwarp();
+    const T* S = buf + par * STG;
+    if (m0.z & (1 << 8)) {   // first stage of a unit: a new row, its p_i moves from the stage buffer into registers
+      T v[NCH * VE];
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) lds16(S + PC::PIOFF + k * VE, v + k * VE);
+#pragma unroll
+      for (int c = 0; c < D; ++c) pi[c] = v[c];
+    }
+    const int nb0 = m0.z & 0xff;
+    auto body = [&](auto full_tag) {
+      constexpr bool FULLSTAGE = decltype(full_tag)::value;
+#pragma unroll
+      for (int pass = 0; pass < PASSES; ++pass) {
+        const int blk = pass * GPW + bl;
+        const int tp = pick(t0, blk);
+        const bool on = FULLSTAGE ? (PASSES * GPW == WB || blk < WB) : blk < nb0;
+        if (on) {
+          const T* Br = S + o_row + pass * GPW * DD;
+          const T* Bc = S + o_col + pass * GPW * DD;
+          T pj[NCH * VE];
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) lds16(S + o_pj + pass * GPW * DP + k * VE, pj + k * VE);
+          T t = T(0);
+#pragma unroll
+          for (int c = 0; c < D; ++c) { acc += Br[c] * pj[c]; t += Bc[c * D] * pi[c]; }
+          if (lane_on && tp >= 0) st_global_hint(a.C + (size_t)tp * D + r, t, pol_keep);   // diagonal / padding slots: no deposit
+        }
+      }
+    };
+    if (nb0 == WB) body(std::true_type{}); else body(std::false_type{});
     if (m0.z & (1 << 9)) {   // last stage of its unit: fold the GPW block lanes onto lanes 0..D-1, store the unit's row partial
+      if (!lane_on) acc = T(0);
 #pragma unroll
       for (int k = 1; k < GPW; ++k) {
-        T o = __shfl_sync(0xffffffffu, acc, (lane + k * D) & 31);
+        T o = __shfl_sync(FULL, acc, (lane + k * D) & 31);
         if (lane < D) acc += o;
       }
       if (lane < D) st_global_hint(a.yup + (size_t)m0.w * D + lane, acc, pol_keep);
@@ -224,8 +283,14 @@ __device__ __forceinline__ void spmv_stream(T* buf, int lane, int g0, int g1, co
     }
     __syncwarp();
 #pragma unroll
-    for (int pass = 0; pass < Cfg::PASSES; ++pass) { j0[pass] = j1[pass]; t0[pass] = t1[pass]; j1[pass] = j2[pass]; t1[pass] = t2[pass]; }
-    m0 = m1; m1 = m2; m2 = m3;
+    for (int i = 0; i < NIDX; ++i) {
+      c0[i] = c1[i]; t0[i] = t1[i]; c1[i] = c2[i]; t1[i] = t2[i];
+      if (NST == 3) { c2[i] = c3[i]; t2[i] = t3[i]; }
+    }
+    m0 = m1; m1 = m2;
+    if (NST == 3) { m2 = m3; m3 = mn; } else { m2 = mn; }
+    par = par == NST - 1 ? 0 : par + 1;
+    nxt = nxt == NST - 1 ? 0 : nxt + 1;
   }
 }
 
@@ -263,7 +328,7 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
   // mat-vec stages of this warp (whole units: a unit's row partial is produced by exactly one warp)
   const int wg = blockIdx.x * NW + w;
   const int wg0 = __ldg(a.warp_stage_ptr + wg), wg1 = __ldg(a.warp_stage_ptr + wg + 1);
-  T* wbuf = smem + (size_t)w * 2 * PC::STG;
+  T* wbuf = smem + (size_t)w * PC::NST * PC::STG;
 
   // combine phase geometry: the row pairs (b, n - 1 - b) -- equal work on a dense system -- are dealt
   // to the CTAs in contiguous shares; a CTA with m pairs forms groups of NW / m warps (all its
@@ -280,19 +345,15 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
   const int gg = gt / D, gc = gt % D;
   constexpr int MLP = 16;
 
-  // cameras of the update / direction phases: an even share, or -- two-level -- whole clusters
+  // cameras of the update / direction phases: an even share of the cameras per CTA.  Two-level: the
+  // share overlaps the clusters [cl_lo, cl_lo + nov); the CTA publishes ITS part of their coarse
+  // residuals, every CTA sums the parts in CTA order (same numbers everywhere, no atomics).
   constexpr int CPB = NT / D;
   const bool coarse = a.coarse && *a.coarse_fail == 0;
-  int cam0, cam1, ncl_cta = 0, first_cl = 0;
-  if (a.coarse) {
-    first_cl = blockIdx.x * a.kcl;
-    ncl_cta = max(0, min(a.kcl, a.ncl - first_cl));
-    cam0 = ncl_cta ? first_cl * a.cs : n;
-    cam1 = ncl_cta ? (first_cl + ncl_cta == a.ncl ? n : (first_cl + ncl_cta) * a.cs) : n;
-  } else {
-    cam0 = min(n, blockIdx.x * a.cams_per_cta);
-    cam1 = min(n, cam0 + a.cams_per_cta);
-  }
+  const int cam0 = min(n, blockIdx.x * a.cams_per_cta), cam1 = min(n, cam0 + a.cams_per_cta);
+  auto cluster_of = [&](int cam) { return min(cam / a.cs, a.ncl - 1); };
+  int cl_lo = 0, nov = 0;
+  if (a.coarse && cam0 < cam1) { cl_lo = cluster_of(cam0); nov = cluster_of(cam1 - 1) - cl_lo + 1; }
   const int ucam = tid / D, uk = tid % D;
 
   int done = 0, it = 0;
@@ -320,7 +381,8 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
     const int parity = (int)((seq + 1u) & 1u);
     if (mode != INIT) {
     // ---------------- P1: mat-vec ----------------
-    spmv_stream<T, D>(wbuf, lane, wg0, wg1, a, pol_stream, pol_keep, !a.keep_in_l2);
+    if (a.keep_in_l2) spmv_stream<T, D, false>(wbuf, lane, wg0, wg1, a, pol_stream, pol_keep);
+    else spmv_stream<T, D, true>(wbuf, lane, wg0, wg1, a, pol_stream, pol_keep);
     if (!grid_barrier<false>(st, epoch)) return;
     lap(PH_SPMV);
 
@@ -456,9 +518,9 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
     const bool verify_pass = mode == VERIFY;
     double rz_acc = 0.0, rr_acc = 0.0;
     double* cw = reinterpret_cast<double*>(pcg_smem);                 // [CPB][8] coarse contributions of one pass
-    double* rc_loc = cw + (size_t)CPB * 8;                            // [ncl_cta][8]
+    double* rc_loc = cw + (size_t)CPB * 8;                            // [nov][8]
     if (coarse) {
-      for (int i = tid; i < ncl_cta * 8; i += NT) rc_loc[i] = 0.0;
+      for (int i = tid; i < nov * 8; i += NT) rc_loc[i] = 0.0;
       __syncthreads();
     }
     for (int c0 = cam0; c0 < cam1; c0 += CPB) {
@@ -497,36 +559,50 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
       }
       if (coarse) {
         __syncthreads();
-        if (tid < ncl_cta * PCG_MODES) {
-          const int cl = tid / PCG_MODES, k = tid % PCG_MODES;
-          const int b0 = max(cam0 + cl * a.cs, c0), b1 = min(cl == ncl_cta - 1 ? cam1 : cam0 + (cl + 1) * a.cs, c0 + CPB);
-          double s = rc_loc[cl * 8 + k];
+        if (tid < nov * PCG_MODES) {
+          const int slot = tid / PCG_MODES, k = tid % PCG_MODES, cl = cl_lo + slot;
+          const int b0 = max(cl * a.cs, c0), b1 = min(min(cl == a.ncl - 1 ? n : (cl + 1) * a.cs, c0 + CPB), cam1);
+          double s = rc_loc[slot * 8 + k];
           for (int cc = b0; cc < b1; ++cc) s += cw[(cc - c0) * 8 + k];
-          rc_loc[cl * 8 + k] = s;
+          rc_loc[slot * 8 + k] = s;
         }
         __syncthreads();
       }
     }
     if (coarse) {
-      if (tid < ncl_cta * PCG_MODES) {
-        const int cl = tid / PCG_MODES, k = tid % PCG_MODES;
-        a.rc[(first_cl + cl) * PCG_MODES + k] = rc_loc[cl * 8 + k];
+      if (tid < nov * PCG_MODES) {
+        const int slot = tid / PCG_MODES, k = tid % PCG_MODES;
+        a.rc[((size_t)blockIdx.x * a.maxov + slot) * 8 + k] = rc_loc[slot * 8 + k];
       }
       rr_acc = block_sum(rr_acc);
       if (tid == 0) a.part_b[blockIdx.x] = rr_acc;
       if (!grid_barrier<false>(st, epoch)) return;
       lap(PH_UPDATE);
-      // zc = rows of Ac^-1 of the own clusters times rc; then z += P zc
-      double* zc = reinterpret_cast<double*>(pcg_smem);   // [ncl_cta][8]
-      for (int rowi = w; rowi < ncl_cta * PCG_MODES; rowi += NW) {
-        const int cl = rowi / PCG_MODES, k = rowi % PCG_MODES;
-        double s = 0.0;
-        {
-          const T* __restrict__ arow = a.Ainv + (size_t)((first_cl + cl) * PCG_MODES + k) * a.ncp;
-          for (int j = lane; j < a.ncl * PCG_MODES; j += 32) s += (double)__ldg(arow + j) * __ldcg(a.rc + j);
+      // the whole coarse residual, summed from the CTAs' parts in CTA order; then zc = rows of Ac^-1
+      // of the clusters this CTA's cameras overlap times rc; then z += P zc
+      double* rcs = reinterpret_cast<double*>(pcg_smem);          // [ncl * PCG_MODES]
+      double* zc = rcs + (size_t)a.ncl * PCG_MODES;               // [nov][8]
+      for (int idx = tid; idx < a.ncl * PCG_MODES; idx += NT) {
+        const int cl = idx / PCG_MODES, k = idx - cl * PCG_MODES;
+        const int c_lo = cl * a.cs, c_hi = cl == a.ncl - 1 ? n : (cl + 1) * a.cs;
+        const int b_lo = c_lo / a.cams_per_cta, b_hi = (c_hi - 1) / a.cams_per_cta;
+        double sum = 0.0;
+        for (int bb2 = b_lo; bb2 <= b_hi; ++bb2) {
+          const int slot = cl - cluster_of(bb2 * a.cams_per_cta);
+          sum += __ldcg(a.rc + ((size_t)bb2 * a.maxov + slot) * 8 + k);
         }
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) zc[cl * 8 + k] = s;
+        rcs[idx] = sum;
+      }
+      __syncthreads();
+      for (int rowi = w; rowi < nov * PCG_MODES; rowi += NW) {
+        const int slot = rowi / PCG_MODES, k = rowi % PCG_MODES;
+        double sum = 0.0;
+        {
+          const double* __restrict__ arow = a.Ainv + (size_t)((cl_lo + slot) * PCG_MODES + k) * a.ncp;
+          for (int j = lane; j < a.ncl * PCG_MODES; j += 32) sum += __ldg(arow + j) * rcs[j];
+        }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) zc[slot * 8 + k] = sum;
       }
       __syncthreads();
       rz_acc = 0.0;
@@ -536,18 +612,18 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
           const size_t o = (size_t)cam * D + uk;
           T zz = a.z[o];
           if (uk < 6) {
-            const double* zcl = zc + min((cam - cam0) / a.cs, ncl_cta - 1) * 8;
+            const double* zcl = zc + (cluster_of(cam) - cl_lo) * 8;
             const T* __restrict__ pm = a.Pm + (size_t)cam * (6 * PCG_MODES) + uk * PCG_MODES;
-            double s = 0.0;
+            double sum = 0.0;
 #pragma unroll
-            for (int mm = 0; mm < PCG_MODES; ++mm) s += (double)pm[mm] * zcl[mm];
-            zz += (T)s;
+            for (int mm = 0; mm < PCG_MODES; ++mm) sum += (double)pm[mm] * zcl[mm];
+            zz += (T)sum;
             a.z[o] = zz;
           }
           rz_acc += (double)zz * (double)a.r[o];
         }
       }
-      __syncthreads();   // zc (shared memory) is dead before block_sum / the next phase reuse it
+      __syncthreads();   // rcs / zc (shared memory) are dead before block_sum / the next phase reuse it
       rz_acc = block_sum(rz_acc);
       if (tid == 0) a.part_a[blockIdx.x] = rz_acc;
       if (!grid_barrier<false>(st, epoch)) return;
@@ -567,7 +643,7 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
     bool to_verify = false;
     if (mode == ITER) {
       ++it;
-      if (!(isfinite(rho_new) && isfinite(rr))) { done = 2; break; }
+      if (!(isfinite(rho_new) && isfinite(rr)) || (!(rho_new > 0.0) && rr > 0.0)) { done = 2; break; }   // r.z <= 0: preconditioner not SPD
       if (rr < a.tol2 * bb) {
         if (!a.verify) { done = 1; break; }
         to_verify = true;               // p := x below, then one mat-vec for the true residual

@@ -134,3 +134,38 @@ def make_pixel_scene(models=(3,), n_img=12, n_trk=200, mean_len=4.0, seed=0, out
     for i, img in enumerate(images):
         img.features = np.array(feats[i]).reshape(-1, 2)
     return cameras, images, tracks
+
+
+# ---------------------------------------------------------------------------------------------
+# gauge alignment
+# ---------------------------------------------------------------------------------------------
+def gauge_align(cam, pts, pts_ref, sample=None):
+    """Bundle adjustment determines the scene up to a similarity transform of the world (7 gauge
+    freedoms): the cost, the residuals and the RMSE do not see it, and the damped LM step pins it only
+    through eigenvalues of the size of the damping (1e-4 here), so two solvers whose linear solves
+    agree to 1e-6 in the residual still drift apart ALONG the gauge by orders of magnitude more than
+    across it.  Poses / points are therefore compared after the least-squares similarity
+    X -> s R X + t (Umeyama) that maps this solution's points onto the reference's; the cameras
+    [t, q_xyzw, intrinsics] follow: R_c -> R_c R^T, t_c -> s t_c - R_c R^T t (projection unchanged).
+    ``sample``: indices of ``pts`` that correspond to ``pts_ref`` (default: all).  Returns
+    (cam_aligned, pts_aligned, (s, R, t))."""
+    from scipy.spatial.transform import Rotation
+    cam = np.asarray(cam, np.float64); pts = np.asarray(pts, np.float64); ref = np.asarray(pts_ref, np.float64)
+    src = pts if sample is None else pts[sample]
+    mu_s, mu_r = src.mean(0), ref.mean(0)
+    A, B = src - mu_s, ref - mu_r
+    U, S, Vt = np.linalg.svd(B.T @ A / len(src))
+    d = np.sign(np.linalg.det(U @ Vt))
+    Dm = np.diag([1.0, 1.0, d])
+    R = U @ Dm @ Vt
+    s = float((S * np.diag(Dm)).sum() / (A * A).sum() * len(src))
+    t = mu_r - s * R @ mu_s
+    pts_al = s * pts @ R.T + t
+    cam_al = cam.copy()
+    Rc = Rotation.from_quat(cam[:, 3:7]).as_matrix()
+    Rn = Rc @ R.T
+    cam_al[:, :3] = s * cam[:, :3] - np.einsum("nij,j->ni", Rn, t)
+    q = Rotation.from_matrix(Rn).as_quat()
+    flip = np.sign(np.einsum("ni,ni->n", q, cam[:, 3:7]))
+    cam_al[:, 3:7] = q * np.where(flip == 0, 1.0, flip)[:, None]
+    return cam_al, pts_al, (s, R, t)

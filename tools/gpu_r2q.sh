@@ -1,0 +1,19 @@
+#!/bin/bash
+# balanced coarse update phase: tests; cluster-size sweep on dense C3 / C2 / C1; C5 N=1
+OUT=gpurun_out/${1:-r2q}; mkdir -p "$OUT"
+timeout 900 python -m pytest tests/test_baseline_configs_gpu.py tests/test_ba_gpu.py tests/test_processors_gpu.py -q --timeout 600 > "$OUT/pytest.log" 2>&1; echo "pytest exit $?"; grep -E "^(FAILED|E  )" "$OUT/pytest.log" | head; tail -2 "$OUT/pytest.log"
+run() { env $2 timeout 600 python bench.py $3 --no-cpu --quick > "$OUT/$1.json" 2> "$OUT/$1.err"; echo "$1 exit $?"; }
+for c in 444 222 111 55 28 12; do run c3_cs$c "ISFM_TWO_LEVEL=1 ISFM_COARSE_CS=$c" "--steps 10 --warmup 3"; done
+for c in 215 107 54 27; do run c2_cs$c "ISFM_TWO_LEVEL=1 ISFM_COARSE_CS=$c" "--config C2 --steps 10 --warmup 3"; done
+for c in 32 16 8 4; do run c1_cs$c "ISFM_TWO_LEVEL=1 ISFM_COARSE_CS=$c" "--config C1 --steps 10 --warmup 3"; done
+run c1 "X=1" "--config C1 --steps 10 --warmup 3"
+run c5_n1 "X=1" "--config C5 --steps 10 --warmup 2"
+python - "$OUT" <<'P'
+import json, sys, os, glob
+for f in sorted(glob.glob(os.path.join(sys.argv[1], "*.json"))):
+    try:
+        d = json.load(open(f)); w = d["work"]
+        print(os.path.basename(f), "ms/step %.3f its/step %.1f us/it %.1f" % (d["ms_per_step"], w["pcg_iters_per_step"], w["us_per_pcg_iter"]), {k: round(v, 1) for k, v in w["pcg_phase_us_per_iter"].items()}, {k: round(v["ms_per_step"], 3) for k, v in d["kernels"].items() if k in ("pcg_solve", "coarse", "misc")}, d["final_robust_cost"], d["rejects"], d["pcg_iters"])
+    except Exception as e:
+        print(f, "no line", e)
+P
