@@ -591,8 +591,9 @@ struct BlockPCG {
     size_t len = (size_t)n * D;
     x.alloc(len); r.alloc(len); z.alloc(len); p.alloc(len); q.alloc(len); y.alloc(len);
     pp.alloc((size_t)n * PersistCfg<T, D>::DP); pp.zero(s);
-    yup.alloc((size_t)std::max<int64_t>(n_chunks, 1) * D);
-    C.alloc((size_t)std::max<int64_t>(n_off, 1) * D);
+    // + 16 bytes: the combine phase copies whole 16-byte vectors and may read past a run's last entry
+    yup.alloc((size_t)std::max<int64_t>(n_chunks, 1) * D + 16 / sizeof(T));
+    C.alloc((size_t)std::max<int64_t>(n_off, 1) * D + 16 / sizeof(T));
     const size_t n_part = (size_t)std::max(n, 1024);   // >= any grid of the persistent kernel
     part_pq.alloc(n_part); part_a.alloc(n_part); part_b.alloc(n_part);
     state.alloc(1);
@@ -732,6 +733,9 @@ struct BlockPCG {
         rc_parts.alloc((size_t)persist_grid * a.maxov * 8);
       }
       a.Pm = coarse.Pm; a.Ainv = coarse.Ainv; a.rc = rc_parts.get(); a.coarse_fail = coarse.fail;
+      const size_t upd_smem = (size_t)a.cams_per_cta * (2 * D * sizeof(T) + 64) + 16 + ((size_t)a.ncl * PCG_MODES + (size_t)a.maxov * 8) * 8;
+      const size_t persist_smem = PersistCfg<T, D>::SMEM;
+      ISFM_REQUIRE(upd_smem <= persist_smem, ISFM_EINVAL, "persistent PCG kernel: camera share per CTA exceeds shared memory");
       a.phase_ns = &state.get()->phase_ns[0];
       if (coarse.enabled) ISFM_CUDA(cudaMemsetAsync(q.get(), 0, (size_t)n_cam * D * sizeof(T), s));   // alpha = 0 pass reads q
       { TimerScope ts(kt, T_PCG_SPMV);

@@ -330,20 +330,29 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
   const int wg0 = __ldg(a.warp_stage_ptr + wg), wg1 = __ldg(a.warp_stage_ptr + wg + 1);
   T* wbuf = smem + (size_t)w * PC::NST * PC::STG;
 
-  // combine phase geometry: the row pairs (b, n - 1 - b) -- equal work on a dense system -- are dealt
-  // to the CTAs in contiguous shares; a CTA with m pairs forms groups of NW / m warps (all its
-  // threads work whether it owns 1 pair or 100), one pair per group and round
-  // (multi-rank, local pattern: only the rows of this rank's ring carry anything -- the items are then
-  // those rows, one per group, so that ALL CTAs share them)
+  // combine phase geometry.  Virtual row sequence of NR rows: single rank / shared pattern -- row(i) =
+  // i / 2 for even i, n - 1 - i / 2 for odd i (a short and a long lower-triangle row side by side:
+  // equal work per pair on a dense system); multi-rank with a local pattern -- only the rows of this
+  // rank's ring carry anything: row(i) = (row_lo + i) mod n.  CTAs take contiguous shares of whole
+  // pairs; inside a CTA one warp streams one row at a time (see P2).
   const bool ring_items = a.peer && a.row_len[me] < n;
-  const int n_pairs = ring_items ? (a.row_len[me] + 1) / 2 : (n + 1) / 2;
-  const int pair0 = (int)(((long long)blockIdx.x * n_pairs) / nblk), pair1 = (int)(((long long)(blockIdx.x + 1) * n_pairs) / nblk);
-  const int m_pairs = pair1 - pair0;
-  const int wpr = m_pairs >= NW ? 1 : NW / max(m_pairs, 1);
-  const int gthreads = 32 * wpr, G = gthreads / D;
-  const int grp = w / wpr, gpc = NW / wpr, gt = tid - grp * gthreads;   // group in CTA, groups per CTA, thread in group
-  const int gg = gt / D, gc = gt % D;
-  constexpr int MLP = 16;
+  const int NR = ring_items ? a.row_len[me] : n;
+  const int n_pairs = (NR + 1) / 2;
+  const int ri0 = min(NR, 2 * (int)(((long long)blockIdx.x * n_pairs) / nblk)), ri1 = min(NR, 2 * (int)(((long long)(blockIdx.x + 1) * n_pairs) / nblk));
+  auto row_at = [&](int i) -> int {
+    if (ring_items) { const int rr2 = a.row_lo[me] + i; return rr2 >= n ? rr2 - n : rr2; }
+    return (i & 1) ? n - 1 - (i >> 1) : (i >> 1);
+  };
+  // shared memory of the combine phase: row table and row sums of a batch of RBC rows, then NCB chunk
+  // buffers per warp
+  constexpr int RBC = 256, VEc = 16 / (int)sizeof(T), G = 32 / D;
+  constexpr size_t CHEAD = ((size_t)RBC * 5 * sizeof(int) + (size_t)RBC * D * sizeof(T) + 15) / 16 * 16;
+  constexpr int NCB = 2;                                                              // chunk buffers per warp (measured: 2 large beat 4 small)
+  constexpr int BUFE = (int)((PC::SMEM - CHEAD) / NW / NCB / sizeof(T)) / VEc * VEc;  // elements per chunk buffer
+  constexpr int CHD = (BUFE - VEc) / D;                                               // D-element entries per chunk (room for the alignment skew)
+  int* rowtab = reinterpret_cast<int*>(pcg_smem);
+  T* ysm = reinterpret_cast<T*>(pcg_smem + (size_t)RBC * 5 * sizeof(int));
+  T* cbuf = reinterpret_cast<T*>(pcg_smem + CHEAD) + (size_t)w * NCB * BUFE;
 
   // cameras of the update / direction phases: an even share of the cameras per CTA.  Two-level: the
   // share overlaps the clusters [cl_lo, cl_lo + nov); the CTA publishes ITS part of their coarse
@@ -387,67 +396,116 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
     lap(PH_SPMV);
 
     // ---------------- P2: combine ----------------
-    {
-      int round = 0;
-      for (int item0 = pair0; item0 < pair1; item0 += gpc, ++round) {
-        const int item = item0 + grp;
-        T* sh = smem + (size_t)(round & 1) * (NW * 32 * 2) + (size_t)grp * (gthreads * 2);   // [half][G][D] per group
-        int rows[2] = {-1, -1};
-        if (item < pair1 && grp < gpc) {
-          if (ring_items) {   // two consecutive rows of the ring
-            rows[0] = a.row_lo[me] + 2 * item;
-            rows[1] = 2 * item + 1 < a.row_len[me] ? rows[0] + 1 : -1;
-            if (rows[0] >= n) rows[0] -= n;
-            if (rows[1] >= n) rows[1] -= n;
-          } else {
-            rows[0] = (int)item;
-            rows[1] = n - 1 - (int)item;
-            if (rows[1] <= rows[0]) rows[1] = -1;   // middle row of an odd system: once
-          }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int row = rows[h];
-          if (row >= 0 && gg < G) {
-            T acc = T(0);
-            const int ke = min(__ldg(a.chunk_ptr + row + 1), a.unit_hi);
-            for (int k = max(__ldg(a.chunk_ptr + row), a.unit_lo) + gg; k < ke; k += G) acc += __ldcg(a.yup + (size_t)k * D + gc);
-            const int end = __ldg(a.dep_end + row);
-            int k = __ldg(a.dep_beg + row) + gg;
-            T v[MLP];
-#pragma unroll
-            for (int u = 0; u < MLP; ++u) v[u] = T(0);
-            for (; k + (MLP - 1) * G < end; k += MLP * G) {
-#pragma unroll
-              for (int u = 0; u < MLP; ++u) v[u] += __ldcg(a.C + (size_t)(k + u * G) * D + gc);
+    // y_row = sum of the row's deposits (one contiguous run of C) + the unit partials of the row (one
+    // contiguous run of yup).  Both runs are D-element entries and stream through the warp's two
+    // chunk buffers with 16-byte cp.async (the next chunk -- of this row or the warp's next row -- is
+    // in flight while the current one is summed): one L2 round trip per 6 KB instead of one per batch
+    // of 4-byte loads.  Row sums land in shared memory; q = Hd p - y (or the push to the peers)
+    // follows for the whole batch with every thread busy.
+    for (int rb0 = ri0; rb0 < ri1; rb0 += RBC) {
+      const int nbr = min(RBC, ri1 - rb0);
+      __syncthreads();   // previous batch finished with the row table / sums
+      for (int j = tid; j < nbr; j += NT) {
+        const int row = row_at(rb0 + j);
+        rowtab[5 * j] = row;
+        rowtab[5 * j + 1] = __ldg(a.dep_beg + row);
+        rowtab[5 * j + 2] = __ldg(a.dep_end + row);
+        rowtab[5 * j + 3] = max(__ldg(a.chunk_ptr + row), a.unit_lo);
+        rowtab[5 * j + 4] = min(__ldg(a.chunk_ptr + row + 1), a.unit_hi);
+      }
+      for (int idx = tid; idx < nbr * D; idx += NT) ysm[idx] = T(0);
+      __syncthreads();
+      {
+        // cursor over the chunks of this warp's rows j = w, w + NW, ...: (row slot, run, entry range)
+        int j = w, run = 0, k = 0, ke = 0;
+        bool open = false;
+        auto next = [&](int& cj, int& crun, int& ck0, int& ck1) -> bool {
+          while (true) {
+            if (!open) {
+              if (j >= nbr) return false;
+              k = rowtab[5 * j + 1 + 2 * run]; ke = rowtab[5 * j + 2 + 2 * run]; open = true;
             }
-            for (; k < end; k += G) v[0] += __ldcg(a.C + (size_t)k * D + gc);
-#pragma unroll
-            for (int u = 1; u < MLP; ++u) v[0] += v[u];
-            sh[(h * G + gg) * D + gc] = acc + v[0];
+            if (k < ke) { cj = j; crun = run; ck0 = k; ck1 = min(k + CHD, ke); k = ck1; return true; }
+            open = false;
+            if (run == 0) run = 1; else { run = 0; j += NW; }
           }
-        }
-        __syncthreads();
-        if (gt < 2 * D) {
-          const int h = gt / D, c = gt % D, row = rows[h];
-          if (row >= 0) {
-            T y = T(0);
-            for (int k = 0; k < G; ++k) y += sh[(h * G + k) * D + c];
-            if (!a.peer) {
-              const T* __restrict__ hd = a.Hd + (size_t)row * (D * D) + c * D;
-              const T* __restrict__ pi = a.p + (size_t)row * D;
-              T qv = T(0);
+        };
+        // one commit group per call, empty when there is no chunk: the wait count below stays constant
+        auto issue = [&](T* dst, bool valid, int crun, int ck0, int ck1) {
+          if (valid) {
+            const T* base = crun ? a.yup : a.C;
+            const size_t e0 = (size_t)ck0 * D, a0 = e0 / VEc * VEc;
+            const int nvec = (int)(((size_t)ck1 * D + VEc - 1) / VEc - a0 / VEc);   // may read < 16 bytes past the run: the arrays are padded
+            const T* src = base + a0;
+            for (int v = lane; v < nvec; v += 32) cp_async16(dst + v * VEc, src + (size_t)v * VEc);
+          }
+          cp_async_commit();
+        };
+        const int lg = lane / D, lc = lane % D;
+        // descriptors of the chunks in flight: [0] is consumed next
+        int qj[NCB - 1], qrun[NCB - 1], qk0[NCB - 1], qk1[NCB - 1];
+        bool qv[NCB - 1];
 #pragma unroll
-              for (int k = 0; k < D; ++k) qv += hd[k] * __ldcg(pi + k);
-              qv -= y;
-              a.q[(size_t)row * D + c] = qv;
-              pq_acc += (double)qv * (double)__ldcg(pi + c);
-            } else if (a.push_grid) {
-              a.y[(size_t)row * D + c] = y;
-            } else {
-              for (int dst = 0; dst < world; ++dst) peer_slot<T>(a.px, dst, parity, me)[(size_t)row * D + c] = y;
+        for (int i = 0; i < NCB - 1; ++i) {
+          qj[i] = qrun[i] = qk0[i] = qk1[i] = 0;
+          qv[i] = next(qj[i], qrun[i], qk0[i], qk1[i]);
+          issue(cbuf + i * BUFE, qv[i], qrun[i], qk0[i], qk1[i]);
+        }
+        int pb = 0, acc_j = -1;
+        T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
+        auto flush = [&]() {
+          T v = (acc0 + acc1) + (acc2 + acc3);
+          if (lg >= G) v = T(0);
+#pragma unroll
+          for (int g2 = 1; g2 < G; ++g2) { const T o = __shfl_sync(0xffffffffu, v, (lane + g2 * D) & 31); if (lane < D) v += o; }
+          if (lane < D && acc_j >= 0) ysm[acc_j * D + lane] = v;
+          acc0 = acc1 = acc2 = acc3 = T(0);
+        };
+        while (qv[0]) {
+          int nj = 0, nrun = 0, nk0 = 0, nk1 = 0;
+          const bool hn = next(nj, nrun, nk0, nk1);
+          const int pin = pb == 0 ? NCB - 1 : pb - 1;   // the buffer consumed in the previous round
+          issue(cbuf + pin * BUFE, hn, nrun, nk0, nk1);
+          cp_async_wait<NCB - 1>();
+          __syncwarp();
+          if (qj[0] != acc_j) { flush(); acc_j = qj[0]; }
+          {
+            const T* src = cbuf + pb * BUFE + (int)(((size_t)qk0[0] * D) % VEc) + lc;
+            const int m = qk1[0] - qk0[0];
+            if (lg < G) {
+              int d = lg;
+              for (; d + 3 * G < m; d += 4 * G) {
+                acc0 += src[d * D]; acc1 += src[(d + G) * D]; acc2 += src[(d + 2 * G) * D]; acc3 += src[(d + 3 * G) * D];
+              }
+              for (; d < m; d += G) acc0 += src[d * D];
             }
           }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i + 1 < NCB - 1; ++i) { qj[i] = qj[i + 1]; qrun[i] = qrun[i + 1]; qk0[i] = qk0[i + 1]; qk1[i] = qk1[i + 1]; qv[i] = qv[i + 1]; }
+          qj[NCB - 2] = nj; qrun[NCB - 2] = nrun; qk0[NCB - 2] = nk0; qk1[NCB - 2] = nk1; qv[NCB - 2] = hn;
+          pb = pb == NCB - 1 ? 0 : pb + 1;
+        }
+        cp_async_wait<0>();
+        flush();
+      }
+      __syncthreads();
+      for (int idx = tid; idx < nbr * D; idx += NT) {
+        const int jj = idx / D, c = idx - jj * D, row = rowtab[5 * jj];
+        const T y = ysm[idx];
+        if (!a.peer) {
+          const T* __restrict__ hd = a.Hd + (size_t)row * (D * D) + c * D;
+          const T* __restrict__ pi = a.p + (size_t)row * D;
+          T qv = T(0);
+#pragma unroll
+          for (int k2 = 0; k2 < D; ++k2) qv += hd[k2] * __ldcg(pi + k2);
+          qv -= y;
+          a.q[(size_t)row * D + c] = qv;
+          pq_acc += (double)qv * (double)__ldcg(pi + c);
+        } else if (a.push_grid) {
+          a.y[(size_t)row * D + c] = y;
+        } else {
+          for (int dst = 0; dst < world; ++dst) peer_slot<T>(a.px, dst, parity, me)[(size_t)row * D + c] = y;
         }
       }
     }
@@ -517,62 +575,61 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
     }
     const bool verify_pass = mode == VERIFY;
     double rz_acc = 0.0, rr_acc = 0.0;
-    double* cw = reinterpret_cast<double*>(pcg_smem);                 // [CPB][8] coarse contributions of one pass
-    double* rc_loc = cw + (size_t)CPB * 8;                            // [nov][8]
-    if (coarse) {
-      for (int i = tid; i < nov * 8; i += NT) rc_loc[i] = 0.0;
-      __syncthreads();
-    }
-    for (int c0 = cam0; c0 < cam1; c0 += CPB) {
-      const int cam = c0 + ucam;
-      const bool on = ucam < CPB && cam < cam1;
-      T rv[D];
-      if (on) {
-        if (verify_pass) {   // true residual: q holds S x
-#pragma unroll
-          for (int c = 0; c < D; ++c) { const size_t o = (size_t)cam * D + c; rv[c] = __ldg(a.b + o) - __ldcg(a.q + o); }
-        } else {
-#pragma unroll
-          for (int c = 0; c < D; ++c) { const size_t o = (size_t)cam * D + c; rv[c] = __ldcg(a.r + o) - alpha * __ldcg(a.q + o); }
-        }
+    // Shared memory of the update / coarse / direction phases (the stage buffers are idle): the new
+    // residual and z of the CTA's cameras, their coarse contributions, the coarse residual and the
+    // coarse solution of the overlapped clusters.  Every global value is touched once, by one thread.
+    const int ncam_cta = cam1 - cam0;
+    T* rs = reinterpret_cast<T*>(pcg_smem);                                   // [cams_per_cta][D]
+    T* zs = rs + (size_t)a.cams_per_cta * D;                                  // [cams_per_cta][D]
+    double* cw = reinterpret_cast<double*>(pcg_smem + ((size_t)a.cams_per_cta * D * sizeof(T) * 2 + 15) / 16 * 16);   // [cams_per_cta][8]
+    double* rcs = cw + (size_t)a.cams_per_cta * 8;                            // [ncl * PCG_MODES]
+    double* zc = rcs + (size_t)a.ncl * PCG_MODES;                             // [nov][8]
+    {
+      const size_t e0 = (size_t)cam0 * D;
+      const int ne = ncam_cta * D;
+      for (int e = tid; e < ne; e += NT) {
+        const size_t o = e0 + e;
+        T rn;
+        if (verify_pass) rn = __ldg(a.b + o) - __ldcg(a.q + o);   // true residual: q holds S x
+        else { rn = __ldcg(a.r + o) - alpha * __ldcg(a.q + o); a.x[o] += alpha * __ldcg(a.p + o); }
+        a.r[o] = rn;
+        rs[e] = rn;
+        rr_acc += (double)rn * (double)rn;
       }
-      __syncthreads();   // every thread of a camera has read the old r before anyone overwrites it
-      if (on) {
-        const size_t o = (size_t)cam * D + uk;
-        if (!verify_pass) a.x[o] += alpha * __ldcg(a.p + o);
-        a.r[o] = rv[uk];
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < ncam_cta; c0 += CPB) {
+      const int lcam = c0 + ucam;
+      if (ucam < CPB && lcam < ncam_cta) {
+        const int cam = cam0 + lcam;
         const T* __restrict__ m = a.Minv + (size_t)cam * (D * D) + uk * D;
+        const T* rv = rs + lcam * D;
         T zz = T(0);
 #pragma unroll
-        for (int c = 0; c < D; ++c) zz += m[c] * rv[c];
-        a.z[o] = zz;
+        for (int c = 0; c < D; ++c) zz += __ldg(m + c) * rv[c];
+        zs[lcam * D + uk] = zz;
+        if (!coarse) a.z[(size_t)cam * D + uk] = zz;
         rz_acc += (double)zz * (double)rv[uk];
-        rr_acc += (double)rv[uk] * (double)rv[uk];
         if (coarse && uk < PCG_MODES) {
           // (P_cam^T r_cam)[uk]: the pose part of the residual against mode uk
           const T* __restrict__ pm = a.Pm + (size_t)cam * (6 * PCG_MODES) + uk;
-          double s = 0.0;
+          double sum = 0.0;
 #pragma unroll
-          for (int mm = 0; mm < 6; ++mm) s += (double)pm[mm * PCG_MODES] * (double)rv[mm];
-          cw[ucam * 8 + uk] = s;
+          for (int mm = 0; mm < 6; ++mm) sum += (double)__ldg(pm + mm * PCG_MODES) * (double)rv[mm];
+          cw[lcam * 8 + uk] = sum;
         }
-      }
-      if (coarse) {
-        __syncthreads();
-        if (tid < nov * PCG_MODES) {
-          const int slot = tid / PCG_MODES, k = tid % PCG_MODES, cl = cl_lo + slot;
-          const int b0 = max(cl * a.cs, c0), b1 = min(min(cl == a.ncl - 1 ? n : (cl + 1) * a.cs, c0 + CPB), cam1);
-          double s = rc_loc[slot * 8 + k];
-          for (int cc = b0; cc < b1; ++cc) s += cw[(cc - c0) * 8 + k];
-          rc_loc[slot * 8 + k] = s;
-        }
-        __syncthreads();
       }
     }
     if (coarse) {
-      if (tid < nov * PCG_MODES) {
-        const int slot = tid / PCG_MODES, k = tid % PCG_MODES;
-        a.rc[((size_t)blockIdx.x * a.maxov + slot) * 8 + k] = rc_loc[slot * 8 + k];
+      __syncthreads();
+      // this CTA's part of the coarse residual of every cluster it overlaps: a warp per (cluster, mode)
+      for (int pr = w; pr < nov * PCG_MODES; pr += NW) {
+        const int slot = pr / PCG_MODES, k = pr - slot * PCG_MODES, cl = cl_lo + slot;
+        const int b0 = max(cl * a.cs, cam0) - cam0, b1 = min(cl == a.ncl - 1 ? n : (cl + 1) * a.cs, cam1) - cam0;
+        double sum = 0.0;
+        for (int cc = b0 + lane; cc < b1; cc += 32) sum += cw[cc * 8 + k];
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) a.rc[((size_t)blockIdx.x * a.maxov + slot) * 8 + k] = sum;
       }
       rr_acc = block_sum(rr_acc);
       if (tid == 0) a.part_b[blockIdx.x] = rr_acc;
@@ -580,8 +637,6 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
       lap(PH_UPDATE);
       // the whole coarse residual, summed from the CTAs' parts in CTA order; then zc = rows of Ac^-1
       // of the clusters this CTA's cameras overlap times rc; then z += P zc
-      double* rcs = reinterpret_cast<double*>(pcg_smem);          // [ncl * PCG_MODES]
-      double* zc = rcs + (size_t)a.ncl * PCG_MODES;               // [nov][8]
       for (int idx = tid; idx < a.ncl * PCG_MODES; idx += NT) {
         const int cl = idx / PCG_MODES, k = idx - cl * PCG_MODES;
         const int c_lo = cl * a.cs, c_hi = cl == a.ncl - 1 ? n : (cl + 1) * a.cs;
@@ -606,24 +661,24 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
       }
       __syncthreads();
       rz_acc = 0.0;
-      for (int c0 = cam0; c0 < cam1; c0 += CPB) {
-        const int cam = c0 + ucam;
-        if (ucam < CPB && cam < cam1) {
-          const size_t o = (size_t)cam * D + uk;
-          T zz = a.z[o];
+      for (int c0 = 0; c0 < ncam_cta; c0 += CPB) {
+        const int lcam = c0 + ucam;
+        if (ucam < CPB && lcam < ncam_cta) {
+          const int cam = cam0 + lcam;
+          T zz = zs[lcam * D + uk];
           if (uk < 6) {
             const double* zcl = zc + (cluster_of(cam) - cl_lo) * 8;
             const T* __restrict__ pm = a.Pm + (size_t)cam * (6 * PCG_MODES) + uk * PCG_MODES;
             double sum = 0.0;
 #pragma unroll
-            for (int mm = 0; mm < PCG_MODES; ++mm) sum += (double)pm[mm] * zcl[mm];
+            for (int mm = 0; mm < PCG_MODES; ++mm) sum += (double)__ldg(pm + mm) * zcl[mm];
             zz += (T)sum;
-            a.z[o] = zz;
+            zs[lcam * D + uk] = zz;
           }
-          rz_acc += (double)zz * (double)a.r[o];
+          a.z[(size_t)cam * D + uk] = zz;
+          rz_acc += (double)zz * (double)rs[lcam * D + uk];
         }
       }
-      __syncthreads();   // rcs / zc (shared memory) are dead before block_sum / the next phase reuse it
       rz_acc = block_sum(rz_acc);
       if (tid == 0) a.part_a[blockIdx.x] = rz_acc;
       if (!grid_barrier<false>(st, epoch)) return;
@@ -673,13 +728,15 @@ pcg_persistent_kernel(const PcgArgs<T> a) {
       lap(PH_DIRECTION);
       continue;
     }
-    for (int c0 = cam0; c0 < cam1; c0 += CPB) {
-      const int cam = c0 + ucam;
-      if (ucam < CPB && cam < cam1) {
-        const size_t o = (size_t)cam * D + uk;
-        const T pn = a.z[o] + beta * a.p[o];
+    {
+      // p = z + beta p: z of the CTA's cameras is still in shared memory
+      const int ne = ncam_cta * D;
+      for (int e = tid; e < ne; e += NT) {
+        const int lcam = e / D, k2 = e - lcam * D;
+        const size_t o = (size_t)cam0 * D + e;
+        const T pn = zs[e] + beta * __ldcg(a.p + o);
         a.p[o] = pn;
-        a.pp[(size_t)cam * PC::DP + uk] = pn;
+        a.pp[(size_t)(cam0 + lcam) * PC::DP + k2] = pn;
       }
     }
     if (!grid_barrier<false>(st, epoch)) return;
