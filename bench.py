@@ -53,7 +53,13 @@ def emit(line):
 METRIC = "ba_lm_observations_per_sec"
 UNIT = "obs/s"
 CPU_SAMPLE_SCALE = 0.02   # cpu_baseline: config with points/observations scaled by this factor
-C5_STEPS, C5_WARMUP = 10, 2   # fixed so that every rank count repeats the run of profiles/r2_c5_n1.json
+# C5 window, fixed so that every rank count repeats the run of profiles/r2_c5_n1.json: LM steps 4-6.
+# The first six LM steps take the cost from 1.18e8 to 3.887e7 and are the same at every rank count (PCG
+# iterations 56 / 64 / 68 / 72 / ...).  From step 7 on the cost moves by < 1e-3 per step and the trust
+# region has grown to the damping floor: accept / reject decisions then depend on the rounding of the
+# summation order, and runs of the SAME configuration differ by rejected trials and 13 - 238 PCG
+# iterations per step (profiles/README.md) -- timing those steps compares trajectories, not machines.
+C5_STEPS, C5_WARMUP = 3, 3
 # dram__bytes_read.sum + dram__bytes_write.sum per launch on config C3 (1 GPU, full size), from the
 # `ncu --set full` captures summarised under profiles/ (ncu cannot run inside the bench).  pcg_solve: per PCG iteration.
 NCU_TRAFFIC_C3 = {"pcg_solve": 535.1e6, "schur_offdiag": 2887.5e6, "linearize": 788.6e6, "camera_blocks": 664.7e6,
@@ -520,14 +526,16 @@ def main_ours(args):
             with open(fx) as f:
                 ref = json.load(f)
             ref = ref.get("c5", ref)
-            c5["n1_reference"] = {"file": "profiles/r2_c5_n1.json", "ms_per_step": ref["ms_per_step"], "final_robust_cost": ref["final_robust_cost"]}
+            c5["n1_reference"] = {"file": "profiles/r2_c5_n1.json", "ms_per_step": ref["ms_per_step"], "final_robust_cost": ref["final_robust_cost"],
+                                  "steps": ref.get("steps"), "warmup": ref.get("warmup"), "pcg_iters": ref.get("pcg_iters")}
+            c5["same_window_as_n1"] = bool(ref.get("steps") == C5_STEPS and ref.get("warmup") == C5_WARMUP)
             c5["speedup_vs_n1"] = ref["ms_per_step"] / c5["ms_per_step"]
             c5["cost_rel_diff_vs_n1"] = abs(c5["final_robust_cost"] - ref["final_robust_cost"]) / ref["final_robust_cost"]
             c5["loss_rel_diff_vs_n1_max"] = float(max(abs(x - y) / y for x, y in zip(c5["losses"], ref["losses"])))
         extra["c5"] = c5
     if rank == 0 and world == 1 and args.config == "C5":
         extra["c5"] = {"ms_per_step": res["ms_total"] / args.steps, "final_robust_cost": res["final_robust_cost"], "losses": res["losses"],
-                       "steps": args.steps, "warmup": args.warmup}
+                       "steps": args.steps, "warmup": args.warmup, "pcg_iters": res["pcg_iters"], "rejects": res["rejects"], "work": res["work"]}
 
     cpu = c1 = ref_gpu = dropin = None
     if rank == 0 and world == 1 and not args.no_cpu:

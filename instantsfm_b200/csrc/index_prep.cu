@@ -408,7 +408,9 @@ void build_schur_pattern(SchurPattern& sp, const ObsIndex& ix, cudaStream_t s, K
     int unit = SPMV_CHUNK;
     if (grid_warps > 0 && !getenv("ISFM_FIXED_UNITS")) {
       const int64_t slots_per_warp = nnzp / ((int64_t)grid_warps * std::max(hook ? hook->matvec_share : 1, 1));
-      while (unit > 12 && slots_per_warp / unit < 8) unit /= 2;
+      int min_units = 8;   // units per warp below which the unit is halved (tail balance of the static deal)
+      if (const char* e = getenv("ISFM_UNITS_PER_WARP")) min_units = std::max(1, atoi(e));
+      while (unit > 12 && slots_per_warp / unit < min_units) unit /= 2;
     }
     sp.unit_slots = unit;
     for (int64_t i = 0; i < n_cam; ++i) {
