@@ -62,9 +62,10 @@ CPU_SAMPLE_SCALE = 0.02   # cpu_baseline: config with points/observations scaled
 C5_STEPS, C5_WARMUP = 3, 3
 # dram__bytes_read.sum + dram__bytes_write.sum per launch on config C3 (1 GPU, full size), from the
 # `ncu --set full` captures summarised under profiles/ (ncu cannot run inside the bench).  pcg_solve: per PCG iteration.
-NCU_TRAFFIC_C3 = {"pcg_solve": 535.1e6, "schur_offdiag": 2887.5e6, "linearize": 788.6e6, "camera_blocks": 664.7e6,
-                  "backsub": 800.7e6}
-NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_full_summary.txt (bytes per launch; pcg_solve: per PCG iteration)"
+NCU_TRAFFIC_C3 = {"pcg_solve": 549.4e6, "schur_offdiag": 2882.6e6, "linearize": 797.6e6, "camera_blocks": 665.8e6,
+                  "backsub": 802.0e6}
+NCU_TRAFFIC_SOURCE = ("profiles/r2_ncu_full_summary.txt (dram__bytes_read + write per launch; pcg_solve: the captured solve of 33 "
+                      "PCG iterations moved 18.13 GB = 549 MB per iteration)")
 PHASES = ["matvec", "combine", "exchange", "update", "coarse", "direction"]
 
 
@@ -184,6 +185,7 @@ def run_resident(a, comm, world, local_rank, steps, warmup, n_total):
     eng.set_problem(*pinned_np)
     pat = eng.schur_pattern()
     mv_owned, mv_total = eng.matvec_units()
+    rob_initial = eng.cost()[0]   # same instance at every rank count <=> same initial cost
     wl = [eng.step()[0] for _ in range(warmup)]
     ph0, solves0, two_level = eng.pcg_phases()
     sampler = ClockSampler(local_rank)
@@ -245,7 +247,7 @@ def run_resident(a, comm, world, local_rank, steps, warmup, n_total):
                 "share_of_step": kernels[top]["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values())}
     out = {"ms_total": ms_total, "value": n_total * steps / (ms_total * 1e-3), "losses": [float(x) for x in wl + losses],
            "pcg_iters": [int(s["pcg_iters"]) for s in stats], "rejects": int(sum(s["rejects"] for s in stats)),
-           "final_robust_cost": rob, "final_rmse_px": float(np.sqrt(sq / n_total)), "kernels": kernels, "work": work,
+           "final_robust_cost": rob, "initial_robust_cost": rob_initial, "final_rmse_px": float(np.sqrt(sq / n_total)), "kernels": kernels, "work": work,
            "roofline": roofline, "clocks": clocks, "launches": int(launches), "pattern": pat, "matvec": (mv_owned, mv_total)}
     eng.close()
     return out
@@ -518,7 +520,8 @@ def main_ours(args):
         r5 = run_resident(a5, comm, world, local_rank, C5_STEPS, C5_WARMUP, a5.n_obs_total)
         c5 = {"workload": "C5 city-scale synthetic BA (street geometry): 20000 cameras / 10000000 points / 60000000 observations, strong scaling",
               "n_gpus": world, "steps": C5_STEPS, "warmup": C5_WARMUP, "ms_per_step": r5["ms_total"] / C5_STEPS, "value": r5["value"], "unit": UNIT,
-              "losses": r5["losses"], "final_robust_cost": r5["final_robust_cost"], "final_rmse_px": r5["final_rmse_px"],
+              "losses": r5["losses"], "final_robust_cost": r5["final_robust_cost"], "initial_robust_cost": r5["initial_robust_cost"],
+              "final_rmse_px": r5["final_rmse_px"],
               "pcg_iters": r5["pcg_iters"], "rejects": r5["rejects"], "work": r5["work"],
               "kernels": {k: {"ms_per_step": v["ms_per_step"], "us_per_launch": v["us_per_launch"]} for k, v in r5["kernels"].items()}}
         fx = os.path.join(ROOT, "profiles", "r2_c5_n1.json")
@@ -532,9 +535,14 @@ def main_ours(args):
             c5["speedup_vs_n1"] = ref["ms_per_step"] / c5["ms_per_step"]
             c5["cost_rel_diff_vs_n1"] = abs(c5["final_robust_cost"] - ref["final_robust_cost"]) / ref["final_robust_cost"]
             c5["loss_rel_diff_vs_n1_max"] = float(max(abs(x - y) / y for x, y in zip(c5["losses"], ref["losses"])))
+            c5["loss_rel_diff_note"] = ("max over the LM steps run; the first step is a long nonlinear step from the perturbed start whose outcome "
+                                        "depends on the inexact (1e-6) PCG solve at the 1e-2 level; the rank counts meet again: see cost_rel_diff_vs_n1")
+            if ref.get("initial_robust_cost"):
+                c5["initial_cost_rel_diff_vs_n1"] = abs(c5["initial_robust_cost"] - ref["initial_robust_cost"]) / ref["initial_robust_cost"]
         extra["c5"] = c5
     if rank == 0 and world == 1 and args.config == "C5":
         extra["c5"] = {"ms_per_step": res["ms_total"] / args.steps, "final_robust_cost": res["final_robust_cost"], "losses": res["losses"],
+                       "initial_robust_cost": res["initial_robust_cost"],
                        "steps": args.steps, "warmup": args.warmup, "pcg_iters": res["pcg_iters"], "rejects": res["rejects"], "work": res["work"]}
 
     cpu = c1 = ref_gpu = dropin = None
@@ -567,7 +575,8 @@ def main_ours(args):
                            "total_observations": n_total, "l2_policy": "inputs larger than L2 (J blocks alone exceed 126 MB)",
                            "pcg_tol": 1e-6, "schur_blocks": pat["nnzb"], "schur_pairs": pat["n_pairs"]},
                 "lm_iters_per_sec": args.steps / (res["ms_total"] * 1e-3), "final_rmse_px": res["final_rmse_px"],
-                "final_robust_cost": res["final_robust_cost"], "pcg_iters": res["pcg_iters"], "losses": res["losses"], "rejects": res["rejects"],
+                "final_robust_cost": res["final_robust_cost"], "initial_robust_cost": res["initial_robust_cost"],
+                "pcg_iters": res["pcg_iters"], "losses": res["losses"], "rejects": res["rejects"],
                 "work": res["work"],
                 "matvec_split": (None if world == 1 else {"units_owned_rank0": mv_owned, "units_total": mv_total}),
                 "pcg_exchange": (None if world == 1 else ("peer-memory push over NVLink inside the persistent PCG kernel"
