@@ -65,3 +65,24 @@ def test_partitioned_normal_equations_sum_to_the_whole(world):
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert sorted(ret.keys()) == list(range(world))
+
+
+@pytest.mark.parametrize("config,scale", [("C5", 0.01), ("C3", 0.02)])
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_generator_slices_one_instance(config, scale, world):
+    """bench.py's strong-scaling legs rest on this: make_config(shard=(rank, world)) for all ranks
+    concatenates to exactly the arrays of the single-rank instance (same cameras on every rank, the
+    points / observations of contiguous point ranges), so N ranks solve the SAME problem as one."""
+    from instantsfm_b200.synthetic import make_config
+    whole = make_config(config, scale=scale, shard=(0, 1))
+    parts = [make_config(config, scale=scale, shard=(r, world)) for r in range(world)]
+    assert sum(p.n_obs for p in parts) == whole.n_obs == whole.n_obs_total
+    assert all(p.n_obs_total == whole.n_obs_total and p.n_pt_total == whole.n_pt for p in parts)
+    assert all(np.array_equal(p.camera_params, whole.camera_params) and np.array_equal(p.camera_pps, whole.camera_pps) for p in parts)
+    assert np.array_equal(np.concatenate([p.points_3d for p in parts]), whole.points_3d)
+    assert np.array_equal(np.concatenate([p.points_2d for p in parts]), whole.points_2d)
+    assert np.array_equal(np.concatenate([p.camera_indices for p in parts]), whole.camera_indices)
+    off = np.cumsum([0] + [p.n_pt for p in parts])
+    assert np.array_equal(np.concatenate([p.point_indices + off[r] for r, p in enumerate(parts)]), whole.point_indices)
+    # balanced by observation count
+    assert max(p.n_obs for p in parts) - min(p.n_obs for p in parts) <= 64
