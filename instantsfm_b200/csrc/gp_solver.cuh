@@ -436,7 +436,10 @@ struct GPSolver : GPSolverBase {
     int rejects = 0;
     const int trial = cur ^ 1;
     while (last <= loss) {
-      mu = std::min(mu * (1.0 + tr.damping), sizeof(T) == 4 ? 1e24 : 1e100);
+      // fp32: same damping floor as bundle adjustment (ba_solver.cuh) -- the reduced
+      // centre system has gauge modes (translation, scale) too, left with nothing but the damping term
+      const double floor_T = sizeof(T) == 4 ? 1e-6 : 0.0;
+      mu = std::min(mu * (1.0 + std::max(tr.damping, floor_T)), sizeof(T) == 4 ? 1e24 : 1e100);
       const T m = (T)mu;
       { TimerScope ts(timers, T_POINT_SOLVE);
         gp_point_solve_kernel<T><<<div_up(n_pt, GP_TPB), GP_TPB, 0, s>>>(n_pt, ix.pt_off.get(), ix.obs_perm.get(), fixed_ptr(),
