@@ -564,6 +564,8 @@ struct BlockPCG {
   bool ring_valid = false;
   DeviceBuffer<PcgState> state;
   DeviceBuffer<double> rc_parts;   // persistent kernel, two-level: [grid][maxov][8]
+  const char* env_push = nullptr;
+  bool env_verify = false, env_no_l2_keep = false, env_no_graph = false;
   PcgState* h_state = nullptr;  // pinned
   // The whole iteration loop of a single-rank solve is ONE graph launch: a conditional WHILE node
   // whose body holds the kernels of one iteration; the last kernel sets the loop condition on the
@@ -601,6 +603,9 @@ struct BlockPCG {
     coarse = CoarseRef{};
     ring_valid = false;
     stream_lo = stream_hi = -1;
+    // environment switches: read once per problem, not per solve
+    env_push = getenv("ISFM_PEER_PUSH"); env_verify = getenv("ISFM_PCG_VERIFY") != nullptr;
+    env_no_l2_keep = getenv("ISFM_NO_L2_KEEP") != nullptr; env_no_graph = getenv("ISFM_NO_GRAPH") != nullptr;
     // persistent solve kernel: one CTA per SM, if the device can co-schedule them
     persist_grid = 0;
     if (!getenv("ISFM_NO_PERSISTENT")) {
@@ -688,7 +693,7 @@ struct BlockPCG {
     const bool peer = multi && comm->peer_ready && (size_t)n_cam * D * sizeof(T) <= comm->px.slot_bytes;
     const PeerExchange px = peer ? comm->px : PeerExchange{};
     // ISFM_PEER_PUSH = "grid" / "fused" forces the push variant (tests); default: by vector size
-    const char* push_env = getenv("ISFM_PEER_PUSH");
+    const char* push_env = env_push;
     const bool big_push = peer && (push_env ? push_env[0] == 'g' : (size_t)n_cam * D * sizeof(T) > ((size_t)128 << 10));
     const bool merged = (int64_t)n_cam * D <= 4096;   // the last CTA of the update kernel also builds p
     { TimerScope ts(kt, T_PCG_VEC);
@@ -711,13 +716,13 @@ struct BlockPCG {
       // from it if it is above the tolerance.  Off by default: measured +60 % PCG iterations at C3 /
       // C5 for an LM trajectory that agrees to 7 digits either way (the fp32 recursive residual under-
       // states the true one, but LM only needs an inexact Newton step).
-      a.verify = getenv("ISFM_PCG_VERIFY") ? 1 : 0;
+      a.verify = env_verify ? 1 : 0;
       a.x = x.get(); a.r = r.get(); a.z = z.get(); a.p = p.get(); a.pp = pp.get(); a.q = q.get(); a.y = y.get(); a.yup = yup.get(); a.C = C.get();
       a.part_pq = part_pq.get(); a.part_a = part_a.get(); a.part_b = part_b.get();
       a.st = state.get(); a.tol2 = tol2;
       a.cams_per_cta = div_up(n_cam, persist_grid);
       const int64_t my_slots = n_units > 0 ? (int64_t)std::min<int64_t>((int64_t)n_units * sp.unit_slots, sp.nnzu) : 0;
-      a.keep_in_l2 = (size_t)my_slots * D * D * sizeof(T) <= ((size_t)72 << 20) && !getenv("ISFM_NO_L2_KEEP");
+      a.keep_in_l2 = (size_t)my_slots * D * D * sizeof(T) <= ((size_t)72 << 20) && !env_no_l2_keep;
       a.peer = peer ? 1 : 0;
       a.push_grid = big_push ? 1 : 0;
       a.px = px;
@@ -804,7 +809,7 @@ struct BlockPCG {
     const int vec_per_iter = (merged ? 2 : 3) + (multi ? 1 : 0) + (big_push ? 1 : 0);
     // No per-kernel timing and no NCCL call inside the loop (single rank, or the peer-memory
     // exchange): device-side WHILE graph.
-    bool use_graph = (!multi || peer) && !kt.enabled && !graph_disabled && !getenv("ISFM_NO_GRAPH");
+    bool use_graph = (!multi || peer) && !kt.enabled && !graph_disabled && !env_no_graph;
     if (use_graph && !(graph_exec && g_E == E && g_Hd == Hd && g_Minv == Minv && g_tol2 == tol2 && g_units == sp.n_chunks && g_unit_lo == unit_lo && g_unit_hi == unit_hi &&
                        g_peer_base == (peer ? (const void*)comm->px.base[0] : nullptr))) {
       if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }

@@ -40,12 +40,18 @@ def concat_features(images, attr):
 def flatten_observations(tracks, track_ids):
     """Concatenated (image_id, feature_id, position-in-track_ids) of the given tracks, in the
     order of the reference's nested loops (bundle_adjustment.py:88-96)."""
-    obs_list = [np.asarray(tracks[t].observations).reshape(-1, 2) for t in track_ids]
-    lengths = np.array([o.shape[0] for o in obs_list], dtype=np.int64)
+    obs_list = [tracks[t].observations for t in track_ids]
+    lengths = np.fromiter(map(len, obs_list), dtype=np.int64, count=len(obs_list))
     if lengths.sum() == 0:
         z = np.zeros(0, dtype=np.int64)
         return z, z, z
-    obs = np.concatenate(obs_list, axis=0).astype(np.int64)
+    try:       # the common case: every track holds an [k, 2] integer array -- one C-level concatenate
+        obs = np.concatenate(obs_list, axis=0)
+        if obs.ndim != 2 or obs.shape[1] != 2:
+            raise ValueError
+    except ValueError:   # lists of tuples, empty lists, 1-d arrays: normalise per track
+        obs = np.concatenate([np.asarray(o).reshape(-1, 2) for o in obs_list], axis=0)
+    obs = obs.astype(np.int64, copy=False)
     which = np.repeat(np.arange(len(track_ids), dtype=np.int64), lengths)
     return obs[:, 0], obs[:, 1], which
 

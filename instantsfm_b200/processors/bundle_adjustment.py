@@ -12,7 +12,7 @@ import numpy as np
 
 from ..engine import BAEngine
 from ..geometry import matrices_to_pose7, pose7_to_matrices, quat_to_mat as quat_rows_to_matrices
-from ._common import concat_features, device_index, flatten_observations, should_stop
+from ._common import concat_features, device_index, should_stop
 
 # CameraModelId.value -> principal-point indices inside Camera.params (scene/defs.py:115-140).
 # FOV (7) and THIN_PRISM_FISHEYE (10) are listed by the reference but their cost functions
@@ -62,8 +62,13 @@ class TorchBA:
 
     # -- tensor set-up, bundle_adjustment.py:66-113 ---------------------------------------
     def _build(self, cameras, images, tracks, options, model_value):
+        # ONE pass over the track objects (a million of them on a C3-sized scene: every Python-level
+        # touch costs ~0.3 s there): keys, observation arrays and points are collected together, the
+        # observations of ALL tracks are concatenated once and the invalid tracks masked out afterwards
         track_keys = list(tracks.keys())
-        track_lengths = np.array([len(tracks[k].observations) for k in track_keys])
+        track_objs = list(tracks.values())
+        obs_list = [t.observations for t in track_objs]
+        track_lengths = np.fromiter(map(len, obs_list), dtype=np.int64, count=len(obs_list))
         is_track_valid = track_lengths >= options["min_num_view_per_track"]
         registered = np.array([img.is_registered for img in images], dtype=bool)
 
@@ -77,12 +82,24 @@ class TorchBA:
         remaining = np.array([i for i in range(camera_params.shape[1]) if i not in pp_indices])
         camera_pps = camera_params[:, pp_indices]
         camera_params = camera_params[:, remaining]
-        points_3d = np.stack([np.asarray(t.xyz, dtype=np.float64) for t in tracks.values()], 0)
+        points_3d = np.array([t.xyz for t in track_objs], dtype=np.float64).reshape(len(track_objs), 3)
 
         valid_ids = np.flatnonzero(is_track_valid)
-        image_id, feature_id, which = flatten_observations(tracks, [track_keys[i] for i in valid_ids])
+        if track_lengths.sum() == 0:
+            image_id = feature_id = which = np.zeros(0, dtype=np.int64)
+        else:
+            try:       # the common case: every track holds an [k, 2] integer array
+                obs = np.concatenate(obs_list, axis=0)
+                if obs.ndim != 2 or obs.shape[1] != 2:
+                    raise ValueError
+            except ValueError:   # lists of tuples, empty lists, 1-d arrays: normalise per track
+                obs = np.concatenate([np.asarray(o).reshape(-1, 2) for o in obs_list], axis=0)
+            obs = obs.astype(np.int64, copy=False)
+            owner = np.repeat(np.arange(len(obs_list), dtype=np.int64), track_lengths)
+            sel = is_track_valid[owner]
+            image_id, feature_id, which = obs[sel, 0], obs[sel, 1], owner[sel]
         keep = registered[image_id] if image_id.size else np.zeros(0, bool)
-        image_id, feature_id, point_idx = image_id[keep], feature_id[keep], valid_ids[which[keep]]
+        image_id, feature_id, point_idx = image_id[keep], feature_id[keep], which[keep]
         table, offsets = concat_features(images, "features")
         points_2d = table[offsets[image_id] + feature_id].reshape(-1, 2)
 
