@@ -564,7 +564,7 @@ struct BlockPCG {
   bool ring_valid = false;
   DeviceBuffer<PcgState> state;
   DeviceBuffer<double> rc_parts;   // persistent kernel, two-level: [grid][maxov][8]
-  const char* env_push = nullptr;
+  bool env_push_set = false, env_push_grid = false;   // ISFM_PEER_PUSH given / starts with 'g' (values copied: the environment may change)
   bool env_verify = false, env_no_l2_keep = false, env_no_graph = false;
   PcgState* h_state = nullptr;  // pinned
   // The whole iteration loop of a single-rank solve is ONE graph launch: a conditional WHILE node
@@ -604,7 +604,8 @@ struct BlockPCG {
     ring_valid = false;
     stream_lo = stream_hi = -1;
     // environment switches: read once per problem, not per solve
-    env_push = getenv("ISFM_PEER_PUSH"); env_verify = getenv("ISFM_PCG_VERIFY") != nullptr;
+    { const char* e = getenv("ISFM_PEER_PUSH"); env_push_set = e != nullptr; env_push_grid = e && e[0] == 'g'; }
+    env_verify = getenv("ISFM_PCG_VERIFY") != nullptr;
     env_no_l2_keep = getenv("ISFM_NO_L2_KEEP") != nullptr; env_no_graph = getenv("ISFM_NO_GRAPH") != nullptr;
     // persistent solve kernel: one CTA per SM, if the device can co-schedule them
     persist_grid = 0;
@@ -693,8 +694,8 @@ struct BlockPCG {
     const bool peer = multi && comm->peer_ready && (size_t)n_cam * D * sizeof(T) <= comm->px.slot_bytes;
     const PeerExchange px = peer ? comm->px : PeerExchange{};
     // ISFM_PEER_PUSH = "grid" / "fused" forces the push variant (tests); default: by vector size
-    const char* push_env = env_push;
-    const bool big_push = peer && (push_env ? push_env[0] == 'g' : (size_t)n_cam * D * sizeof(T) > ((size_t)128 << 10));
+    const bool push_env = env_push_set;
+    const bool big_push = peer && (push_env ? env_push_grid : (size_t)n_cam * D * sizeof(T) > ((size_t)128 << 10));
     const bool merged = (int64_t)n_cam * D <= 4096;   // the last CTA of the update kernel also builds p
     { TimerScope ts(kt, T_PCG_VEC);
       pcg_init_kernel<T, D><<<nb, PCG_TPB, 0, s>>>(n_cam, b, Minv, x.get(), r.get(), p.get(), part_a.get(), part_b.get()); }
