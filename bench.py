@@ -548,9 +548,15 @@ def main_ours(args):
     cpu = c1 = ref_gpu = dropin = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        cpu = run_cpu_port(args.config if args.config != "C5" else "C3", 2, threads, CPU_SAMPLE_SCALE, compare_gpu=True)
-        c1 = run_cpu_port("C1", 3, threads, 1.0, compare_gpu=True)
-        c1["what"] = "BASELINE.json config 1 (64 cameras / 10 k points / 60 k observations) at FULL size on both arms"
+        try:   # a baseline leg must never take the bench line down
+            cpu = run_cpu_port(args.config if args.config != "C5" else "C3", 2, threads, CPU_SAMPLE_SCALE, compare_gpu=True)
+        except Exception as e:
+            cpu = {"error": repr(e)[:300], "kind": "port", "cores": threads}
+        try:
+            c1 = run_cpu_port("C1", 3, threads, 1.0, compare_gpu=True)
+            c1["what"] = "BASELINE.json config 1 (64 cameras / 10 k points / 60 k observations) at FULL size on both arms"
+        except Exception as e:
+            c1 = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.quick and args.config in ("C1", "C2", "C3"):
         try:
             ref_gpu = run_reference_gpu(a, 2)
