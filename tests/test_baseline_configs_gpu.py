@@ -167,3 +167,25 @@ def test_two_level_stays_positive_definite_at_late_lm_damping(monkeypatch):
         assert s1["pcg_status"] == 1 and s1["rejects"] == s0["rejects"], (it, s0, s1)
         it0 += s0["pcg_iters"]; it1 += s1["pcg_iters"]
     assert it1 * 1.5 <= it0, (it0, it1)
+
+
+@pytest.mark.parametrize("model_id", [0, 2, 4, 6])   # D = 7, 8, 12, 16 (RADIAL, D = 9, is what the configs above run)
+def test_two_level_every_block_size(model_id):
+    """The persistent kernel with the coarse level for every camera-block size: 40 cameras (two-level on
+    by default), fp64 vs the oracle's exact solves, fp32 at the north-star tolerance."""
+    from instantsfm_b200.synthetic import make_ba_problem
+    from oracle.ba import BAProblem, make_optimizer
+    a = make_ba_problem(40, 1500, 9000, seed=80 + model_id, model_id=model_id)
+    pb = BAProblem(a.model_id, a.camera_params, a.camera_pps, a.points_3d, a.points_2d, a.camera_indices, a.point_indices)
+    opt = make_optimizer(pb, 1.0, solver="direct")
+    e64 = _engine(a, np.float64, pcg_tol=1e-12)
+    e32 = _engine(a, np.float32)
+    assert e64.pcg_phases()[2] and e32.pcg_phases()[2]
+    for it in range(5):
+        ref = opt.step()
+        l64, s64 = e64.step()
+        l32, s32 = e32.step()
+        assert abs(l64 - ref) <= 1e-8 * ref, (it, l64, ref)
+        assert abs(l32 - ref) <= TOL * ref, (it, l32, ref)
+        assert s64["pcg_status"] == 1 and s32["pcg_status"] == 1
+    assert e64.pcg_phases()[1] > 0   # solved by the persistent kernel
