@@ -245,6 +245,16 @@ def run_resident(a, comm, world, local_rank, steps, warmup, n_total):
                 "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
                 "note": "pcg_solve = one persistent kernel per PCG solve: bytes = per-iteration bytes x iterations of the launch",
                 "share_of_step": kernels[top]["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values())}
+    if top == "pcg_solve" and phases.get("matvec", 0.0) > 0.0:
+        # the kernel's time includes the grid barriers and the small phases of every iteration; the
+        # mat-vec phase is the part that streams the matrix (timed by CTA 0 with %globaltimer)
+        try:
+            ab_it = algorithmic_bytes("pcg_solve", a.n_obs, a.n_pt, a.n_cam, d, pat["n_pairs"], (pat["nnzb"] - a.n_cam) // 2, pat["nnzb"]) * mv_owned / max(mv_total, 1)
+            gbs = ab_it / (phases["matvec"] * 1e-6) / 1e9
+            roofline["matvec_phase"] = {"us_per_iteration": phases["matvec"], "achieved": gbs, "frac": gbs / peak,
+                                        "note": "same algorithmic bytes per iteration over the mat-vec phase alone"}
+        except Exception as e:   # informational only
+            roofline["matvec_phase"] = {"error": repr(e)[:200]}
     out = {"ms_total": ms_total, "value": n_total * steps / (ms_total * 1e-3), "losses": [float(x) for x in wl + losses],
            "pcg_iters": [int(s["pcg_iters"]) for s in stats], "rejects": int(sum(s["rejects"] for s in stats)),
            "final_robust_cost": rob, "initial_robust_cost": rob_initial, "final_rmse_px": float(np.sqrt(sq / n_total)), "kernels": kernels, "work": work,
