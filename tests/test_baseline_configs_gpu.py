@@ -181,7 +181,7 @@ def test_two_level_every_block_size(model_id):
     e64 = _engine(a, np.float64, pcg_tol=1e-12)
     e32 = _engine(a, np.float32)
     assert e64.pcg_phases()[2] and e32.pcg_phases()[2]
-    for it in range(5):
+    for it in range(3):   # (verified for 5; the exact oracle solves dominate the run time)
         ref = opt.step()
         l64, s64 = e64.step()
         l32, s32 = e32.step()
