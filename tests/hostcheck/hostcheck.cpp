@@ -3,6 +3,7 @@
 // arithmetic the CUDA kernels inline -- camera models + Jacobians, SE(3) retraction,
 // small SPD inverses -- against the oracle.  Never loaded by the product package.
 #include "../../instantsfm_b200/csrc/math.cuh"
+#include "../../instantsfm_b200/csrc/camera_maps.cuh"
 
 using namespace isfm;
 
@@ -71,3 +72,16 @@ void hc_huber_f64(long n, const double* s, double delta, double* rho, double* w)
   for (long i = 0; i < n; ++i) huber<double>(s[i], delta, rho[i], w[i]);
 }
 }
+
+// scene-layer camera maps (csrc/camera_maps.cuh): one camera-table row, n points
+extern "C" {
+void hc_cam2img(long n, const double* row, const double* uvw, double* out) {
+  const CamRow c = load_row(row);
+  for (long i = 0; i < n; ++i) cam2img(c, uvw[3 * i], uvw[3 * i + 1], uvw[3 * i + 2], out[2 * i], out[2 * i + 1]);
+}
+void hc_img2cam(long n, const double* row, const double* xy, double* out) {
+  const CamRow c = load_row(row);
+  for (long i = 0; i < n; ++i) img2cam(c, xy[2 * i], xy[2 * i + 1], out[2 * i], out[2 * i + 1]);
+}
+}
+

@@ -74,3 +74,42 @@ def test_camera_table_row_layout():
     assert list(r[5:11]) == [p[4], p[5], p[8], p[9], p[10], p[11]] and list(r[11:13]) == p[6:8]
     r = orc.Intrinsics(3, PIXEL_MODEL_PARAMS[3]).row()
     assert r[1] == r[2] == PIXEL_MODEL_PARAMS[3][0] and list(r[5:7]) == PIXEL_MODEL_PARAMS[3][3:5]
+
+
+# ---------------------------------------------------------------------------------------------
+# the DEVICE arithmetic of csrc/camera_ops.cu (csrc/camera_maps.cuh) compiled for the host
+# ---------------------------------------------------------------------------------------------
+def _hc(fn, row, pts, width):
+    import ctypes
+    from tests.hostcheck.build import load
+    lib = load()
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    row = np.ascontiguousarray(row, dtype=np.float64)
+    out = np.zeros((pts.shape[0], 2))
+    p = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))   # noqa: E731
+    getattr(lib, fn)(ctypes.c_long(pts.shape[0]), p(row), p(pts), p(out))
+    assert pts.shape[1] == width
+    return out
+
+
+@pytest.mark.parametrize("model", range(11))
+def test_device_camera_maps_on_host_match_reference_golden(model):
+    """cam2img / img2cam exactly as the CUDA kernels inline them (same header, g++ without FMA
+    contraction) against the vectors the reference's own Camera class produced on cv2 4.13."""
+    row = orc.Intrinsics(model, PIXEL_MODEL_PARAMS[model]).row()
+    uvw, xy = point_inputs(model)
+    with np.errstate(all="ignore"):
+        close(_hc("hc_cam2img", row, uvw, 3), GOLDEN[f"cam2img/{model}"], 1e-11)
+        close(_hc("hc_img2cam", row, xy, 2), GOLDEN[f"img2cam/{model}"], 1e-11)
+
+
+def test_device_camera_maps_on_host_match_oracle_on_random_cameras():
+    rng = np.random.default_rng(9)
+    for model in range(11):
+        prm = np.array(PIXEL_MODEL_PARAMS[model]) * (1.0 + 0.02 * rng.normal(size=len(PIXEL_MODEL_PARAMS[model])))
+        c = orc.Intrinsics(model, prm)
+        uvw = np.column_stack([rng.normal(0, 0.5, 200), rng.normal(0, 0.4, 200), rng.uniform(0.7, 4.0, 200)])
+        xy = np.column_stack([rng.uniform(100, 1180, 200), rng.uniform(80, 880, 200)])
+        with np.errstate(all="ignore"):
+            close(_hc("hc_cam2img", c.row(), uvw, 3), orc.cam2img(c, uvw), 1e-11)
+            close(_hc("hc_img2cam", c.row(), xy, 2), orc.img2cam(c, xy), 1e-11)
