@@ -80,25 +80,7 @@ template <typename T>
 __global__ void coarse_modes_kernel(CoarseGeom g, int cw, const T* __restrict__ cam, const double* __restrict__ c0, T* __restrict__ Pm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n_cam) return;
-  const T* c = cam + (size_t)i * cw;
-  const double* o = c0 + g.cluster_of(i) * 3;
-  double R[9];
-  const double q[4] = {(double)c[3], (double)c[4], (double)c[5], (double)c[6]};
-  quat_to_rot(q, R);
-  double tt[3];
-  for (int k = 0; k < 3; ++k) tt[k] = (double)c[k] + R[k * 3 + 0] * o[0] + R[k * 3 + 1] * o[1] + R[k * 3 + 2] * o[2];
-  const double tx[9] = {0, -tt[2], tt[1], tt[2], 0, -tt[0], -tt[1], tt[0], 0};
-  T* P = Pm + (size_t)i * (6 * CM);
-  for (int r = 0; r < 3; ++r) {
-    for (int k = 0; k < 3; ++k) {
-      P[r * CM + k] = (T)(-R[r * 3 + k]);                                                                   // dtau / v
-      P[r * CM + 3 + k] = (T)(-(tx[r * 3 + 0] * R[0 * 3 + k] + tx[r * 3 + 1] * R[1 * 3 + k] + tx[r * 3 + 2] * R[2 * 3 + k]));   // dtau / w
-      P[(3 + r) * CM + k] = T(0);                                                                           // dphi / v
-      P[(3 + r) * CM + 3 + k] = (T)(-R[r * 3 + k]);                                                         // dphi / w
-    }
-    P[r * CM + 6] = (T)tt[r];                                                                               // dtau / s
-    P[(3 + r) * CM + 6] = T(0);
-  }
+  similarity_modes<T>(cam + (size_t)i * cw, c0 + g.cluster_of(i) * 3, Pm + (size_t)i * (6 * CM));
 }
 
 // ---- per trial: G = P^T E P (dense [ncp][ncp], fp64) ----

@@ -398,4 +398,32 @@ template <int D> ISFM_HD bool spd_inverse(double* A) {
   return ok;
 }
 
+// --------------------------------------------------------------------------------------
+// Prolongation block of the two-level PCG preconditioner (coarse.cuh): the seven similarity modes
+// of a rigid piece of the scene about the centre c0 -- translation v, rotation w, scale s --
+// expressed in one camera's left-perturbation tangent [dtau, dphi] (pose c = [t, q_xyzw, ...]):
+//   dphi = -R w,   dtau = -R v - tt x (R w) + s tt,   tt = t + R c0.
+// P is [6][7] row-major: rows dtau (3), dphi (3); columns v (3), w (3), s.
+// --------------------------------------------------------------------------------------
+template <typename T>
+ISFM_HD void similarity_modes(const T* c, const double* o, T* P) {
+  constexpr int NM = 7;
+  double R[9];
+  const double q[4] = {(double)c[3], (double)c[4], (double)c[5], (double)c[6]};
+  quat_to_rot(q, R);
+  double tt[3];
+  for (int k = 0; k < 3; ++k) tt[k] = (double)c[k] + R[k * 3 + 0] * o[0] + R[k * 3 + 1] * o[1] + R[k * 3 + 2] * o[2];
+  const double tx[9] = {0, -tt[2], tt[1], tt[2], 0, -tt[0], -tt[1], tt[0], 0};
+  for (int r = 0; r < 3; ++r) {
+    for (int k = 0; k < 3; ++k) {
+      P[r * NM + k] = (T)(-R[r * 3 + k]);                                                                   // dtau / v
+      P[r * NM + 3 + k] = (T)(-(tx[r * 3 + 0] * R[0 * 3 + k] + tx[r * 3 + 1] * R[1 * 3 + k] + tx[r * 3 + 2] * R[2 * 3 + k]));   // dtau / w
+      P[(3 + r) * NM + k] = T(0);                                                                           // dphi / v
+      P[(3 + r) * NM + 3 + k] = (T)(-R[r * 3 + k]);                                                         // dphi / w
+    }
+    P[r * NM + 6] = (T)tt[r];                                                                               // dtau / s
+    P[(3 + r) * NM + 6] = T(0);
+  }
+}
+
 }  // namespace isfm

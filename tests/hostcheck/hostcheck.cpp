@@ -85,3 +85,13 @@ void hc_img2cam(long n, const double* row, const double* xy, double* out) {
 }
 }
 
+// prolongation blocks of the two-level preconditioner (math.cuh::similarity_modes): n poses [n][7], one centre
+extern "C" {
+void hc_similarity_modes_f64(long n, const double* pose, const double* c0, double* P) {
+  for (long i = 0; i < n; ++i) similarity_modes<double>(pose + 7 * i, c0, P + 42 * i);
+}
+void hc_similarity_modes_f32(long n, const float* pose, const double* c0, float* P) {
+  for (long i = 0; i < n; ++i) similarity_modes<float>(pose + 7 * i, c0, P + 42 * i);
+}
+}
+
