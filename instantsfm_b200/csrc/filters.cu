@@ -6,21 +6,14 @@
 //   per observation: image id 4 + track index 4 + bearing 24 read, 1 byte written; the 3x4 pose
 //   (96 B / image) and the point (24 B / track) come from L2.
 #include "common.cuh"
+#include "filter_math.cuh"
 
 namespace isfm {
 namespace {
 
-constexpr double FILTER_EPS = 1e-10;   // track_filter.py:3
 constexpr int FILTER_TPB = 256;
 
-__device__ __forceinline__ double dot3_nofma(double a0, double a1, double a2, double b0, double b1, double b2) {
-  return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
-}
-
-// MODE 0: FilterTracksByAngle (track_filter.py:5-24)
-//   pt = R X + t; reject if pt.z < EPS; pt /= ||pt||; keep iff dot(pt, f) > cos(max_angle)
-// MODE 1: FilterTracksByReprojectionNormalized (track_filter.py:26-66)
-//   pt = [R|t] [X;1]; valid = pt.z > EPS; e = || pt.xy/(pt.z+EPS) - f.xy/(f.z+EPS) ||; keep iff valid && e < thr
+// MODE 0 / 1: see filter_math.cuh::filter_keep
 template <int MODE>
 __global__ void __launch_bounds__(FILTER_TPB)
 filter_observations_kernel(int64_t n_obs, const double* __restrict__ world2cam, const double* __restrict__ xyz,
@@ -29,30 +22,7 @@ filter_observations_kernel(int64_t n_obs, const double* __restrict__ world2cam, 
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
     const double* __restrict__ M = world2cam + (size_t)image_ids[i] * 16;
     const double* __restrict__ X = xyz + (size_t)track_idx[i] * 3;
-    const double x = X[0], y = X[1], z = X[2];
-    const double f0 = feat[3 * i], f1 = feat[3 * i + 1], f2 = feat[3 * i + 2];
-    double p[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      // (R X) first, then + t: `R @ xyz + t` (:12) and einsum over [x, y, z, 1] (:50) agree on this order
-      p[r] = __dadd_rn(dot3_nofma(M[4 * r], M[4 * r + 1], M[4 * r + 2], x, y, z), M[4 * r + 3]);
-    }
-    bool keep;
-    if (MODE == 0) {
-      if (p[2] < FILTER_EPS) {
-        keep = false;
-      } else {
-        const double n = sqrt(dot3_nofma(p[0], p[1], p[2], p[0], p[1], p[2]));   // np.linalg.norm
-        keep = dot3_nofma(__ddiv_rn(p[0], n), __ddiv_rn(p[1], n), __ddiv_rn(p[2], n), f0, f1, f2) > thr;
-      }
-    } else {
-      const double pz = __dadd_rn(p[2], FILTER_EPS), fz = __dadd_rn(f2, FILTER_EPS);
-      const double d0 = __dadd_rn(__ddiv_rn(p[0], pz), -__ddiv_rn(f0, fz));
-      const double d1 = __dadd_rn(__ddiv_rn(p[1], pz), -__ddiv_rn(f1, fz));
-      const double e = sqrt(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)));
-      keep = (p[2] > FILTER_EPS) && (e < thr);
-    }
-    valid_out[i] = keep ? 1 : 0;
+    valid_out[i] = filter_keep<MODE>(M, X[0], X[1], X[2], feat[3 * i], feat[3 * i + 1], feat[3 * i + 2], thr) ? 1 : 0;
   }
 }
 

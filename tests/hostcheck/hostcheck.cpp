@@ -4,6 +4,7 @@
 // small SPD inverses -- against the oracle.  Never loaded by the product package.
 #include "../../instantsfm_b200/csrc/math.cuh"
 #include "../../instantsfm_b200/csrc/camera_maps.cuh"
+#include "../../instantsfm_b200/csrc/filter_math.cuh"
 
 using namespace isfm;
 
@@ -93,5 +94,18 @@ void hc_similarity_modes_f64(long n, const double* pose, const double* c0, doubl
 void hc_similarity_modes_f32(long n, const float* pose, const double* c0, float* P) {
   for (long i = 0; i < n; ++i) similarity_modes<float>(pose + 7 * i, c0, P + 42 * i);
 }
+}
+
+// per-observation track-filter tests (csrc/filter_math.cuh), the loop of filter_observations_kernel
+extern "C" int hc_filter_observations(int mode, long n_obs, const double* world2cam, const double* xyz, const double* feat,
+                                      const int* image_ids, const int* track_idx, double thr, unsigned char* valid_out) {
+  for (long i = 0; i < n_obs; ++i) {
+    const double* M = world2cam + (long)image_ids[i] * 16;
+    const double* X = xyz + (long)track_idx[i] * 3;
+    const bool k = mode == 0 ? filter_keep<0>(M, X[0], X[1], X[2], feat[3 * i], feat[3 * i + 1], feat[3 * i + 2], thr)
+                             : filter_keep<1>(M, X[0], X[1], X[2], feat[3 * i], feat[3 * i + 1], feat[3 * i + 2], thr);
+    valid_out[i] = k ? 1 : 0;
+  }
+  return 0;
 }
 

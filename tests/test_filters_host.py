@@ -219,3 +219,27 @@ def test_retriangulate_tracks_sequences_the_reference_loop(fake_lib):
     assert bopts['optimize_poses'] is True                      # caller's dict untouched (:248-249 copies it)
     assert images[2].is_registered is False and images[1].is_registered is True
     assert len(tracks) > 200 and sum(len(t.observations) for t in tracks.values()) > 1000
+
+
+class DeviceMathLib(FakeLib):
+    """isfm_filter_observations backed by the HOST BUILD of the kernel's own arithmetic
+    (csrc/filter_math.cuh through tests/hostcheck): the CPU suite then checks the device code of the
+    two per-observation filters bit for bit against the reference-generated golden vectors."""
+
+    def isfm_filter_observations(self, mode, n_obs, n_img, n_trk, w2c, xyz, feat, ids, tix, thr, out, stream):
+        from tests.hostcheck.build import load
+        p = ctypes.c_void_p
+        return load().hc_filter_observations(ctypes.c_int(mode), ctypes.c_long(n_obs), p(w2c), p(xyz), p(feat), p(ids), p(tix),
+                                             ctypes.c_double(thr), p(out))
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[1] != "FilterTracksTriangulationAngle"], ids=lambda c: c[0])
+def test_filter_device_math_on_host_matches_reference_golden(case, monkeypatch):
+    lib = DeviceMathLib()
+    monkeypatch.setattr(tf._lib, "load", lambda: lib)
+    name, fn, thr, kw = case
+    _, images, tracks = make_filter_scene(**kw)
+    tracks = copy.deepcopy(tracks)
+    with redirect_stdout(io.StringIO()):
+        ret = getattr(tf, fn)([], images, tracks, thr)
+    check_against_golden(name, tracks, -1 if fn == "FilterTracksByAngle" else ret)
